@@ -1,0 +1,161 @@
+/*
+ * medtok_vq.h -- C ABI of the B200-native MedTok vector quantizer (libmedtok_vq.so).
+ *
+ * The reference (mims-harvard/MedTok) is pure PyTorch: its quantizer has no plugin / FFI layer,
+ * the boundary is the nn.Module surface of MedTok/norm_ema_quantizer.py and
+ * MedTok/vector_quantization_soft_one_new.py.  This header is the C ABI a maintainer binds
+ * *underneath* those modules (see INTEGRATION.md for the ctypes stub); every entry point names
+ * the reference lines whose ATen ops it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; tensors are row-major,
+ *     contiguous, fp32 unless stated; code indices are int64 (torch.argmin / topk dtype)
+ *   - the caller owns every buffer, including the workspace; the library never allocates, frees or
+ *     retains device memory and keeps no global state beyond cached function attributes
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises the
+ *     host; calls are re-entrant for distinct (stream, workspace) pairs
+ *   - return value: 0 on success, a positive cudaError_t, or a negative MTVQ_ERR_* code;
+ *     mtvq_last_error() returns a thread-local message.  No C++ exception crosses the ABI.
+ *   - there is no CPU fallback and no alternate backend: sm_100a only.
+ */
+#ifndef MEDTOK_VQ_H
+#define MEDTOK_VQ_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MTVQ_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define MTVQ_API __attribute__((visibility("default")))
+#else
+#define MTVQ_API
+#endif
+
+#define MTVQ_ERR_BAD_ARG      (-1)  /* shape / alignment / null-pointer violation detected on the host */
+#define MTVQ_ERR_UNSUPPORTED  (-2)  /* e.g. D not a multiple of 16, D > 256, top-k > 8 */
+#define MTVQ_ERR_WORKSPACE    (-3)  /* workspace smaller than mtvq_workspace_bytes() */
+#define MTVQ_ERR_NO_DEVICE    (-4)  /* current device is not compute capability 10.x */
+
+/* l2norm reduction order (how the REFERENCE's torch CPU path sums the squares, DESIGN.md "canonical
+ * arithmetic"): unit-stride rows ([N,D,1,1] module inputs, codebooks) vs a channel-strided view
+ * (b c h w inputs with h*w > 1, normalised through rearrange's permuted view). */
+#define MTVQ_NORM_CONTIGUOUS 0
+#define MTVQ_NORM_STRIDED    1
+
+/* flags for mtvq_hard_forward */
+#define MTVQ_F_TRAINING        1u   /* module.training                          (norm_ema_quantizer.py:185,191) */
+#define MTVQ_F_UPDATE          2u   /* module.embedding.update                  (:191) */
+#define MTVQ_F_SKIP_FINALIZE   4u   /* multi-GPU: stop after the packed statistics; the caller all-reduces
+                                       `stats` and then calls mtvq_ema_finalize (replaces :188,195,203) */
+
+MTVQ_API int mtvq_abi_version(void);
+MTVQ_API const char * mtvq_last_error(void);
+
+/* Bytes of caller-provided scratch needed by the calls below for up to n rows, dim d, k codes
+ * (top-k `topk` for the soft path, 1 for the hard path). */
+MTVQ_API size_t mtvq_workspace_bytes(int64_t n, int d, int k, int topk);
+
+/* Number of doubles in the packed statistics buffer: [ bins(k) | embed_sum(k*d) | sse | rows ].
+ * This one buffer is what crosses NVLink (one all-reduce instead of the reference's two plus a
+ * rank-local loss, norm_ema_quantizer.py:195,203,212). */
+MTVQ_API size_t mtvq_stats_len(int d, int k);
+
+/* ---- hard path: NormEMAVectorQuantizer.forward (norm_ema_quantizer.py:166-218) ------------- */
+
+/* Whole training/eval forward of one rank's rows, stream-ordered:
+ *   z        [n,d]  raw rows (b h w c order); normalised inside           (:169-171, l2norm :8-9)
+ *   weight   [k,d]  codebook, updated IN PLACE when TRAINING|UPDATE       (:199-210, :136-138)
+ *   cluster_size [k] module buffer, updated IN PLACE                      (:189,197, ema_inplace :11-12)
+ *   z_q      [n,d]  out: zf + (w[idx] - zf), rows of the PRE-update codebook (:181,214)
+ *   idx      [n]    out: int64 first-index argmin of ||zf||^2 + ||w||^2 - 2 zf.w  (:175-179)
+ *   loss     [1]    out: beta * mean((z_q - zf)^2) over this call's rows   (:212)
+ *   stats    [mtvq_stats_len]  out (fp64): this rank's bins | embed_sum | sse | rows  (:187,194,202)
+ * With MTVQ_F_SKIP_FINALIZE the codebook / cluster_size are left untouched. */
+MTVQ_API int mtvq_hard_forward(const float *z, int64_t n, int d, int norm_mode,
+                      float *weight, int k, float *cluster_size,
+                      double beta, double decay, unsigned flags,
+                      float *z_q, int64_t *idx, float *loss, double *stats,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
+/* EMA step from (all-reduced) packed statistics: cluster_size <- decay*cs + (1-decay)*bins and,
+ * when update_weight, w_k <- l2norm(decay*w_k + (1-decay)*l2norm(embed_sum_k / bins_k)), rows with
+ * bins_k == 0 keeping w_k (:197-210).  Also (re)computes loss = beta * sse / (rows * d) from the
+ * packed totals when loss != NULL (global-batch loss; pass NULL to keep the rank-local one). */
+MTVQ_API int mtvq_ema_finalize(float *weight, float *cluster_size, const double *stats, int k, int d,
+                      double beta, double decay, int update_cluster_size, int update_weight,
+                      float *loss, void *stream);
+
+/* Pieces of the forward, exposed for tests, k-means and the lookup-only VectorQuantizer
+ * (norm_ema_quantizer.py:222-268). */
+
+/* idx[n] = first-index argmin_k d(zf_n, w_k); also writes denom[n] = max(||z_n||, 1e-12)
+ * (denom may be NULL).  Tensor-core coarse pass + exact fp32 re-scoring of every near-tie. */
+MTVQ_API int mtvq_hard_assign(const float *z, int64_t n, int d, int norm_mode, const float *weight, int k,
+                     int64_t *idx, float *denom, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Same result through the exact fp32 CUDA-core kernel only (reference order, no tensor cores);
+ * the slow cross-check used by tests and by the near-tie overflow fallback. */
+MTVQ_API int mtvq_hard_assign_exact(const float *z, int64_t n, int d, int norm_mode, const float *weight, int k,
+                           int64_t *idx, float *denom, void *workspace, size_t workspace_bytes, void *stream);
+
+/* z_q = zf + (w[idx] - zf), sse += sum (w[idx]-zf)^2 (fp64), bins[idx] += 1 (F.embedding :117-118,
+ * one_hot/sum :183-194 without the N x K one-hot).  denom as written by mtvq_hard_assign. */
+MTVQ_API int mtvq_gather_ste(const float *z, const float *denom, const float *weight, const int64_t *idx,
+                    int64_t n, int d, int k, float *z_q, double *stats, void *stream);
+
+/* embed_sum[k,d] += sum_{n: idx_n = k} zf_n  (replaces the second N x K GEMM, :202): counting sort of
+ * the rows by code + fp64 segmented sums.  Needs bins in `stats` (mtvq_gather_ste). */
+MTVQ_API int mtvq_code_sums(const float *z, const float *denom, const int64_t *idx, int64_t n, int d, int k,
+                   double *stats, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- soft path: VectorQuantizer.specific_embedding / shared core
+ *      (vector_quantization_soft_one_new.py:120-125,147-185,187-217) ------------------------- */
+
+/* One soft quantisation of n projected rows x [n,d] against `k` RAW codebook rows `codes`
+ * (the active slice; normalised inside, :148,198-200):
+ *   idx [n,topk] int64 ascending-distance code indices (slice-relative)        (:157,159,203)
+ *   vals[n,topk] the distances, wts[n,topk] = softmax(-vals)                    (:158,160,204)
+ *   zq  [n,d]    sum_j wts_j * cn[idx_j]                                        (:164-165,205)
+ *   out [n,d]    x + (zq - x)                                                   (:181-182,214)
+ *   sse [1] fp64 += sum (zq - x)^2  (vq_loss = sse/(n d), commit = beta*vq_loss, :169-173,208-209) */
+MTVQ_API int mtvq_soft_forward(const float *x, int64_t n, int d, const float *codes, int k, int topk,
+                      int64_t *idx, float *vals, float *wts, float *zq, float *out, double *sse,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
+/* Backward of mtvq_soft_forward w.r.t. x and the raw codebook rows (autograd of :196-214, maths in
+ * DESIGN.md): g_zq is dL/dzq [n,d] (from the vq loss and anything else consuming zq); writes
+ * grad_x [n,d] (through the softmax weights and normalize) and ACCUMULATES grad_codes [k,d]. */
+MTVQ_API int mtvq_soft_backward(const float *x, int64_t n, int d, const float *codes, int k, int topk,
+                       const int64_t *idx, const float *wts, const float *g_zq,
+                       float *grad_x, float *grad_codes, void *workspace, size_t workspace_bytes,
+                       void *stream);
+
+/* ---- diagnostics (not part of the drop-in surface) ---------------------------------------- */
+
+/* counters of the last assignment run on this workspace (same n, d, k, topk as that call), copied to
+ * HOST after a stream sync: out_host[0] = rows sent to exact re-scoring (near-ties), [1] = rows that
+ * overflowed the candidate list and took the full exact scan, [2] = candidates re-scored in total,
+ * [3] = kernels/memsets this thread enqueued since the previous call of this function. */
+MTVQ_API int mtvq_debug_counters(const void *workspace, int64_t n, int d, int k, int topk, int64_t *out_host,
+                        void *stream);
+
+/* raw tensor-core scores of the first `rows` rows against all codes, [rows, kpad] fp32
+ * (coarse score = zf.w - ||w||^2/2 from fp16 operands); used by tests to validate the MMA path. */
+MTVQ_API int mtvq_debug_coarse_scores(const float *z, int64_t n, int d, int norm_mode, const float *weight, int k,
+                             float *scores, int64_t rows, int *kpad_host,
+                             void *workspace, size_t workspace_bytes, void *stream);
+
+/* micro-benchmarks used to size the epilogue (DESIGN.md "measured machine limits"):
+ * which = 0: tcgen05.ld throughput, 1: FMNMX3 tree throughput; result_host[0] = device ms,
+ * result_host[1] = bytes or ops processed. */
+MTVQ_API int mtvq_microbench(int which, int warps, int iters, double *result_host, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEDTOK_VQ_H */

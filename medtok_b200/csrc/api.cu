@@ -1,0 +1,327 @@
+// api.cu -- extern "C" surface of libmedtok_vq.so (declared in include/medtok_vq.h).
+// Host-side argument checks, workspace carving and kernel sequencing only; no device allocation,
+// no host synchronisation (diagnostic entry points excepted), no exceptions across the ABI.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/medtok_vq.h"
+#include "assign_exact.h"
+#include "assign_tc.h"
+#include "microbench.h"
+#include "rows.h"
+#include "soft.h"
+#include "workspace.h"
+
+using namespace mtvq;
+
+namespace {
+
+thread_local char g_err[512] = "";
+thread_local long g_launches = 0;
+
+int fail(int code, const char* fmt, const char* a = "", long b = 0, long c = 0) {
+    snprintf(g_err, sizeof(g_err), fmt, a, b, c);
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* where) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+    return (int)e;
+}
+#define MTVQ_CUDA(call, where)                                 \
+    do {                                                       \
+        cudaError_t e__ = (call);                              \
+        ++g_launches;                                          \
+        if (e__ != cudaSuccess) return cuda_fail(e__, where);  \
+    } while (0)
+
+struct DeviceInfo {
+    int device = -1;
+    int num_sms = 0;
+    int major = 0;
+};
+int device_info(DeviceInfo* out) {
+    static DeviceInfo cache[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    if (dev < 0 || dev >= 64) return fail(MTVQ_ERR_NO_DEVICE, "device ordinal out of range%s", "");
+    if (cache[dev].device != dev) {
+        cudaDeviceProp p;
+        e = cudaGetDeviceProperties(&p, dev);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
+        cache[dev].device = dev;
+        cache[dev].num_sms = p.multiProcessorCount;
+        cache[dev].major = p.major;
+    }
+    if (cache[dev].major != 10)
+        return fail(MTVQ_ERR_NO_DEVICE, "libmedtok_vq is sm_100a-only; device has compute capability %s%ld.x", "",
+                    (long)cache[dev].major);
+    *out = cache[dev];
+    return 0;
+}
+
+int check_dims(int64_t n, int d, int k) {
+    if (n < 0 || k <= 0 || d <= 0) return fail(MTVQ_ERR_BAD_ARG, "bad extents%s n=%ld k=%ld", "", (long)n, (long)k);
+    if (d % 16 != 0 || d > kMaxDim)
+        return fail(MTVQ_ERR_UNSUPPORTED, "embedding dim must be a multiple of 16 and <= 256%s (got %ld)", "", (long)d);
+    if (n > 0x7fffffffLL) return fail(MTVQ_ERR_UNSUPPORTED, "more than 2^31-1 rows per call%s", "");
+    return 0;
+}
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+bool desc_swap() {
+    static int v = -1;
+    if (v < 0) { const char* s = getenv("MTVQ_DESC_SWAP"); v = (s && s[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
+void fill_coarse(CoarseParams& p, const float* z, int64_t n, int d, int norm_mode, int k, const Workspace& ws,
+                 float* denom, int topk) {
+    memset(&p, 0, sizeof(p));
+    p.z = z; p.n = n; p.d = d; p.norm_mode = norm_mode;
+    p.b_image = ws.b_image; p.kpad = pad_codes(k); p.k = k; p.meta = ws.meta;
+    p.denom = denom; p.best_col = ws.best_col; p.best_val = ws.best_val;
+    p.flag_rows = ws.flag_rows; p.counters = ws.counters;
+    p.cand = ws.cand; p.cand_cnt = ws.cand_cnt; p.cand_cap = cand_capacity(topk); p.topk = topk;
+    p.lbo_bytes = desc_swap() ? 128 : 2048;
+    p.sbo_bytes = desc_swap() ? 2048 : 128;
+}
+
+// hard assignment into ws.best_col (+ denom); `codes` are the rows the distances are taken against
+int assign_into_ws(const float* z, int64_t n, int d, int norm_mode, const float* codes, int k, float* denom,
+                   const Workspace& ws, const DeviceInfo& di, bool exact_only, cudaStream_t st) {
+    MTVQ_CUDA(cudaMemsetAsync(ws.counters, 0, sizeof(int) * CNT_COUNT, st), "memset counters");
+    MTVQ_CUDA(launch_codebook_prep(codes, k, d, 0, ws, st), "codebook_prep");
+    if (n == 0) return 0;
+    if (exact_only) {
+        MTVQ_CUDA(launch_exact_scan(z, n, d, norm_mode, codes, k, ws.cc, nullptr, nullptr, ws.best_col, denom,
+                                    di.num_sms, st), "exact_scan");
+        return 0;
+    }
+    MTVQ_CUDA(cudaMemsetAsync(ws.cand_cnt, 0, sizeof(int) * n, st), "memset cand_cnt");
+    CoarseParams p;
+    fill_coarse(p, z, n, d, norm_mode, k, ws, denom, 1);
+    MTVQ_CUDA(launch_coarse(p, MODE_ARGMAX, coarse_row_tiles(d, n, di.num_sms), di.num_sms, st), "coarse argmax");
+    // near-tie rows: collect every code within the margin, then decide in exact fp32
+    CoarseParams c = p;
+    c.row_list = ws.flag_rows;
+    c.n_rows_dev = ws.counters + CNT_FLAGGED;
+    c.denom = nullptr;
+    MTVQ_CUDA(launch_coarse(c, MODE_COLLECT, 1, di.num_sms, st), "coarse collect");
+    MTVQ_CUDA(launch_resolve(z, d, norm_mode, codes, k, ws, p.cand_cap, di.num_sms, st), "resolve");
+    MTVQ_CUDA(launch_exact_scan(z, n, d, norm_mode, codes, k, ws.cc, ws.full_rows, ws.counters + CNT_FULL, ws.best_col,
+                                nullptr, di.num_sms, st), "exact_scan(overflow)");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mtvq_abi_version(void) { return MTVQ_ABI_VERSION; }
+const char* mtvq_last_error(void) { return g_err; }
+
+size_t mtvq_workspace_bytes(int64_t n, int d, int k, int topk) {
+    if (n < 0 || d <= 0 || k <= 0) return 0;
+    return carve(nullptr, n, d, k, topk < 1 ? 1 : topk).total_bytes;
+}
+size_t mtvq_stats_len(int d, int k) { return (size_t)k + (size_t)k * d + 2; }
+
+static int hard_assign_impl(const float* z, int64_t n, int d, int norm_mode, const float* weight, int k, int64_t* idx,
+                            float* denom, void* workspace, size_t workspace_bytes, void* stream, bool exact_only) {
+    if (int r = check_dims(n, d, k)) return r;
+    if (!z || !weight || !idx || !workspace) return fail(MTVQ_ERR_BAD_ARG, "null pointer%s", "");
+    if (!aligned16(z) || !aligned16(weight) || !aligned16(workspace))
+        return fail(MTVQ_ERR_BAD_ARG, "z, weight and workspace must be 16-byte aligned%s", "");
+    DeviceInfo di;
+    if (int r = device_info(&di)) return r;
+    Workspace ws = carve(workspace, n, d, k, 1);
+    if (ws.total_bytes > workspace_bytes)
+        return fail(MTVQ_ERR_WORKSPACE, "workspace too small%s: need %ld, got %ld", "", (long)ws.total_bytes,
+                    (long)workspace_bytes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* den = denom ? denom : ws.denom;
+    if (int r = assign_into_ws(z, n, d, norm_mode, weight, k, den, ws, di, exact_only, st)) return r;
+    if (n > 0) MTVQ_CUDA(launch_emit_idx(ws.best_col, n, idx, di.num_sms, st), "emit_idx");
+    return 0;
+}
+
+int mtvq_hard_assign(const float* z, int64_t n, int d, int norm_mode, const float* weight, int k, int64_t* idx,
+                     float* denom, void* workspace, size_t workspace_bytes, void* stream) {
+    return hard_assign_impl(z, n, d, norm_mode, weight, k, idx, denom, workspace, workspace_bytes, stream, false);
+}
+int mtvq_hard_assign_exact(const float* z, int64_t n, int d, int norm_mode, const float* weight, int k, int64_t* idx,
+                           float* denom, void* workspace, size_t workspace_bytes, void* stream) {
+    return hard_assign_impl(z, n, d, norm_mode, weight, k, idx, denom, workspace, workspace_bytes, stream, true);
+}
+
+int mtvq_gather_ste(const float* z, const float* denom, const float* weight, const int64_t* idx, int64_t n, int d,
+                    int k, float* z_q, double* stats, void* stream) {
+    if (int r = check_dims(n, d, k)) return r;
+    if (!z || !denom || !weight || !idx || !z_q || !stats) return fail(MTVQ_ERR_BAD_ARG, "null pointer%s", "");
+    if (!aligned16(z) || !aligned16(weight) || !aligned16(z_q)) return fail(MTVQ_ERR_BAD_ARG, "16-byte alignment%s", "");
+    DeviceInfo di;
+    if (int r = device_info(&di)) return r;
+    if (n > 0)
+        MTVQ_CUDA(launch_gather_ste(z, denom, weight, idx, n, d, k, z_q, stats, di.num_sms, static_cast<cudaStream_t>(stream)),
+                  "gather_ste");
+    return 0;
+}
+
+int mtvq_code_sums(const float* z, const float* denom, const int64_t* idx, int64_t n, int d, int k, double* stats,
+                   void* workspace, size_t workspace_bytes, void* stream) {
+    if (int r = check_dims(n, d, k)) return r;
+    if (!z || !denom || !idx || !stats || !workspace) return fail(MTVQ_ERR_BAD_ARG, "null pointer%s", "");
+    DeviceInfo di;
+    if (int r = device_info(&di)) return r;
+    Workspace ws = carve(workspace, n, d, k, 1);
+    if (ws.total_bytes > workspace_bytes) return fail(MTVQ_ERR_WORKSPACE, "workspace too small%s", "");
+    if (n > 0)
+        MTVQ_CUDA(launch_code_sums(z, denom, idx, n, d, k, stats, ws, di.num_sms, static_cast<cudaStream_t>(stream)),
+                  "code_sums");
+    return 0;
+}
+
+int mtvq_ema_finalize(float* weight, float* cluster_size, const double* stats, int k, int d, double beta, double decay,
+                      int update_cluster_size, int update_weight, float* loss, void* stream) {
+    if (int r = check_dims(0, d, k)) return r;
+    if (!stats || (update_weight && !weight) || (update_cluster_size && !cluster_size))
+        return fail(MTVQ_ERR_BAD_ARG, "null pointer%s", "");
+    DeviceInfo di;
+    if (int r = device_info(&di)) return r;
+    MTVQ_CUDA(launch_ema_finalize(weight, cluster_size, stats, k, d, beta, decay, update_cluster_size, update_weight, loss,
+                                  static_cast<cudaStream_t>(stream)), "ema_finalize");
+    return 0;
+}
+
+int mtvq_hard_forward(const float* z, int64_t n, int d, int norm_mode, float* weight, int k, float* cluster_size,
+                      double beta, double decay, unsigned flags, float* z_q, int64_t* idx, float* loss, double* stats,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+    if (int r = check_dims(n, d, k)) return r;
+    if (!z || !weight || !z_q || !idx || !loss || !stats || !workspace) return fail(MTVQ_ERR_BAD_ARG, "null pointer%s", "");
+    if (!aligned16(z) || !aligned16(weight) || !aligned16(z_q) || !aligned16(workspace))
+        return fail(MTVQ_ERR_BAD_ARG, "z, weight, z_q and workspace must be 16-byte aligned%s", "");
+    DeviceInfo di;
+    if (int r = device_info(&di)) return r;
+    Workspace ws = carve(workspace, n, d, k, 1);
+    if (ws.total_bytes > workspace_bytes)
+        return fail(MTVQ_ERR_WORKSPACE, "workspace too small%s: need %ld, got %ld", "", (long)ws.total_bytes,
+                    (long)workspace_bytes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool training = flags & MTVQ_F_TRAINING, update = flags & MTVQ_F_UPDATE;
+    const bool upd_w = training && update;            // norm_ema_quantizer.py:191
+    const bool upd_cs = (!training) || update;        // :185 / :191 are the only branches touching cluster_size
+    if (upd_cs && !cluster_size && !(flags & MTVQ_F_SKIP_FINALIZE))
+        return fail(MTVQ_ERR_BAD_ARG, "cluster_size is null%s", "");
+
+    MTVQ_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * mtvq_stats_len(d, k), st), "memset stats");
+    if (int r = assign_into_ws(z, n, d, norm_mode, weight, k, ws.denom, ws, di, false, st)) return r;
+    if (n > 0) {
+        MTVQ_CUDA(launch_emit_idx(ws.best_col, n, idx, di.num_sms, st), "emit_idx");
+        MTVQ_CUDA(launch_gather_ste(z, ws.denom, weight, idx, n, d, k, z_q, stats, di.num_sms, st), "gather_ste");
+        if (upd_w) MTVQ_CUDA(launch_code_sums(z, ws.denom, idx, n, d, k, stats, ws, di.num_sms, st), "code_sums");
+    }
+    if (flags & MTVQ_F_SKIP_FINALIZE) {
+        MTVQ_CUDA(launch_loss(stats, k, d, beta, loss, st), "loss");
+    } else {
+        MTVQ_CUDA(launch_ema_finalize(weight, cluster_size, stats, k, d, beta, decay, upd_cs, upd_w, loss, st),
+                  "ema_finalize");
+    }
+    return 0;
+}
+
+int mtvq_soft_forward(const float* x, int64_t n, int d, const float* codes, int k, int topk, int64_t* idx, float* vals,
+                      float* wts, float* zq, float* out, double* sse, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+    if (int r = check_dims(n, d, k)) return r;
+    if (topk < 1 || topk > 8 || topk > k) return fail(MTVQ_ERR_UNSUPPORTED, "top-k must be in [1, min(8, k)]%s", "");
+    if (!x || !codes || !idx || !vals || !wts || !zq || !out || !sse || !workspace)
+        return fail(MTVQ_ERR_BAD_ARG, "null pointer%s", "");
+    if (!aligned16(x) || !aligned16(codes) || !aligned16(zq) || !aligned16(out) || !aligned16(workspace))
+        return fail(MTVQ_ERR_BAD_ARG, "16-byte alignment%s", "");
+    DeviceInfo di;
+    if (int r = device_info(&di)) return r;
+    Workspace ws = carve(workspace, n, d, k, topk);
+    if (ws.total_bytes > workspace_bytes) return fail(MTVQ_ERR_WORKSPACE, "workspace too small%s", "");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MTVQ_CUDA(cudaMemsetAsync(ws.counters, 0, sizeof(int) * CNT_COUNT, st), "memset counters");
+    MTVQ_CUDA(launch_codebook_prep(codes, k, d, 1, ws, st), "codebook_prep(normalise)");
+    if (n == 0) return 0;
+    MTVQ_CUDA(cudaMemsetAsync(ws.cand_cnt, 0, sizeof(int) * n, st), "memset cand_cnt");
+    CoarseParams p;
+    fill_coarse(p, x, n, d, MTVQ_NORM_CONTIGUOUS, k, ws, ws.denom, topk);
+    const int rt = coarse_row_tiles(d, n, di.num_sms);
+    MTVQ_CUDA(launch_coarse(p, MODE_THRESH, rt, di.num_sms, st), "coarse thresh");
+    CoarseParams c = p;
+    c.denom = nullptr;
+    MTVQ_CUDA(launch_coarse(c, MODE_COLLECT, rt, di.num_sms, st), "coarse collect");
+    MTVQ_CUDA(launch_soft_resolve(x, n, d, k, topk, ws, idx, vals, wts, zq, out, sse, di.num_sms, st), "soft_resolve");
+    return 0;
+}
+
+int mtvq_soft_backward(const float* x, int64_t n, int d, const float* codes, int k, int topk, const int64_t* idx,
+                       const float* wts, const float* g_zq, float* grad_x, float* grad_codes, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+    if (int r = check_dims(n, d, k)) return r;
+    if (topk < 1 || topk > 8) return fail(MTVQ_ERR_UNSUPPORTED, "top-k must be in [1, 8]%s", "");
+    if (!x || !codes || !idx || !wts || !g_zq || !grad_x || !grad_codes) return fail(MTVQ_ERR_BAD_ARG, "null pointer%s", "");
+    DeviceInfo di;
+    if (int r = device_info(&di)) return r;
+    (void)workspace; (void)workspace_bytes;
+    if (n > 0)
+        MTVQ_CUDA(launch_soft_backward(x, n, d, codes, k, topk, idx, wts, g_zq, grad_x, grad_codes, di.num_sms,
+                                       static_cast<cudaStream_t>(stream)), "soft_backward");
+    return 0;
+}
+
+int mtvq_debug_counters(const void* workspace, int64_t n, int d, int k, int topk, int64_t* out_host, void* stream) {
+    if (!workspace || !out_host) return fail(MTVQ_ERR_BAD_ARG, "null pointer%s", "");
+    Workspace ws = carve(const_cast<void*>(workspace), n, d, k, topk < 1 ? 1 : topk);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int h[CNT_COUNT] = {0};
+    cudaError_t e = cudaMemcpyAsync(h, ws.counters, sizeof(h), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return cuda_fail(e, "memcpy counters");
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(e, "sync");
+    out_host[0] = h[CNT_FLAGGED];
+    out_host[1] = h[CNT_FULL];
+    out_host[2] = h[CNT_CANDS];
+    out_host[3] = g_launches;
+    g_launches = 0;
+    return 0;
+}
+
+int mtvq_debug_coarse_scores(const float* z, int64_t n, int d, int norm_mode, const float* weight, int k, float* scores,
+                             int64_t rows, int* kpad_host, void* workspace, size_t workspace_bytes, void* stream) {
+    if (int r = check_dims(n, d, k)) return r;
+    DeviceInfo di;
+    if (int r = device_info(&di)) return r;
+    Workspace ws = carve(workspace, n, d, k, 1);
+    if (ws.total_bytes > workspace_bytes) return fail(MTVQ_ERR_WORKSPACE, "workspace too small%s", "");
+    if (kpad_host) *kpad_host = pad_codes(k);
+    if (!scores) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MTVQ_CUDA(cudaMemsetAsync(ws.counters, 0, sizeof(int) * CNT_COUNT, st), "memset counters");
+    MTVQ_CUDA(launch_codebook_prep(weight, k, d, 0, ws, st), "codebook_prep");
+    CoarseParams p;
+    fill_coarse(p, z, n, d, norm_mode, k, ws, ws.denom, 1);
+    p.dump = scores;
+    p.dump_rows = rows < n ? rows : n;
+    const char* rt_env = getenv("MTVQ_DEBUG_ROW_TILES");
+    int rt = rt_env ? atoi(rt_env) : coarse_row_tiles(d, n, di.num_sms);
+    if (rt != 1 && rt != 2 && rt != 4) rt = 1;
+    if (rt * d > 256) rt = 256 / d;
+    MTVQ_CUDA(launch_coarse(p, MODE_DUMP, rt, di.num_sms, st), "coarse dump");
+    return 0;
+}
+
+int mtvq_microbench(int which, int warps, int iters, double* result_host, void* stream) {
+    DeviceInfo di;
+    if (int r = device_info(&di)) return r;
+    MTVQ_CUDA(run_microbench(which, warps, iters, di.num_sms, result_host, static_cast<cudaStream_t>(stream)), "microbench");
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,25 @@
+// assign_exact.h -- launchers of the exact (reference-order fp32) assignment kernels
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "workspace.h"
+
+namespace mtvq {
+
+// fp32 codebook [k,d] -> ws.b_image (fp16 operand tiles + bias planes), ws.cc, ws.meta (margin);
+// normalize != 0 (soft path): rows are l2-normalised first and also written to ws.codes_n
+cudaError_t launch_codebook_prep(const float* w, int k, int d, int normalize, const Workspace& ws,
+                                 cudaStream_t stream);
+
+// near-tie rows (ws.flag_rows / counters[CNT_FLAGGED]) x their collected candidates -> ws.best_col;
+// rows whose candidate list is empty or overflowed go to ws.full_rows / counters[CNT_FULL]
+cudaError_t launch_resolve(const float* z, int d, int norm_mode, const float* w, int k, const Workspace& ws,
+                           int cand_cap, int num_sms, cudaStream_t stream);
+
+// exact first-index argmin over ALL k codes for the rows in row_list (or rows [0,n) when null)
+cudaError_t launch_exact_scan(const float* z, int64_t n, int d, int norm_mode, const float* w, int k,
+                              const float* cc, const int* row_list, const int* n_rows_dev, int* best_col,
+                              float* denom_out, int num_sms, cudaStream_t stream);
+
+}  // namespace mtvq

@@ -1,0 +1,47 @@
+// assign_tc.h -- parameters / launcher of the tcgen05 coarse-score kernel (assign_tc.cu)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "workspace.h"
+
+namespace mtvq {
+
+enum CoarseMode { MODE_ARGMAX = 0, MODE_THRESH = 1, MODE_COLLECT = 2, MODE_DUMP = 3 };
+
+struct CoarseParams {
+    // rows
+    const float* z;          // [*, d] raw rows (normalised by the A loader)
+    int64_t      n;          // rows to process when n_rows_dev == nullptr
+    int          d;
+    int          norm_mode;  // MTVQ_NORM_*
+    const int*   row_list;   // optional gather list (COLLECT over near-tie rows)
+    const int*   n_rows_dev; // optional device-side row count (length of row_list)
+    // codebook (prepared by codebook_prep_kernel)
+    const void*  b_image;
+    int          kpad;       // codes padded to a multiple of 128
+    int          k;
+    const float* meta;       // META_MARGIN ...
+    // outputs / state
+    float*       denom;      // [n] or nullptr
+    int*         best_col;   // [n]
+    float*       best_val;   // [n]
+    int*         flag_rows;  // [n]
+    int*         counters;   // [CNT_COUNT]
+    int*         cand;       // [rows * cand_cap]   indexed by position in row_list
+    int*         cand_cnt;   // [rows]
+    int          cand_cap;
+    int          topk;
+    float*       dump;       // DUMP: [dump_rows, kpad]
+    int64_t      dump_rows;
+    // shared-memory descriptor strides (kept as parameters so tests can probe the encoding)
+    uint32_t     lbo_bytes;  // 2048
+    uint32_t     sbo_bytes;  // 128
+};
+
+// rows per CTA block = 128 * row_tiles; bounded by shared memory (row_tiles * d <= 256)
+int         coarse_row_tiles(int d, int64_t nrows, int num_sms);
+cudaError_t launch_coarse(const CoarseParams& p, int mode, int row_tiles, int num_sms, cudaStream_t stream);
+int         coarse_smem_bytes();
+
+}  // namespace mtvq

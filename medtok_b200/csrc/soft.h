@@ -1,0 +1,17 @@
+// soft.h -- launchers of the soft-one (top-k) row kernels (soft.cu)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "workspace.h"
+
+namespace mtvq {
+
+cudaError_t launch_soft_resolve(const float* x, int64_t n, int d, int k, int topk, const Workspace& ws, int64_t* idx,
+                                float* vals, float* wts, float* zq, float* out, double* sse, int num_sms,
+                                cudaStream_t stream);
+cudaError_t launch_soft_backward(const float* x, int64_t n, int d, const float* codes, int k, int topk,
+                                 const int64_t* idx, const float* wts, const float* g_zq, float* grad_x,
+                                 float* grad_codes, int num_sms, cudaStream_t stream);
+
+}  // namespace mtvq

@@ -1,0 +1,75 @@
+// workspace.h -- host-side carving of the caller-provided scratch blob (the library never allocates).
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+namespace mtvq {
+
+constexpr int kMaxDim = 256;   // D must be a multiple of 16 and <= kMaxDim
+
+// meta block written by the codebook prep kernel (floats)
+enum MetaSlot { META_MARGIN = 0, META_EPS = 1, META_MAXNORM = 2, META_COUNT = 8 };
+// counters (ints), zeroed at the start of every assign
+enum Counter { CNT_FLAGGED = 0, CNT_FULL = 1, CNT_CANDS = 2, CNT_LAUNCHES = 3, CNT_COUNT = 8 };
+
+struct Workspace {
+    // codebook side
+    void*    b_image;      // fp16 operand image, kpad/128 tiles x (d/8+2) planes x 128 rows x 16 B
+    float*   cc;           // [kpad]  canonical ||w_k||^2
+    float*   codes_n;      // [k,d]   normalised codebook rows (soft path only)
+    float*   meta;         // [META_COUNT]
+    // row side
+    float*   denom;        // [n]
+    int*     best_col;     // [n]   winning code, -1 while unresolved
+    float*   best_val;     // [n]   best coarse score
+    int*     flag_rows;    // [n]   rows needing exact re-scoring
+    int*     cand;         // [n * kCandMax]  (soft: [n * cand_cap])
+    int*     cand_cnt;     // [n]
+    int*     full_rows;    // [n]
+    int*     counters;     // [CNT_COUNT]
+    // statistics side
+    int*     bins_i32;     // [k]
+    int*     offsets;      // [k+1]
+    int*     cursor;       // [k]
+    int*     perm;         // [n]
+    size_t   total_bytes;
+};
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline int    pad_codes(int k) { return (int)align_up((size_t)k, 128); }
+// near-tie candidates kept per row before the row falls back to the full exact scan
+inline int    cand_capacity(int topk) { return topk > 1 ? 24 : 16; }
+inline size_t image_bytes(int d, int k) { return (size_t)(pad_codes(k) / 128) * (size_t)(d / 8 + 2) * 2048; }
+
+inline Workspace carve(void* base, int64_t n, int d, int k, int topk) {
+    Workspace w{};
+    size_t off = 0;
+    char*  p   = static_cast<char*>(base);
+    auto take  = [&](size_t bytes) {
+        void* r = p ? p + off : nullptr;
+        off += align_up(bytes, 256);
+        return r;
+    };
+    const int    kpad     = pad_codes(k);
+    const size_t cand_cap = (size_t)cand_capacity(topk);
+    w.b_image   = take(image_bytes(d, k));
+    w.cc        = (float*)take(sizeof(float) * kpad);
+    w.codes_n   = (float*)take(topk > 1 ? sizeof(float) * (size_t)k * d : 0);
+    w.meta      = (float*)take(sizeof(float) * META_COUNT);
+    w.denom     = (float*)take(sizeof(float) * n);
+    w.best_col  = (int*)take(sizeof(int) * n);
+    w.best_val  = (float*)take(sizeof(float) * n);
+    w.flag_rows = (int*)take(sizeof(int) * n);
+    w.cand      = (int*)take(sizeof(int) * n * cand_cap);
+    w.cand_cnt  = (int*)take(sizeof(int) * n);
+    w.full_rows = (int*)take(sizeof(int) * n);
+    w.counters  = (int*)take(sizeof(int) * CNT_COUNT);
+    w.bins_i32  = (int*)take(sizeof(int) * k);
+    w.offsets   = (int*)take(sizeof(int) * (k + 1));
+    w.cursor    = (int*)take(sizeof(int) * k);
+    w.perm      = (int*)take(sizeof(int) * n);
+    w.total_bytes = off;
+    return w;
+}
+
+}  // namespace mtvq

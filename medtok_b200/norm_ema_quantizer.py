@@ -1,0 +1,301 @@
+"""B200-native drop-in for MedTok/norm_ema_quantizer.py (hard nearest-code quantizer, norm-EMA codebook).
+
+Same public names, constructor signatures, forward contract and state_dict keys as the reference
+(`/root/reference/MedTok/norm_ema_quantizer.py`), so `tokenizer.py` / `train_MedTok.py` /
+`inference.py` can import this module instead.  All tensor work of the forward + EMA update runs in
+libmedtok_vq.so (hand-written sm_100a CUDA, include/medtok_vq.h); this file is host-side glue:
+layout handling, buffer ownership, the torch.distributed exchange and autograd wiring.
+There is no CPU / PyTorch fallback: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as distributed
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+
+
+def l2norm(t):
+    """reference :8-9"""
+    return F.normalize(t, p=2, dim=-1)
+
+
+def ema_inplace(moving_avg, new, decay):
+    """reference :11-12"""
+    moving_avg.data.mul_(decay).add_(new, alpha=(1 - decay))
+
+
+def norm_ema_inplace(moving_avg, new, decay):
+    """reference :136-138"""
+    moving_avg.data.mul_(decay).add_(new, alpha=(1 - decay))
+    moving_avg.data.copy_(l2norm(moving_avg.data))
+
+
+def _rows_f32(t: torch.Tensor) -> torch.Tensor:
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()          # cast policy: fp16/bf16 inputs (autocast) are widened, all maths is fp32
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# thin functional layer over the C ABI (used by the modules, k-means and the tests)
+# ------------------------------------------------------------------------------------------------
+def hard_assign(z_rows: torch.Tensor, weight: torch.Tensor, norm_mode: int = _lib.NORM_CONTIGUOUS,
+                workspace: _lib.Workspace | None = None, exact: bool = False):
+    """idx[n] = first-index argmin_k ||zf_n - w_k||^2-style distance of reference :175-179.
+    Returns (idx int64 [n], denom fp32 [n])."""
+    _lib.require_cuda(z_rows, "z")
+    z_rows, weight = _rows_f32(z_rows), _rows_f32(weight)
+    n, d = z_rows.shape
+    k = weight.shape[0]
+    ws = (workspace or _lib.Workspace()).get(n, d, k, 1, z_rows.device)
+    idx = torch.empty(n, dtype=torch.int64, device=z_rows.device)
+    denom = torch.empty(n, dtype=torch.float32, device=z_rows.device)
+    fn = _lib.lib().mtvq_hard_assign_exact if exact else _lib.lib().mtvq_hard_assign
+    _lib.check(fn(_lib.ptr(z_rows), n, d, norm_mode, _lib.ptr(weight), k, _lib.ptr(idx), _lib.ptr(denom),
+                  _lib.ptr(ws), ws.numel(), _lib.stream_ptr(z_rows.device)), "mtvq_hard_assign")
+    return idx, denom
+
+
+def code_statistics(z_rows, denom, weight, idx, want_sums=True, workspace: _lib.Workspace | None = None):
+    """Packed fp64 statistics [bins(k) | embed_sum(k*d) | sse | rows] and z_q for given indices
+    (reference :181-202 without the one-hot)."""
+    z_rows, weight = _rows_f32(z_rows), _rows_f32(weight)
+    n, d = z_rows.shape
+    k = weight.shape[0]
+    dev = z_rows.device
+    ws = (workspace or _lib.Workspace()).get(n, d, k, 1, dev)
+    stats = torch.zeros(_lib.stats_len(d, k), dtype=torch.float64, device=dev)
+    z_q = torch.empty_like(z_rows)
+    L = _lib.lib()
+    _lib.check(L.mtvq_gather_ste(_lib.ptr(z_rows), _lib.ptr(denom), _lib.ptr(weight), _lib.ptr(idx), n, d, k,
+                                 _lib.ptr(z_q), _lib.ptr(stats), _lib.stream_ptr(dev)), "mtvq_gather_ste")
+    if want_sums:
+        _lib.check(L.mtvq_code_sums(_lib.ptr(z_rows), _lib.ptr(denom), _lib.ptr(idx), n, d, k, _lib.ptr(stats),
+                                    _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "mtvq_code_sums")
+    return z_q, stats
+
+
+def sample_vectors(samples, num):
+    """reference :14-22"""
+    num_samples, device = samples.shape[0], samples.device
+    if num_samples >= num:
+        indices = torch.randperm(num_samples, device=device)[:num]
+    else:
+        indices = torch.randint(0, num_samples, (num,), device=device)
+    return samples[indices]
+
+
+def kmeans(samples, num_clusters, num_iters=10, use_cosine_sim=False, means=None, verbose=True):
+    """reference :24-57 (cosine branch on the CUDA assign/statistics kernels).  `samples` are the
+    l2-normalised rows the quantizer feeds in (:173); argmax of samples @ means.t() is taken as the
+    nearest code of the same kernel that serves the forward (means are unit rows, so the two agree
+    outside fp32 near-ties).  Returns (means, bins)."""
+    if not use_cosine_sim:
+        raise NotImplementedError("only the cosine-similarity branch is used by MedTok (:90)")
+    _lib.require_cuda(samples, "samples")
+    samples = _rows_f32(samples)
+    if means is None:
+        means = sample_vectors(samples, num_clusters)
+    means = means.clone()
+    ws = _lib.Workspace()
+    d = samples.shape[1]
+    bins = None
+    for i in range(num_iters):
+        idx, denom = hard_assign(samples, means, workspace=ws)
+        _, stats = code_statistics(samples, denom, means, idx, workspace=ws)
+        bins = stats[:num_clusters]
+        zero_mask = bins == 0
+        sums = stats[num_clusters:num_clusters + num_clusters * d].view(num_clusters, d)
+        new_means = (sums / bins.masked_fill(zero_mask, 1)[..., None]).float()
+        new_means = l2norm(new_means)
+        means = torch.where(zero_mask[..., None], means, new_means)
+        if verbose:
+            print(f"Iteration {i + 1}/{num_iters} - Zero clusters: {int(zero_mask.sum().item())}")
+    return means, bins.to(torch.int64)
+
+
+# ------------------------------------------------------------------------------------------------
+class EmbeddingEMA(nn.Module):
+    """Codebook container, reference :60-134: `weight`, `cluster_size`, `embed_avg` parameters
+    (requires_grad=False), `initted` buffer, `update` flag; identical state_dict keys."""
+
+    def __init__(self, num_tokens, codebook_dim, decay=0.99, eps=1e-5, kmeans_init=True, codebook_init_path=''):
+        super().__init__()
+        self.num_tokens = num_tokens
+        self.codebook_dim = codebook_dim
+        self.decay = decay
+        self.eps = eps
+        if codebook_init_path == '':
+            if not kmeans_init:
+                weight = l2norm(torch.randn(num_tokens, codebook_dim))
+            else:
+                weight = torch.zeros(num_tokens, codebook_dim)
+            self.register_buffer('initted', torch.Tensor([not kmeans_init]))
+        else:
+            print(f"load init codebook weight from {codebook_init_path}")
+            weight = torch.load(codebook_init_path, map_location='cpu').clone()
+            self.register_buffer('initted', torch.Tensor([True]))
+        self.weight = nn.Parameter(weight, requires_grad=False)
+        self.cluster_size = nn.Parameter(torch.zeros(num_tokens), requires_grad=False)
+        self.embed_avg = nn.Parameter(weight.clone(), requires_grad=False)
+        self.update = True
+        self._initted_host = None       # host mirror of `initted`: avoids the reference's per-forward sync (:87)
+
+    def _is_initted(self) -> bool:
+        if self._initted_host is None:
+            self._initted_host = bool(self.initted.item())
+        return self._initted_host
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._initted_host = None
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    @torch.jit.ignore
+    def init_embed_(self, data):
+        """reference :85-93"""
+        if self._is_initted():
+            return
+        print("Performing Kemans init for codebook")
+        embed, cluster_size = kmeans(data, self.num_tokens, 10, use_cosine_sim=True)
+        self.weight.data.copy_(embed)
+        self.cluster_size.data.copy_(cluster_size)
+        self.initted.data.copy_(torch.Tensor([True]))
+        self._initted_host = True
+
+    def forward(self, embed_id):
+        return F.embedding(embed_id, self.weight)
+
+    def cluster_size_ema_update(self, new_cluster_size):
+        self.cluster_size.data.mul_(self.decay).add_(new_cluster_size, alpha=1 - self.decay)
+
+    def embed_avg_ema_update(self, new_embed_avg):
+        self.embed_avg.data.mul_(self.decay).add_(new_embed_avg, alpha=1 - self.decay)
+
+    def weight_update(self, num_tokens):
+        n = self.cluster_size.sum()
+        smoothed_cluster_size = ((self.cluster_size + self.eps) / (n + num_tokens * self.eps) * n)
+        self.weight.data.copy_(self.embed_avg / smoothed_cluster_size.unsqueeze(1))
+
+
+# ------------------------------------------------------------------------------------------------
+class _HardQuantizeFn(torch.autograd.Function):
+    """Autograd shell around the forward: gradients reach only z (straight-through + commitment
+    term, through l2norm), never the codebook (reference :212-214)."""
+
+    @staticmethod
+    def forward(ctx, z_rows_in, module, norm_mode):
+        z_q, loss, idx = module._run(z_rows_in, norm_mode)
+        ctx.save_for_backward(z_rows_in, z_q)
+        ctx.beta = module.beta
+        ctx.mark_non_differentiable(idx)
+        return z_q, loss, idx
+
+    @staticmethod
+    def backward(ctx, g_zq, g_loss, _g_idx):
+        z_rows, z_q = ctx.saved_tensors
+        z32 = z_rows.float()
+        den = z32.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+        zf = z32 / den
+        g = torch.zeros_like(zf) if g_zq is None else g_zq.float().clone()
+        if g_loss is not None:
+            g = g + g_loss * (2.0 * ctx.beta / zf.numel()) * (zf - z_q)
+        gz = (g - zf * (zf * g).sum(-1, keepdim=True)) / den
+        return gz.to(z_rows.dtype), None, None
+
+
+class NormEMAVectorQuantizer(nn.Module):
+    """Drop-in for reference :140-218."""
+
+    def __init__(self, n_embed, embedding_dim, beta, decay=0.99, eps=1e-5,
+                 statistic_code_usage=True, kmeans_init=False, codebook_init_path=''):
+        super().__init__()
+        self.codebook_dim = embedding_dim
+        self.num_tokens = n_embed
+        self.beta = beta
+        self.decay = decay
+        self.embedding = EmbeddingEMA(self.num_tokens, self.codebook_dim, decay, eps, kmeans_init, codebook_init_path)
+        self.statistic_code_usage = statistic_code_usage
+        if statistic_code_usage:
+            self.register_buffer('cluster_size', torch.zeros(n_embed))
+        # like the reference (:155-159) the exchange is bound at construction time
+        if distributed.is_available() and distributed.is_initialized():
+            print("ddp is enable, so use ddp_reduce to sync the statistic_code_usage for each gpu!")
+            self.all_reduce_fn = distributed.all_reduce
+        else:
+            self.all_reduce_fn = nn.Identity()
+        self.global_loss = False          # True: loss = beta * sum_ranks(sse) / (sum_ranks(rows) * D)
+        self._ws = _lib.Workspace()
+        self.last_stats = None            # packed fp64 statistics of the last forward (diagnostics)
+
+    def reset_cluster_size(self, device):
+        if self.statistic_code_usage:
+            self.register_buffer('cluster_size', torch.zeros(self.num_tokens))
+            self.cluster_size = self.cluster_size.to(device)
+
+    # -- one forward on rows [N, D] -------------------------------------------------------------
+    def _run(self, z_rows_in: torch.Tensor, norm_mode: int):
+        L = _lib.lib()
+        z_rows = _rows_f32(z_rows_in)
+        n, d = z_rows.shape
+        k = self.num_tokens
+        dev = z_rows.device
+        weight = self.embedding.weight.data
+        _lib.require_cuda(weight, "embedding.weight")
+        if weight.dtype != torch.float32 or not weight.is_contiguous():
+            raise _lib.MedTokVQError("embedding.weight must be a contiguous fp32 tensor")
+        has_cs = self.statistic_code_usage
+        distributed_on = not isinstance(self.all_reduce_fn, nn.Identity)
+        flags = (_lib.F_TRAINING if self.training else 0) | (_lib.F_UPDATE if self.embedding.update else 0)
+        if distributed_on or not has_cs:
+            flags |= _lib.F_SKIP_FINALIZE
+        ws = self._ws.get(n, d, k, 1, dev)
+        z_q = torch.empty_like(z_rows)
+        idx = torch.empty(n, dtype=torch.int64, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        stats = torch.empty(_lib.stats_len(d, k), dtype=torch.float64, device=dev)
+        cs = self.cluster_size if has_cs else None
+        _lib.check(L.mtvq_hard_forward(_lib.ptr(z_rows), n, d, norm_mode, _lib.ptr(weight), k, _lib.ptr(cs),
+                                       float(self.beta), float(self.decay), flags, _lib.ptr(z_q), _lib.ptr(idx),
+                                       _lib.ptr(loss), _lib.ptr(stats), _lib.ptr(ws), ws.numel(),
+                                       _lib.stream_ptr(dev)), "mtvq_hard_forward")
+        if flags & _lib.F_SKIP_FINALIZE:
+            upd_w = self.training and self.embedding.update
+            upd_cs = has_cs and ((not self.training) or self.embedding.update)
+            if distributed_on and (upd_w or upd_cs):
+                self.all_reduce_fn(stats)          # ONE packed all-reduce (reference: :188 / :195 + :203)
+            if upd_w or upd_cs:
+                _lib.check(L.mtvq_ema_finalize(_lib.ptr(weight), _lib.ptr(cs), _lib.ptr(stats), k, d,
+                                               float(self.beta), float(self.decay), int(upd_cs), int(upd_w),
+                                               _lib.ptr(loss) if self.global_loss else None,
+                                               _lib.stream_ptr(dev)), "mtvq_ema_finalize")
+        self.last_stats = stats
+        return z_q, loss.reshape(()), idx
+
+    def forward(self, z):
+        _lib.require_cuda(z, "z")
+        b, c, h, w = z.shape
+        if c != self.codebook_dim:
+            raise _lib.MedTokVQError(f"expected {self.codebook_dim} channels, got {c}")
+        if h * w == 1:
+            rows = z.reshape(b, c)                                   # 'b c h w -> b h w c' is a no-op view
+            norm_mode = _lib.NORM_CONTIGUOUS
+        else:
+            rows = z.permute(0, 2, 3, 1).reshape(-1, c)              # reference :169-171
+            norm_mode = _lib.NORM_STRIDED                             # torch normalises the strided view there
+        if not self.embedding._is_initted():
+            self.embedding.init_embed_(l2norm(_rows_f32(rows)))      # reference :173 (k-means on first batch)
+        if torch.is_grad_enabled() and z.requires_grad:
+            z_q, loss, idx = _HardQuantizeFn.apply(rows, self, norm_mode)
+        else:
+            z_q, loss, idx = self._run(rows, norm_mode)
+        if z_q.dtype != z.dtype:
+            z_q = z_q.to(z.dtype)
+        if h * w == 1:
+            z_q = z_q.view(b, c, 1, 1)
+        else:
+            z_q = z_q.view(b, h, w, c).permute(0, 3, 1, 2)           # reference :217
+        return z_q, loss, idx

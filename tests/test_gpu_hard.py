@@ -1,0 +1,207 @@
+"""GPU parity tests of the hard (norm-EMA) quantizer: CUDA path (through the drop-in module and the
+C ABI) vs golden outputs of the unmodified reference and vs the CPU oracle on seeded inputs."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+HARD = [n for n in golden_names("hard_") if "gloo" not in n]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def _module(a, meta, dev):
+    from medtok_b200.norm_ema_quantizer import NormEMAVectorQuantizer
+    k, d = a["weight0"].shape
+    q = NormEMAVectorQuantizer(n_embed=k, embedding_dim=d, beta=meta["beta"], decay=meta["decay"]).to(dev)
+    q.embedding.update = meta["update"]
+    q.train(meta["training"])
+    return q
+
+
+@pytest.mark.parametrize("name", HARD)
+def test_module_matches_reference_golden(name, dev):
+    meta, a = load_golden(name)
+    q = _module(a, meta, dev)
+    assert sorted(q.state_dict().keys()) == meta["state_dict_keys"]
+    z = torch.from_numpy(a["z"]).to(dev)
+    w_prev, cs_prev = a["weight0"], np.zeros(a["weight0"].shape[0], np.float32)
+    for s in range(meta["steps"]):
+        q.embedding.weight.data.copy_(torch.from_numpy(w_prev).to(dev))
+        q.cluster_size.copy_(torch.from_numpy(cs_prev).to(dev))
+        with torch.no_grad():
+            z_q, loss, idx = q(z)
+        assert idx.dtype == torch.int64 and z_q.shape == z.shape and loss.dim() == 0
+        # bit-exact: code indices, cluster_size (counts), quantised output
+        assert np.array_equal(idx.cpu().numpy(), a[f"idx_{s}"]), f"{name}: index mismatch at step {s}"
+        assert np.array_equal(q.cluster_size.cpu().numpy(), a[f"cluster_size_{s}"])
+        assert np.array_equal(z_q.cpu().numpy(), a[f"z_q_{s}"])
+        # stated tolerances: loss rel 1e-5; updated codebook abs 1e-6 (fp64 vs fp32-GEMM embed_sum order)
+        ref_loss = float(a[f"loss_{s}"][0])
+        assert abs(float(loss) - ref_loss) <= 1e-5 * abs(ref_loss) + 1e-12
+        assert np.max(np.abs(q.embedding.weight.cpu().numpy() - a[f"weight_{s}"])) <= 1e-6
+        w_prev, cs_prev = a[f"weight_{s}"], a[f"cluster_size_{s}"]
+
+
+def test_coarse_scores_match_fp16_model(dev):
+    """The tensor-core pass computes zf.w - ||w||^2/2 from fp16 operands: check the raw TMEM scores
+    against the same fp16-rounded operands multiplied in fp32 by torch (validates the UMMA descriptors,
+    operand layout and TMEM lane/column mapping)."""
+    from medtok_b200 import _lib
+    torch.manual_seed(3)
+    for (n, d, k) in ((700, 64, 1000), (300, 128, 384), (130, 256, 256), (256, 32, 512)):
+        z = torch.randn(n, d, device=dev)
+        w = torch.nn.functional.normalize(torch.randn(k, d, device=dev), dim=-1) * 1.3
+        ws = _lib.Workspace().get(n, d, k, 1, dev)
+        kpad = ctypes.c_int(0)
+        L = _lib.lib()
+        _lib.check(L.mtvq_debug_coarse_scores(_lib.ptr(z), n, d, 0, _lib.ptr(w), k, None, 0, ctypes.byref(kpad),
+                                              _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "kpad query")
+        scores = torch.full((n, kpad.value), float("nan"), device=dev)
+        _lib.check(L.mtvq_debug_coarse_scores(_lib.ptr(z), n, d, 0, _lib.ptr(w), k, _lib.ptr(scores), n,
+                                              ctypes.byref(kpad), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)),
+                   "mtvq_debug_coarse_scores")
+        torch.cuda.synchronize()
+        zf = torch.nn.functional.normalize(z, dim=-1)
+        ref = zf.half().double() @ w.half().double().t() - 0.5 * (w.double() ** 2).sum(1)
+        got = scores[:, :k].double()
+        err = (got - ref).abs().max().item()
+        assert err < 2e-5, f"(n={n}, d={d}, k={k}) coarse score mismatch, max err {err}"
+        assert (scores[:, k:] < -1e4).all()            # padding codes can never win
+
+
+@pytest.mark.parametrize("n,d,k", [(20000, 64, 8192), (5000, 128, 4096), (3000, 256, 1024), (9999, 32, 777)])
+def test_assign_matches_oracle_and_exact_kernel(oracle, dev, n, d, k):
+    from medtok_b200 import _lib
+    from medtok_b200.norm_ema_quantizer import hard_assign
+    g = torch.Generator().manual_seed(n + d + k)
+    z = torch.randn(n, d, generator=g)
+    w = torch.nn.functional.normalize(torch.randn(k, d, generator=g), dim=-1)
+    zf, den_ref = oracle.C().l2norm_rows(z.numpy())
+    idx_ref, _ = oracle.C().hard_assign(zf, w.numpy())
+    wsx = _lib.Workspace()
+    idx, den = hard_assign(z.to(dev), w.to(dev), workspace=wsx)
+    cnt = _lib.debug_counters(wsx.buf, n, d, k)
+    idx_x, den_x = hard_assign(z.to(dev), w.to(dev), exact=True)
+    assert np.array_equal(den.cpu().numpy(), den_ref)
+    assert np.array_equal(den_x.cpu().numpy(), den_ref)
+    assert np.array_equal(idx_x.cpu().numpy(), idx_ref), "exact CUDA-core kernel != oracle"
+    assert np.array_equal(idx.cpu().numpy(), idx_ref), "tensor-core path != oracle"
+    assert cnt["full_scan_rows"] == 0 and cnt["near_tie_rows"] < 0.3 * n
+
+
+def test_degenerate_codebooks(oracle, dev):
+    """all-zero codebook (k-means pending: every code ties -> index 0) and massive duplication
+    (candidate list overflows -> exact full scan fallback)."""
+    from medtok_b200 import _lib
+    from medtok_b200.norm_ema_quantizer import hard_assign
+    g = torch.Generator().manual_seed(5)
+    z = torch.randn(300, 64, generator=g)
+    w0 = torch.zeros(512, 64)
+    idx, _ = hard_assign(z.to(dev), w0.to(dev))
+    assert (idx == 0).all()
+    w = torch.nn.functional.normalize(torch.randn(8, 64, generator=g), dim=-1).repeat(64, 1)   # each row 64 times
+    wsx = _lib.Workspace()
+    idx, _ = hard_assign(z.to(dev), w.to(dev), workspace=wsx)
+    zf, _ = oracle.C().l2norm_rows(z.numpy())
+    idx_ref, _ = oracle.C().hard_assign(zf, w.numpy())
+    assert np.array_equal(idx.cpu().numpy(), idx_ref)
+    assert (idx < 8).all()
+    assert _lib.debug_counters(wsx.buf, 300, 64, 512)["full_scan_rows"] == 300
+
+
+def test_forward_matches_oracle_random(oracle, dev):
+    """Training forward on a mid-size seeded problem vs the oracle (statistics included)."""
+    from medtok_b200.norm_ema_quantizer import NormEMAVectorQuantizer
+    n, d, k = 30000, 64, 4096
+    g = torch.Generator().manual_seed(99)
+    z = torch.randn(n, d, generator=g)
+    w = torch.nn.functional.normalize(torch.randn(k, d, generator=g), dim=-1)
+    cs0 = torch.rand(k, generator=g)
+    r = oracle.hard_forward(z.numpy(), w.numpy(), cs0.numpy(), 0.25, 0.99)
+    q = NormEMAVectorQuantizer(k, d, 0.25).to(dev).train()
+    q.embedding.weight.data.copy_(w.to(dev))
+    q.cluster_size.copy_(cs0.to(dev))
+    with torch.no_grad():
+        z_q, loss, idx = q(z.view(n, d, 1, 1).to(dev))
+    assert np.array_equal(idx.cpu().numpy(), r.idx)
+    assert np.array_equal(q.cluster_size.cpu().numpy(), r.cluster_size)
+    assert np.array_equal(z_q.view(n, d).cpu().numpy(), r.z_q)
+    st = q.last_stats.cpu().numpy()
+    assert np.array_equal(st[:k], r.bins)
+    assert np.allclose(st[k:k + k * d].reshape(k, d), r.embed_sum, rtol=0, atol=1e-9)
+    assert abs(st[k + k * d] - r.sse) <= 1e-9 * r.sse and st[k + k * d + 1] == n
+    assert abs(float(loss) - r.loss) <= 1e-6 * r.loss
+    assert np.max(np.abs(q.embedding.weight.cpu().numpy() - r.weight)) <= 1.2e-7   # <= 1 ulp of a unit-norm row
+
+
+def test_gradient_is_straight_through_plus_commitment(dev):
+    """autograd contract (reference :212-214): d/dz of (z_q.sum*g + loss) == torch autograd of the
+    reference formula evaluated with the same indices."""
+    from medtok_b200.norm_ema_quantizer import NormEMAVectorQuantizer
+    n, d, k = 257, 64, 512
+    g = torch.Generator().manual_seed(17)
+    z = torch.randn(n, d, 1, 1, generator=g).to(dev).requires_grad_(True)
+    gout = torch.randn(n, d, 1, 1, generator=g).to(dev)
+    q = NormEMAVectorQuantizer(k, d, 0.25).to(dev).train()
+    w0 = q.embedding.weight.data.clone()
+    z_q, loss, idx = q(z)
+    ((z_q * gout).sum() + 3.0 * loss).backward()
+    z2 = z.detach().clone().requires_grad_(True)
+    zf = torch.nn.functional.normalize(z2.view(n, d), dim=-1)
+    zq_ref = w0[idx]
+    loss_ref = 0.25 * torch.nn.functional.mse_loss(zq_ref, zf)
+    out_ref = zf + (zq_ref - zf).detach()
+    ((out_ref * gout.view(n, d)).sum() + 3.0 * loss_ref).backward()
+    assert torch.allclose(z.grad, z2.grad, rtol=1e-4, atol=1e-6)
+
+
+def test_full_size_config2_properties(oracle, dev):
+    """BASELINE config 2 (N=2^20, D=64, K=8192): tensor-core path == exact CUDA-core kernel on every row,
+    == CPU oracle on a 16K-row sample, plus size-independent invariants of the EMA update."""
+    from medtok_b200 import _lib
+    from medtok_b200.norm_ema_quantizer import NormEMAVectorQuantizer, hard_assign
+    n, d, k = 1 << 20, 64, 8192
+    torch.manual_seed(0)
+    z = torch.randn(n, d)
+    torch.manual_seed(1)
+    w = torch.nn.functional.normalize(torch.randn(k, d), dim=-1)
+    zd, wd = z.to(dev), w.to(dev)
+    q = NormEMAVectorQuantizer(k, d, 0.25).to(dev).train()
+    q.embedding.weight.data.copy_(wd)
+    with torch.no_grad():
+        z_q, loss, idx = q(zd.view(n, d, 1, 1))
+    cnt = _lib.debug_counters(q._ws.buf, n, d, k)
+    idx_x, _ = hard_assign(zd, wd, exact=True)
+    mism = (idx != idx_x).nonzero().flatten()
+    assert mism.numel() == 0, f"{mism.numel()} rows differ from the exact kernel, first {mism[:8].tolist()}"
+    sample = torch.arange(0, n, 64)
+    zf, _ = oracle.C().l2norm_rows(z[sample].numpy())
+    idx_ref, _ = oracle.C().hard_assign(zf, w.numpy())
+    assert np.array_equal(idx[sample.to(dev)].cpu().numpy(), idx_ref)
+    st = q.last_stats
+    assert st[:k].sum().item() == n                                       # sum of bins == N
+    bins = torch.bincount(idx, minlength=k).double()
+    assert torch.equal(st[:k], bins)
+    assert torch.equal(q.cluster_size, (0.01 * bins).float()) or torch.allclose(q.cluster_size, (0.01 * bins).float(), rtol=1e-6)
+    wn = q.embedding.weight.norm(dim=-1)
+    assert (wn - 1).abs().max().item() < 1e-6                              # rows stay unit norm
+    dead = bins == 0
+    if dead.any():                                                          # dead codes unchanged (up to renorm)
+        assert torch.allclose(q.embedding.weight[dead], wd[dead], atol=2e-7)
+    zfd = torch.nn.functional.normalize(zd, dim=-1)
+    assert (z_q.view(n, d) - wd[idx]).abs().max().item() < 2e-7            # STE value == gathered pre-update row
+    ref_loss = 0.25 * ((wd[idx] - zfd).double() ** 2).mean().item()
+    assert abs(float(loss) - ref_loss) <= 1e-5 * ref_loss
+    assert cnt["full_scan_rows"] == 0
+    print("config2 near-tie rows:", cnt)

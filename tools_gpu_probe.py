@@ -1,0 +1,82 @@
+"""First-contact GPU probe (run under gpurun): micro-benchmarks that size the epilogue, a raw
+tensor-core score check, and a coarse timing of the hard forward at BASELINE config 2.
+Writes gpurun_out/probe.json.  Diagnostic tool, not part of the product or the tests."""
+import ctypes
+import json
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from medtok_b200 import _lib  # noqa: E402
+
+out = {}
+dev = torch.device("cuda:0")
+L = _lib.lib()
+st = _lib.stream_ptr(dev)
+props = torch.cuda.get_device_properties(0)
+out["device"] = {"name": props.name, "sms": props.multi_processor_count, "cc": [props.major, props.minor]}
+
+what = sys.argv[1] if len(sys.argv) > 1 else "all"
+
+if what in ("all", "micro"):
+    res = (ctypes.c_double * 2)()
+    mb = {}
+    for which, label in ((0, "tmem_ld_GBps"), (1, "fmnmx_Gscores")):
+        for warps in (4, 8, 16, 32):
+            _lib.check(L.mtvq_microbench(which, warps, 2000, res, st), "microbench")
+            mb[f"{label}_w{warps}"] = res[1] / (res[0] * 1e-3) / 1e9
+    out["microbench"] = mb
+    print(json.dumps(mb, indent=1))
+
+if what in ("all", "scores"):
+    torch.manual_seed(3)
+    n, d, k = 700, 64, 1000
+    z = torch.randn(n, d, device=dev)
+    w = torch.nn.functional.normalize(torch.randn(k, d, device=dev), dim=-1)
+    ws = _lib.Workspace().get(n, d, k, 1, dev)
+    kpad = ctypes.c_int(0)
+    _lib.check(L.mtvq_debug_coarse_scores(_lib.ptr(z), n, d, 0, _lib.ptr(w), k, None, 0, ctypes.byref(kpad),
+                                          _lib.ptr(ws), ws.numel(), st), "kpad")
+    scores = torch.full((n, kpad.value), float("nan"), device=dev)
+    _lib.check(L.mtvq_debug_coarse_scores(_lib.ptr(z), n, d, 0, _lib.ptr(w), k, _lib.ptr(scores), n,
+                                          ctypes.byref(kpad), _lib.ptr(ws), ws.numel(), st), "dump")
+    torch.cuda.synchronize()
+    zf = torch.nn.functional.normalize(z, dim=-1)
+    ref = zf.half().double() @ w.half().double().t() - 0.5 * (w.double() ** 2).sum(1)
+    got = scores[:, :k].double()
+    err = (got - ref).abs()
+    out["scores"] = {"swap": os.environ.get("MTVQ_DESC_SWAP", "0"), "max_err": err.max().item(),
+                     "nan": int(torch.isnan(got).sum()), "frac_ok": float((err < 1e-4).float().mean()),
+                     "got00": got[0, :4].tolist(), "ref00": ref[0, :4].tolist(),
+                     "got_row5": got[5, 128:132].tolist(), "ref_row5": ref[5, 128:132].tolist()}
+    print(json.dumps(out["scores"], indent=1))
+
+if what in ("all", "time"):
+    from medtok_b200.norm_ema_quantizer import NormEMAVectorQuantizer
+    n, d, k = 1 << 20, 64, 8192
+    torch.manual_seed(0)
+    z = torch.randn(n, d, 1, 1, device=dev)
+    q = NormEMAVectorQuantizer(k, d, 0.25).to(dev).train()
+    w0 = q.embedding.weight.data.clone()
+    with torch.no_grad():
+        for _ in range(3):
+            q.embedding.weight.data.copy_(w0)
+            q(z)
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(11)]
+        ev[0].record()
+        for i in range(10):
+            q(z)
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+    ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(10)]
+    out["time_c2_ms"] = ms
+    out["c2_counters"] = _lib.debug_counters(q._ws.buf, n, d, k)
+    print("hard forward C2 ms:", ms, out["c2_counters"])
+
+os.makedirs("gpurun_out", exist_ok=True)
+tag = what + ("_swap" if os.environ.get("MTVQ_DESC_SWAP") == "1" else "")
+json.dump(out, open(f"gpurun_out/probe_{tag}.json", "w"), indent=1)
