@@ -150,6 +150,12 @@ MTVQ_API int mtvq_debug_coarse_scores(const float *z, int64_t n, int d, int norm
                              float *scores, int64_t rows, int *kpad_host,
                              void *workspace, size_t workspace_bytes, void *stream);
 
+/* Profiling hook (bench.py): the next mtvq_hard_forward / mtvq_hard_assign issued by this host thread
+ * records the two caller-owned cudaEvent_t handles on `stream` immediately before and after the launch
+ * of the dominant kernel (the tcgen05 coarse-score pass over all rows).  One-shot: cleared after use;
+ * pass NULLs to cancel.  Never synchronises. */
+MTVQ_API int mtvq_debug_set_events(void *event_before, void *event_after);
+
 /* micro-benchmarks used to size the epilogue (DESIGN.md "measured machine limits"):
  * which = 0: tcgen05.ld throughput, 1: FMNMX3 tree throughput; result_host[0] = device ms,
  * result_host[1] = bytes or ops processed. */

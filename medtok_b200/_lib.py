@@ -43,6 +43,7 @@ _SIGNATURES = {
     "mtvq_debug_counters": (_int, [_vp, _i64, _int, _int, _int, ctypes.POINTER(_i64), _vp]),
     "mtvq_debug_coarse_scores": (_int, [_vp, _i64, _int, _int, _vp, _int, _vp, _i64, ctypes.POINTER(_int),
                                         _vp, _sz, _vp]),
+    "mtvq_debug_set_events": (_int, [_vp, _vp]),
     "mtvq_microbench": (_int, [_int, _int, _int, ctypes.POINTER(_dbl), _vp]),
 }
 
@@ -110,6 +111,13 @@ class Workspace:
 
 def stats_len(d: int, k: int) -> int:
     return int(lib().mtvq_stats_len(d, k))
+
+
+def set_profile_events(before: "torch.cuda.Event | None", after: "torch.cuda.Event | None") -> None:
+    """One-shot: the next hard forward on this thread records `before`/`after` around its dominant kernel."""
+    b = ctypes.c_void_p(before.cuda_event) if before is not None else None
+    a = ctypes.c_void_p(after.cuda_event) if after is not None else None
+    check(lib().mtvq_debug_set_events(b, a), "mtvq_debug_set_events")
 
 
 def debug_counters(ws: torch.Tensor, n: int, d: int, k: int, topk: int = 1) -> dict:

@@ -19,7 +19,8 @@ using namespace mtvq;
 namespace {
 
 thread_local char g_err[512] = "";
-thread_local long g_launches = 0;
+thread_local long g_launches = 0;       // kernels enqueued by this thread (memsets not counted)
+thread_local cudaEvent_t g_ev_before = nullptr, g_ev_after = nullptr;
 
 int fail(int code, const char* fmt, const char* a = "", long b = 0, long c = 0) {
     snprintf(g_err, sizeof(g_err), fmt, a, b, c);
@@ -32,7 +33,7 @@ int cuda_fail(cudaError_t e, const char* where) {
 #define MTVQ_CUDA(call, where)                                 \
     do {                                                       \
         cudaError_t e__ = (call);                              \
-        ++g_launches;                                          \
+        if (strncmp(where, "memset", 6) != 0) ++g_launches;    \
         if (e__ != cudaSuccess) return cuda_fail(e__, where);  \
     } while (0)
 
@@ -103,7 +104,10 @@ int assign_into_ws(const float* z, int64_t n, int d, int norm_mode, const float*
     MTVQ_CUDA(cudaMemsetAsync(ws.cand_cnt, 0, sizeof(int) * n, st), "memset cand_cnt");
     CoarseParams p;
     fill_coarse(p, z, n, d, norm_mode, k, ws, denom, 1);
+    if (g_ev_before) cudaEventRecord(g_ev_before, st);
     MTVQ_CUDA(launch_coarse(p, MODE_ARGMAX, coarse_row_tiles(d, n, di.num_sms), di.num_sms, st), "coarse argmax");
+    if (g_ev_after) cudaEventRecord(g_ev_after, st);
+    g_ev_before = g_ev_after = nullptr;
     // near-tie rows: collect every code within the margin, then decide in exact fp32
     CoarseParams c = p;
     c.row_list = ws.flag_rows;
@@ -314,6 +318,12 @@ int mtvq_debug_coarse_scores(const float* z, int64_t n, int d, int norm_mode, co
     if (rt != 1 && rt != 2 && rt != 4) rt = 1;
     if (rt * d > 256) rt = 256 / d;
     MTVQ_CUDA(launch_coarse(p, MODE_DUMP, rt, di.num_sms, st), "coarse dump");
+    return 0;
+}
+
+int mtvq_debug_set_events(void* event_before, void* event_after) {
+    g_ev_before = static_cast<cudaEvent_t>(event_before);
+    g_ev_after = static_cast<cudaEvent_t>(event_after);
     return 0;
 }
 

@@ -19,11 +19,13 @@
 //   COLLECT  append every column with s >= best_val[row] - margin          (near-tie rows / soft pass B)
 //   DUMP     raw scores to global memory (tests only)
 //
-// Roles (704 threads, 1 CTA per SM, persistent over row blocks of RT x 128 rows):
+// Roles (800 threads, 1 CTA per SM, persistent over row blocks of RT x 128 rows):
 //   warps 0-15  epilogue: warpgroup e owns accumulator slot e (128 TMEM columns)
 //   warps 16-19 A loader: rows -> canonical l2norm -> fp16 -> shared memory operand planes
 //   warp  20    B producer: cp.async.bulk of pre-laid-out codebook tiles (L2 resident) into a ring
-//   warp  21    MMA issuer (one elected thread) + TMEM allocator
+//   warps 21-24 MMA issuers, one elected thread each, issuer j feeds accumulator slot j (a single
+//               issuing thread is instruction-latency bound at ~140 SASS instructions per tile);
+//               warp 21 also owns the TMEM allocation
 //
 // Shared-memory operand layout (both A and B): K-major, no swizzle; "plane" j holds, for every row
 // of the tile, the 8 fp16 elements [8j, 8j+8) as one 16-byte unit => LBO = 2048 B (next plane),
@@ -38,8 +40,8 @@ namespace {
 constexpr int kEpiWarps   = 16;
 constexpr int kLoadWarp0  = 16;
 constexpr int kProdWarp   = 20;
-constexpr int kMmaWarp    = 21;
-constexpr int kThreads    = 22 * 32;
+constexpr int kMmaWarp    = 21;         // 21..24: one MMA issuer per accumulator slot
+constexpr int kThreads    = 25 * 32;
 
 constexpr int kPlaneBytes = kTileRows * 16;          // 2048
 constexpr int kKblkBytes  = 8 * kPlaneBytes;         // 16384: 64 fp16 per row
@@ -146,11 +148,12 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
 
     // ---- one-time setup ------------------------------------------------------------------------
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kDataStages; ++i) { mbar_init(&bars.bd_full[i], 1); mbar_init(&bars.bd_empty[i], 1); }
-        for (int i = 0; i < kBiasStages; ++i) { mbar_init(&bars.bb_full[i], 1); mbar_init(&bars.bb_empty[i], 1); }
+        // a codebook stage is read by the RT tiles (= RT different issuers) of one chunk
+        for (int i = 0; i < kDataStages; ++i) { mbar_init(&bars.bd_full[i], 1); mbar_init(&bars.bd_empty[i], RT); }
+        for (int i = 0; i < kBiasStages; ++i) { mbar_init(&bars.bb_full[i], 1); mbar_init(&bars.bb_empty[i], RT); }
         for (int i = 0; i < 4; ++i) {
             mbar_init(&bars.a_full[i], 128);
-            mbar_init(&bars.a_empty[i], 1);
+            mbar_init(&bars.a_empty[i], 4 / RT);   // one commit from each issuer that reads the tile
             mbar_init(&bars.acc_full[i], 1);
             mbar_init(&bars.acc_empty[i], 128);
         }
@@ -245,12 +248,15 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                         const bool trig = cmax >= T;
                         if (__any_sync(0xffffffffu, trig)) {
                             if (trig) {
-#pragma unroll 1
-                                for (int i = 0; i < 32; ++i) {
-                                    if (v[i] >= T) {
-                                        const int at = atomicAdd(&p.cand_cnt[pos], 1);
-                                        if (at < p.cand_cap) p.cand[pos * p.cand_cap + at] = chunk * kChunk + i;
-                                    }
+                                // static indices only: a runtime index would push v[] into local memory
+                                uint32_t hits = 0;
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) hits |= (v[i] >= T) ? (1u << i) : 0u;
+                                while (hits) {
+                                    const int i = __ffs(hits) - 1;
+                                    hits &= hits - 1;
+                                    const int at = atomicAdd(&p.cand_cnt[pos], 1);
+                                    if (at < p.cand_cap) p.cand[pos * p.cand_cap + at] = chunk * kChunk + i;
                                 }
                             }
                         }
@@ -397,52 +403,62 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                 }
             }
         }
-    } else if (warp == kMmaWarp) {
-        // ---------------------------------- MMA ISSUER ------------------------------------------
+    } else if (warp >= kMmaWarp) {
+        // ---------------------------------- MMA ISSUERS -----------------------------------------
+        // issuer j owns accumulator slot j, i.e. the tiles (c, g) with (c*RT + g) % 4 == j
         if (elect_one()) {
+            const int j = warp - kMmaWarp;
+            const int g = j % RT;
+            constexpr int G = 4 / RT;
             const uint32_t idesc = umma_idesc_f16(kTileRows, kTileCodes);
             const uint32_t lbo = p.lbo_bytes, sbo = p.sbo_bytes;
-            const uint32_t sA = smem_u32(smem + kOffA), sOnes = smem_u32(smem + kOffOnes);
-            const uint32_t sBD = smem_u32(smem + kOffBData), sBB = smem_u32(smem + kOffBBias);
-            uint32_t acc_uses[4] = {0, 0, 0, 0};
-            uint32_t itD = 0, itB = 0, bi = 0;
-            for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x, ++bi) {
-                for (int c = 0; c < nchunks; ++c) {
-                    for (int g = 0; g < RT; ++g) {
-                        const int slot = (c * RT + g) & 3;
-                        mbar_wait(&bars.acc_empty[slot], (acc_uses[slot] & 1) ^ 1);
-                        if (c == 0) mbar_wait(&bars.a_full[g], bi & 1);
+            // descriptors are built once; per MMA only the 14-bit start-address field moves
+            // (units of 16 B: one K-step = 2 planes = 256, one K-block / data stage = 1024)
+            const uint64_t dA = umma_smem_desc(smem_u32(smem + kOffA + g * a_tile_b), lbo, sbo);
+            const uint64_t dOnes = umma_smem_desc(smem_u32(smem + kOffOnes), lbo, sbo);
+            const uint64_t dBD0 = umma_smem_desc(smem_u32(smem + kOffBData), lbo, sbo);
+            const uint64_t dBB0 = umma_smem_desc(smem_u32(smem + kOffBBias), lbo, sbo);
+            const uint32_t tacc = tmem_base + (uint32_t)(j * kTileCodes);
+            uint32_t uses = 0, bi = 0;
+            uint32_t chunk0 = 0;                     // chunks issued by the CTA before this block
+            for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x, ++bi, chunk0 += nchunks) {
+                if (j / RT >= nchunks) {
+                    // fewer chunks than issuers: nothing to issue, but the row tile's release barrier
+                    // still expects this issuer once per block (paced by the tile's own arrival)
+                    mbar_wait(&bars.a_full[g], bi & 1);
+                    mbar_arrive(&bars.a_empty[g]);
+                    continue;
+                }
+                bool first = true;
+                for (int c = j / RT; c < nchunks; c += G) {
+                    const uint32_t gc = chunk0 + c;                       // running chunk number
+                    mbar_wait(&bars.acc_empty[j], (uses & 1u) ^ 1u);
+                    ++uses;
+                    if (first) { mbar_wait(&bars.a_full[g], bi & 1); first = false; }
+                    tc_fence_after();
+                    const uint32_t itD = gc * nkblk;
+                    for (int kb = 0; kb < nkblk; ++kb) {
+                        const uint32_t it = itD + kb;
+                        const uint32_t st = it % kDataStages;
+                        mbar_wait(&bars.bd_full[st], (it / kDataStages) & 1);
                         tc_fence_after();
-                        const uint32_t tacc = tmem_base + (uint32_t)(slot * kTileCodes);
-                        for (int kb = 0; kb < nkblk; ++kb) {
-                            const uint32_t it = itD + kb;
-                            const int st = it % kDataStages;
-                            if (g == 0) {
-                                mbar_wait(&bars.bd_full[st], (it / kDataStages) & 1);
-                                tc_fence_after();
-                            }
-                            const int nsteps = min(8, nplanes - 8 * kb) >> 1;
-                            for (int ks = 0; ks < nsteps; ++ks) {
-                                const uint64_t da = umma_smem_desc(sA + g * a_tile_b + kb * kKblkBytes + ks * 2 * kPlaneBytes, lbo, sbo);
-                                const uint64_t db = umma_smem_desc(sBD + st * kKblkBytes + ks * 2 * kPlaneBytes, lbo, sbo);
-                                umma_f16(tacc, da, db, idesc, (kb | ks) != 0);
-                            }
-                            if (g == RT - 1) umma_commit(&bars.bd_empty[st]);
+                        const int nsteps = min(8, nplanes - 8 * kb) >> 1;
+                        uint64_t da = dA + (uint64_t)(kb * (kKblkBytes >> 4));
+                        uint64_t db = dBD0 + (uint64_t)(st * (kKblkBytes >> 4));
+                        for (int ks = 0; ks < nsteps; ++ks) {
+                            umma_f16(tacc, da, db, idesc, (kb | ks) != 0);
+                            da += (2 * kPlaneBytes) >> 4;
+                            db += (2 * kPlaneBytes) >> 4;
                         }
-                        const int sb = itB % kBiasStages;
-                        if (g == 0) {
-                            mbar_wait(&bars.bb_full[sb], (itB / kBiasStages) & 1);
-                            tc_fence_after();
-                        }
-                        umma_f16(tacc, umma_smem_desc(sOnes, lbo, sbo), umma_smem_desc(sBB + sb * kBiasBytes, lbo, sbo),
-                                 idesc, 1u);
-                        if (g == RT - 1) umma_commit(&bars.bb_empty[sb]);
-                        umma_commit(&bars.acc_full[slot]);
-                        ++acc_uses[slot];
-                        if (c == nchunks - 1) umma_commit(&bars.a_empty[g]);
+                        umma_commit(&bars.bd_empty[st]);
                     }
-                    itD += nkblk;
-                    ++itB;
+                    const uint32_t sb = gc % kBiasStages;
+                    mbar_wait(&bars.bb_full[sb], (gc / kBiasStages) & 1);
+                    tc_fence_after();
+                    umma_f16(tacc, dOnes, dBB0 + (uint64_t)(sb * (kBiasBytes >> 4)), idesc, 1u);
+                    umma_commit(&bars.bb_empty[sb]);
+                    umma_commit(&bars.acc_full[j]);
+                    if (c + G >= nchunks) umma_commit(&bars.a_empty[g]);   // this issuer's last tile of the block
                 }
             }
         }

@@ -80,7 +80,8 @@ def test_coarse_scores_match_fp16_model(dev):
         assert (scores[:, k:] < -1e4).all()            # padding codes can never win
 
 
-@pytest.mark.parametrize("n,d,k", [(20000, 64, 8192), (5000, 128, 4096), (3000, 256, 1024), (9999, 32, 777)])
+@pytest.mark.parametrize("n,d,k", [(20000, 64, 8192), (5000, 128, 4096), (3000, 256, 1024), (9999, 32, 777),
+                                   (1000, 64, 100), (777, 64, 300), (3, 16, 5), (70000, 48, 2000)])
 def test_assign_matches_oracle_and_exact_kernel(oracle, dev, n, d, k):
     from medtok_b200 import _lib
     from medtok_b200.norm_ema_quantizer import hard_assign

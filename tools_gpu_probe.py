@@ -28,6 +28,9 @@ if what in ("all", "micro"):
         for warps in (4, 8, 16, 32):
             _lib.check(L.mtvq_microbench(which, warps, 2000, res, st), "microbench")
             mb[f"{label}_w{warps}"] = res[1] / (res[0] * 1e-3) / 1e9
+    for ncols in (64, 128, 256):
+        _lib.check(L.mtvq_microbench(2, ncols // 8, 20000, res, st), "microbench umma")
+        mb[f"umma_TFLOPs_n{ncols}"] = res[1] / (res[0] * 1e-3) / 1e12
     out["microbench"] = mb
     print(json.dumps(mb, indent=1))
 
