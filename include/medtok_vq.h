@@ -156,6 +156,12 @@ MTVQ_API int mtvq_debug_coarse_scores(const float *z, int64_t n, int d, int norm
  * pass NULLs to cancel.  Never synchronises. */
 MTVQ_API int mtvq_debug_set_events(void *event_before, void *event_after);
 
+/* Pipeline trace (DESIGN.md "slot loop"): while set (device buffer of 512*8 int64, or NULL to stop), the
+ * coarse kernels of this host thread record clock64() stamps of accumulator slot 0 on CTA 0:
+ * [tile*8 + 0] issuer got the slot, +1 issuer done issuing, +2 epilogue saw the tile, +3 slot released,
+ * +4 tile reduced. */
+MTVQ_API int mtvq_debug_set_trace(void *trace_dev);
+
 /* micro-benchmarks used to size the epilogue (DESIGN.md "measured machine limits"):
  * which = 0: tcgen05.ld throughput, 1: FMNMX3 tree throughput; result_host[0] = device ms,
  * result_host[1] = bytes or ops processed. */

@@ -44,6 +44,7 @@ _SIGNATURES = {
     "mtvq_debug_coarse_scores": (_int, [_vp, _i64, _int, _int, _vp, _int, _vp, _i64, ctypes.POINTER(_int),
                                         _vp, _sz, _vp]),
     "mtvq_debug_set_events": (_int, [_vp, _vp]),
+    "mtvq_debug_set_trace": (_int, [_vp]),
     "mtvq_microbench": (_int, [_int, _int, _int, ctypes.POINTER(_dbl), _vp]),
 }
 

@@ -20,6 +20,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 thread_local long g_launches = 0;       // kernels enqueued by this thread (memsets not counted)
+thread_local long long* g_trace = nullptr;
 thread_local cudaEvent_t g_ev_before = nullptr, g_ev_after = nullptr;
 
 int fail(int code, const char* fmt, const char* a = "", long b = 0, long c = 0) {
@@ -86,8 +87,10 @@ void fill_coarse(CoarseParams& p, const float* z, int64_t n, int d, int norm_mod
     p.denom = denom; p.best_col = ws.best_col; p.best_val = ws.best_val;
     p.flag_rows = ws.flag_rows; p.counters = ws.counters;
     p.cand = ws.cand; p.cand_cnt = ws.cand_cnt; p.cand_cap = cand_capacity(topk); p.topk = topk;
+    p.trace = g_trace;
     p.lbo_bytes = desc_swap() ? 128 : 2048;
     p.sbo_bytes = desc_swap() ? 2048 : 128;
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MTVQ_DBG"); dbg = e ? atoi(e) : 0; } p.debug_flags = dbg; }
 }
 
 // hard assignment into ws.best_col (+ denom); `codes` are the rows the distances are taken against
@@ -318,6 +321,11 @@ int mtvq_debug_coarse_scores(const float* z, int64_t n, int d, int norm_mode, co
     if (rt != 1 && rt != 2 && rt != 4) rt = 1;
     if (rt * d > 256) rt = 256 / d;
     MTVQ_CUDA(launch_coarse(p, MODE_DUMP, rt, di.num_sms, st), "coarse dump");
+    return 0;
+}
+
+int mtvq_debug_set_trace(void* trace_dev) {
+    g_trace = static_cast<long long*>(trace_dev);
     return 0;
 }
 

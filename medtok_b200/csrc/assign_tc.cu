@@ -8,8 +8,10 @@
 //   coarse score  s[n,k] = zf_n . w_k - ||w_k||^2 / 2      (argmax s == argmin d)
 //     fp16 operands, fp32 accumulation in tensor memory; the -||w||^2/2 term rides in one extra
 //     UMMA K-step as three fp16 terms (A side = 1,1,1), so the epilogue is a pure max.
-//   epilogue      one thread per row streams its 32-column granules out of TMEM (tcgen05.ld), reduces
-//     them with FMNMX3 trees and keeps per-row running state in registers.
+//   epilogue      each thread owns one row x 64 columns of a 128x128 accumulator tile: it pulls its two
+//     32-column granules out of TMEM with two tcgen05.ld issued back to back, hands the accumulator slot
+//     back to the MMA issuer at once, and only then reduces the 64 scores (FMNMX3 trees) into per-row
+//     running state kept in registers.
 //
 // The coarse score is only used to SELECT candidates: |s - exact| <= eps (rigorous bound computed by
 // the codebook prep kernel), so every code within margin = 2 eps of the best coarse score is
@@ -19,13 +21,17 @@
 //   COLLECT  append every column with s >= best_val[row] - margin          (near-tie rows / soft pass B)
 //   DUMP     raw scores to global memory (tests only)
 //
-// Roles (800 threads, 1 CTA per SM, persistent over row blocks of RT x 128 rows):
-//   warps 0-15  epilogue: warpgroup e owns accumulator slot e (128 TMEM columns)
-//   warps 16-19 A loader: rows -> canonical l2norm -> fp16 -> shared memory operand planes
+// Why the slot is released early (DESIGN.md "slot loop"): tensor memory holds only four 128x128 fp32
+// accumulators, so tensor-pipe utilisation = 4 * T_mma / (latency of one MMA -> epilogue -> MMA round trip
+// of a slot).  Everything on that round trip is kept minimal; reductions happen after the release.
+//
+// Roles (896 threads = 7 warpgroups, 1 CTA per SM, persistent over row blocks of RT x 128 rows):
+//   warps  0-15 epilogue: warp w -> TMEM lane quarter w&3, column half (w>>2)&1, slot pair w>>3 (slots p, p+2)
+//   warps 16-19 A loader: rows -> canonical l2norm -> fp16 -> shared-memory operand planes
 //   warp  20    B producer: cp.async.bulk of pre-laid-out codebook tiles (L2 resident) into a ring
-//   warps 21-24 MMA issuers, one elected thread each, issuer j feeds accumulator slot j (a single
-//               issuing thread is instruction-latency bound at ~140 SASS instructions per tile);
-//               warp 21 also owns the TMEM allocation
+//   warps 24-27 MMA issuers, one elected thread each, issuer j feeds accumulator slot j; warp 24 owns TMEM
+//   (warps 21-23 only pad the producer's warpgroup so that setmaxnreg can rebalance registers:
+//    epilogue 96, loaders 56, producer 24, issuers 40 per thread)
 //
 // Shared-memory operand layout (both A and B): K-major, no swizzle; "plane" j holds, for every row
 // of the tile, the 8 fp16 elements [8j, 8j+8) as one 16-byte unit => LBO = 2048 B (next plane),
@@ -39,27 +45,30 @@ namespace {
 
 constexpr int kEpiWarps   = 16;
 constexpr int kLoadWarp0  = 16;
+constexpr int kLoadWarps  = 4;
 constexpr int kProdWarp   = 20;
-constexpr int kMmaWarp    = 21;         // 21..24: one MMA issuer per accumulator slot
-constexpr int kThreads    = 25 * 32;
+constexpr int kMmaWarp    = 24;         // 24..27: one MMA issuer per accumulator slot
+constexpr int kThreads    = 28 * 32;
 
 constexpr int kPlaneBytes = kTileRows * 16;          // 2048
 constexpr int kKblkBytes  = 8 * kPlaneBytes;         // 16384: 64 fp16 per row
 constexpr int kBiasBytes  = 2 * kPlaneBytes;         // 4096
 constexpr int kDataStages = 4;
 constexpr int kBiasStages = 3;
+constexpr int kRecords    = 1024;                    // 512 epilogue threads x up to 2 row tiles each
 
 // dynamic shared memory map
 constexpr int kOffA      = 0;                                    // RT tiles, <= 64 KB in total
 constexpr int kOffOnes   = 65536;
 constexpr int kOffBData  = kOffOnes + kBiasBytes;
 constexpr int kOffBBias  = kOffBData + kDataStages * kKblkBytes;
-constexpr int kOffSlots  = kOffBBias + kBiasStages * kBiasBytes;  // 4 WG x 128 rows x 128 B
-constexpr int kOffState  = kOffSlots + 4 * 128 * 128;             // 4 WG x 128 rows x 16 B
-constexpr int kOffBars   = kOffState + 4 * 128 * 16;
+constexpr int kOffSlots  = kOffBBias + kBiasStages * kBiasBytes;  // 4 chunks x 1024 records x 16 B (fp16 granules)
+constexpr int kOffState  = kOffSlots + 4 * kRecords * 16;         // 1024 records x 16 B
+constexpr int kOffBars   = kOffState + kRecords * 16;
 constexpr int kNumBars   = 2 * kDataStages + 2 * kBiasStages + 4 + 4 + 4 + 4;
 constexpr int kOffTmem   = kOffBars + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmem + 16;
+static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
 
 struct Bars {
     uint64_t* bd_full;   // [kDataStages]
@@ -113,16 +122,79 @@ __device__ __forceinline__ void topn_insert(float (&t)[NTOP], float x) {
     t[0] = fmaxf(t[0], x);
 }
 
-// slot rows are XOR-swizzled in 16-byte units so that 8 consecutive rows hit 8 different bank groups
-__device__ __forceinline__ void slot_store(unsigned char* slot_row, int r, const float (&v)[32]) {
+// record = the 32 scores of a row's best granule, kept as fp16 (64 B) in chunk-major order so that a warp's
+// 16-byte stores are contiguous (conflict free).  fp16 is relative, the final scan widens its threshold.
+__device__ __forceinline__ void record_store(unsigned char* slots, int rec, const float (&v)[32]) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        float4 q = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        *reinterpret_cast<float4*>(slot_row + ((i ^ (r & 7)) << 4)) = q;
+    for (int c = 0; c < 4; ++c) {
+        __half2 h0 = __floats2half2_rn(v[8 * c + 0], v[8 * c + 1]);
+        __half2 h1 = __floats2half2_rn(v[8 * c + 2], v[8 * c + 3]);
+        __half2 h2 = __floats2half2_rn(v[8 * c + 4], v[8 * c + 5]);
+        __half2 h3 = __floats2half2_rn(v[8 * c + 6], v[8 * c + 7]);
+        uint4 q;
+        q.x = *reinterpret_cast<uint32_t*>(&h0); q.y = *reinterpret_cast<uint32_t*>(&h1);
+        q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(slots + (c * kRecords + rec) * 16) = q;
     }
 }
-__device__ __forceinline__ float slot_load(const unsigned char* slot_row, int r, int col) {
-    return *reinterpret_cast<const float*>(slot_row + (((col >> 2) ^ (r & 7)) << 4) + ((col & 3) << 2));
+
+// per-row running state of one row tile
+template <int NTOP>
+struct RowState {
+    float m1, m2, thr;      // ARGMAX: best granule max, best "other" max, m1 - margin
+    int   best_chunk;
+    float top[NTOP];        // THRESH: largest granule maxima, descending
+    float T;                // COLLECT: threshold
+    int64_t pos, row;
+    bool  valid;
+};
+
+template <int MODE, int NTOP>
+__device__ __forceinline__ void consume(const float (&v)[32], int chunk, RowState<NTOP>& st, float margin,
+                                        const CoarseParams& p, unsigned char* slots, int rec) {
+    if (MODE == MODE_DUMP) {
+        if (st.valid && st.pos < p.dump_rows) {
+            float4* dst = reinterpret_cast<float4*>(p.dump + st.pos * p.kpad + chunk * kChunk);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+        return;
+    }
+    const float cmax = max32(v);
+    if (MODE == MODE_ARGMAX) {
+        const bool trig = cmax >= st.thr;
+        if (__any_sync(0xffffffffu, trig)) {
+            if (trig) {
+                if (cmax > st.m1) {          // new record: remember the granule
+                    st.m2 = fmaxf(st.m2, st.m1);
+                    st.m1 = cmax;
+                    st.thr = cmax - margin;
+                    st.best_chunk = chunk;
+                    record_store(slots, rec, v);
+                } else {                      // another granule within the margin
+                    st.m2 = fmaxf(st.m2, cmax);
+                }
+            }
+        }
+    } else if (MODE == MODE_THRESH) {
+        topn_insert<NTOP>(st.top, cmax);
+    } else if (MODE == MODE_COLLECT) {
+        const bool trig = cmax >= st.T;
+        if (__any_sync(0xffffffffu, trig)) {
+            if (trig) {
+                // static indices only: a runtime index would push v[] into local memory
+                uint32_t hits = 0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) hits |= (v[i] >= st.T) ? (1u << i) : 0u;
+                while (hits) {
+                    const int i = __ffs(hits) - 1;
+                    hits &= hits - 1;
+                    const int at = atomicAdd(&p.cand_cnt[st.pos], 1);
+                    if (at < p.cand_cap) p.cand[st.pos * p.cand_cap + at] = chunk * kChunk + i;
+                }
+            }
+        }
+    }
 }
 
 }  // namespace
@@ -148,18 +220,18 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
 
     // ---- one-time setup ------------------------------------------------------------------------
     if (threadIdx.x == 0) {
-        // a codebook stage is read by the RT tiles (= RT different issuers) of one chunk
-        for (int i = 0; i < kDataStages; ++i) { mbar_init(&bars.bd_full[i], 1); mbar_init(&bars.bd_empty[i], RT); }
-        for (int i = 0; i < kBiasStages; ++i) { mbar_init(&bars.bb_full[i], 1); mbar_init(&bars.bb_empty[i], RT); }
+        // every codebook stage is released by all four issuers (owners via tcgen05.commit, the others arrive)
+        for (int i = 0; i < kDataStages; ++i) { mbar_init(&bars.bd_full[i], 1); mbar_init(&bars.bd_empty[i], 4); }
+        for (int i = 0; i < kBiasStages; ++i) { mbar_init(&bars.bb_full[i], 1); mbar_init(&bars.bb_empty[i], 4); }
         for (int i = 0; i < 4; ++i) {
-            mbar_init(&bars.a_full[i], 128);
-            mbar_init(&bars.a_empty[i], 4 / RT);   // one commit from each issuer that reads the tile
+            mbar_init(&bars.a_full[i], kLoadWarps);  // one elected lane per loader warp
+            mbar_init(&bars.a_empty[i], 4 / RT);     // one commit from each issuer that reads the tile
             mbar_init(&bars.acc_full[i], 1);
-            mbar_init(&bars.acc_empty[i], 128);
+            mbar_init(&bars.acc_empty[i], 8);        // one elected lane per epilogue warp serving the slot
         }
         fence_mbar_init();
     }
-    if (warp >= kLoadWarp0 && warp < kLoadWarp0 + 4) {
+    if (warp >= kLoadWarp0 && warp < kLoadWarp0 + kLoadWarps) {
         // constant A-side planes of the bias K-step: row = (1, 1, 1, 0, 0, 0, 0, 0 | 0 x 8)
         const int r = threadIdx.x - kLoadWarp0 * 32;
         const __half one = __float2half(1.0f), zero = __float2half(0.0f);
@@ -181,201 +253,250 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
+    // register rebalancing between warpgroups (all 4 warps of a warpgroup execute the same instruction)
+    if (warp < kEpiWarps) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+    } else if (warp < kLoadWarp0 + kLoadWarps) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    } else if (warp < kMmaWarp) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    }
+
     // ============================================================================================
     if (warp < kEpiWarps) {
         // ---------------------------------- EPILOGUE --------------------------------------------
-        const int e  = warp >> 2;                 // warpgroup == accumulator slot
-        const int g  = e % RT;                    // row tile served by this warpgroup
-        const int r  = (warp & 3) * 32 + lane;    // row within the tile == TMEM lane
-        constexpr int G = 4 / RT;                 // warpgroups sharing one row tile
+        constexpr int NS = (RT == 4) ? 2 : 1;       // row tiles (state sets) per thread
+        const int quarter = warp & 3;               // TMEM lane quarter
+        const int half    = (warp >> 2) & 1;        // columns [64*half, 64*half + 64) of every tile
+        const int pair    = warp >> 3;              // serves accumulator slots pair and pair + 2
+        const int rq      = quarter * 32 + lane;    // row within the tile == TMEM lane
         const float margin = p.meta[META_MARGIN];
-        const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(e * kTileCodes);
-        unsigned char* my_slot = smem + kOffSlots + (e * 128 + r) * 128;
-        float4* my_state = reinterpret_cast<float4*>(smem + kOffState) + (e * 128 + r);
-        uint32_t uses = 0;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 64);
+        unsigned char* slots = smem + kOffSlots;
+        float4* state = reinterpret_cast<float4*>(smem + kOffState);
+        const int rec0 = warp * 32 + lane;          // record of state set ss = ss * 512 + rec0
+        uint32_t uses[2] = {0, 0};
+        const bool tracing = (p.trace != nullptr) && blockIdx.x == 0 && warp == 0 && lane == 0;
 
         for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
-            const int64_t pos = (int64_t)blk * rows_blk + g * kTileRows + r;
-            const bool valid = pos < nrows;
-            const int64_t row = valid ? (p.row_list ? (int64_t)p.row_list[pos] : pos) : 0;
-
-            float m1 = -INFINITY, m2 = -INFINITY, thr = -INFINITY;   // ARGMAX
-            int best_chunk = 0;
-            float top[NTOP];                                          // THRESH
+            RowState<NTOP> st[NS];
 #pragma unroll
-            for (int i = 0; i < NTOP; ++i) top[i] = -INFINITY;
-            float T = INFINITY;                                       // COLLECT
-            if (MODE == MODE_COLLECT && valid) T = p.best_val[row] - margin;
-
-            for (int c = e / RT; c < nchunks; c += G) {
-                mbar_wait(&bars.acc_full[e], uses & 1);
-                ++uses;
-                tc_fence_after();
-#pragma unroll 1
-                for (int q = 0; q < 4; ++q) {
-                    float v[32];
-                    tmem_ld32(t_lane + q * kChunk, v);
-                    tmem_ld_wait();
-                    const int chunk = c * 4 + q;
-                    if (MODE == MODE_DUMP) {
-                        if (valid && pos < p.dump_rows) {
-                            float4* dst = reinterpret_cast<float4*>(p.dump + pos * p.kpad + chunk * kChunk);
+            for (int ss = 0; ss < NS; ++ss) {
+                const int g = (RT == 4) ? pair + 2 * ss : (RT == 2 ? pair : 0);
+                st[ss].pos = (int64_t)blk * rows_blk + g * kTileRows + rq;
+                st[ss].valid = st[ss].pos < nrows;
+                st[ss].row = st[ss].valid ? (p.row_list ? (int64_t)p.row_list[st[ss].pos] : st[ss].pos) : 0;
+                st[ss].m1 = st[ss].m2 = st[ss].thr = -INFINITY;
+                st[ss].best_chunk = 0;
 #pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                        }
-                        continue;
-                    }
-                    const float cmax = max32(v);
-                    if (MODE == MODE_ARGMAX) {
-                        const bool trig = cmax >= thr;
-                        if (__any_sync(0xffffffffu, trig)) {
-                            if (trig) {
-                                if (cmax > m1) {          // new record: remember the granule
-                                    m2 = fmaxf(m2, m1);
-                                    m1 = cmax;
-                                    thr = m1 - margin;
-                                    best_chunk = chunk;
-                                    slot_store(my_slot, r, v);
-                                } else {                  // another granule within the margin
-                                    m2 = fmaxf(m2, cmax);
-                                }
-                            }
-                        }
-                    } else if (MODE == MODE_THRESH) {
-                        topn_insert<NTOP>(top, cmax);
-                    } else if (MODE == MODE_COLLECT) {
-                        const bool trig = cmax >= T;
-                        if (__any_sync(0xffffffffu, trig)) {
-                            if (trig) {
-                                // static indices only: a runtime index would push v[] into local memory
-                                uint32_t hits = 0;
-#pragma unroll
-                                for (int i = 0; i < 32; ++i) hits |= (v[i] >= T) ? (1u << i) : 0u;
-                                while (hits) {
-                                    const int i = __ffs(hits) - 1;
-                                    hits &= hits - 1;
-                                    const int at = atomicAdd(&p.cand_cnt[pos], 1);
-                                    if (at < p.cand_cap) p.cand[pos * p.cand_cap + at] = chunk * kChunk + i;
-                                }
-                            }
-                        }
-                    }
-                }
-                tc_fence_before();
-                mbar_arrive(&bars.acc_empty[e]);
+                for (int i = 0; i < NTOP; ++i) st[ss].top[i] = -INFINITY;
+                st[ss].T = INFINITY;
+                if (MODE == MODE_COLLECT && st[ss].valid) st[ss].T = p.best_val[st[ss].row] - margin;
             }
 
-            // ---- end of row block: merge the warpgroups that shared this row tile, emit ----------
+            for (int c = 0; c < nchunks; ++c) {
+#pragma unroll
+                for (int si = 0; si < 2; ++si) {
+                    const int s = pair + 2 * si;                 // accumulator slot
+                    if (((s - c * RT) & 3) >= RT) continue;      // no tile of this chunk lives in slot s
+                    constexpr int kZero = 0;
+                    const int ss = (RT == 4) ? si : kZero;
+                    mbar_wait(&bars.acc_full[s], uses[si] & 1);
+                    if (tracing && si == 0 && uses[0] < 512) p.trace[uses[0] * 8 + 2] = clock64();
+                    ++uses[si];
+                    tc_fence_after();
+                    float va[32], vb[32];
+                    if (!(p.debug_flags & 1)) {
+                        tmem_ld32(t_lane + (uint32_t)(s * kTileCodes), va);
+                        tmem_ld32(t_lane + (uint32_t)(s * kTileCodes + kChunk), vb);
+                        tmem_ld_wait();
+                    }
+                    // both granules are in registers: hand the accumulator back before reducing them
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars.acc_empty[s]);
+                    if (tracing && si == 0 && uses[0] <= 512) p.trace[(uses[0] - 1) * 8 + 3] = clock64();
+                    if (p.debug_flags & 1) continue;             // timing experiment: no epilogue work
+                    consume<MODE, NTOP>(va, c * 4 + 2 * half, st[ss], margin, p, slots, ss * 512 + rec0);
+                    consume<MODE, NTOP>(vb, c * 4 + 2 * half + 1, st[ss], margin, p, slots, ss * 512 + rec0);
+                    if (tracing && si == 0 && uses[0] <= 512) p.trace[(uses[0] - 1) * 8 + 4] = clock64();
+                }
+            }
+
+            // ---- end of row block: merge the threads that shared each row, emit ----------------------
+            // a row's columns were split over 2 threads (column halves); with RT == 1 also over the 2 pairs
+            constexpr int NP = (RT == 1) ? 2 : 1;
+            const int bar_id = (RT == 1) ? 1 : 1 + pair;
+            const int bar_n  = (RT == 1) ? 512 : 256;
+            const bool leader = (half == 0) && (RT != 1 || pair == 0);
             if (MODE == MODE_ARGMAX) {
-                if (G > 1) {
-                    *my_state = make_float4(m1, m2, __int_as_float(best_chunk), 0.f);
-                    named_bar_sync(1 + g, G * 128);
-                }
-                if (e < RT) {
-                    float M = m1, m2all = m2;
-                    if (G > 1) {
 #pragma unroll
-                        for (int j = 1; j < G; ++j) {
-                            const float4 s = reinterpret_cast<const float4*>(smem + kOffState)[(e + j * RT) * 128 + r];
-                            M = fmaxf(M, s.x);
-                            m2all = fmaxf(m2all, s.y);
-                        }
-                    }
-                    const float thrF = M - margin;
-                    int cnt = 0, col = -1;
+                for (int ss = 0; ss < NS; ++ss)
+                    state[ss * 512 + rec0] = make_float4(st[ss].m1, st[ss].m2, __int_as_float(st[ss].best_chunk), 0.f);
+                named_bar_sync(bar_id, bar_n);
+                if (leader) {
 #pragma unroll
-                    for (int j = 0; j < G; ++j) {
-                        const int ee = e + j * RT;
-                        float mj = m1;
-                        int cj = best_chunk;
-                        if (j > 0) {
-                            const float4 s = reinterpret_cast<const float4*>(smem + kOffState)[ee * 128 + r];
-                            mj = s.x;
-                            cj = __float_as_int(s.z);
-                        }
-                        if (mj >= thrF) {
-                            const unsigned char* sl = smem + kOffSlots + (ee * 128 + r) * 128;
-#pragma unroll 1
-                            for (int i = 0; i < 32; ++i) {
-                                if (slot_load(sl, r, i) >= thrF) { ++cnt; col = cj * kChunk + i; }
+                    for (int ss = 0; ss < NS; ++ss) {
+                        float M = -INFINITY, m2all = -INFINITY;
+#pragma unroll
+                        for (int pp = 0; pp < NP; ++pp)
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh) {
+                                const int w2 = quarter + 4 * hh + 8 * ((RT == 1) ? pp : pair);
+                                const float4 sv = state[ss * 512 + w2 * 32 + lane];
+                                M = fmaxf(M, sv.x);
+                                m2all = fmaxf(m2all, sv.y);
                             }
+                        const float thrF = M - margin;
+                        // records are fp16: accept anything that could be >= thrF before rounding
+                        const float thrS = thrF - (fmaxf(fabsf(M), fabsf(thrF)) * 4.8829e-4f + 1e-7f);
+                        int cnt = 0, col = -1;
+#pragma unroll
+                        for (int pp = 0; pp < NP; ++pp)
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh) {
+                                const int w2 = quarter + 4 * hh + 8 * ((RT == 1) ? pp : pair);
+                                const int rec = ss * 512 + w2 * 32 + lane;
+                                const float4 sv = state[rec];
+                                if (sv.x >= thrF) {
+                                    const int cj = __float_as_int(sv.z);
+#pragma unroll
+                                    for (int cc = 0; cc < 4; ++cc) {
+                                        const uint4 q = *reinterpret_cast<const uint4*>(slots + (cc * kRecords + rec) * 16);
+                                        const uint32_t wds[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                                        for (int t = 0; t < 4; ++t) {
+                                            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&wds[t]));
+                                            if (f.x >= thrS) { ++cnt; col = cj * kChunk + cc * 8 + 2 * t; }
+                                            if (f.y >= thrS) { ++cnt; col = cj * kChunk + cc * 8 + 2 * t + 1; }
+                                        }
+                                    }
+                                }
+                            }
+                        const bool flagged = st[ss].valid && ((cnt != 1) || (m2all >= thrF) || (col >= p.k));
+                        if (st[ss].valid) {
+                            p.best_val[st[ss].row] = M;
+                            p.best_col[st[ss].row] = flagged ? -1 : col;
+                        }
+                        const unsigned ball = __ballot_sync(0xffffffffu, flagged);
+                        if (ball) {
+                            int base = 0;
+                            if (lane == 0) base = atomicAdd(&p.counters[CNT_FLAGGED], __popc(ball));
+                            base = __shfl_sync(0xffffffffu, base, 0);
+                            if (flagged) p.flag_rows[base + __popc(ball & ((1u << lane) - 1))] = (int)st[ss].row;
                         }
                     }
-                    const bool flagged = valid && ((cnt != 1) || (m2all >= thrF) || (col >= p.k));
-                    if (valid) {
-                        p.best_val[row] = M;
-                        p.best_col[row] = flagged ? -1 : col;
-                    }
-                    const unsigned ball = __ballot_sync(0xffffffffu, flagged);
-                    if (ball) {
-                        int base = 0;
-                        if (lane == 0) base = atomicAdd(&p.counters[CNT_FLAGGED], __popc(ball));
-                        base = __shfl_sync(0xffffffffu, base, 0);
-                        if (flagged) p.flag_rows[base + __popc(ball & ((1u << lane) - 1))] = (int)row;
-                    }
                 }
-                if (G > 1) named_bar_sync(1 + g, G * 128);
+                named_bar_sync(bar_id, bar_n);
             } else if (MODE == MODE_THRESH) {
-                float* st = reinterpret_cast<float*>(smem + kOffSlots);   // [4][128][8]
-                if (G > 1) {
+                float* tl = reinterpret_cast<float*>(smem + kOffSlots);   // [record][8]
 #pragma unroll
-                    for (int i = 0; i < NTOP; ++i) st[(e * 128 + r) * 8 + i] = top[i];
-                    named_bar_sync(1 + g, G * 128);
-                }
-                if (e < RT) {
-                    if (G > 1) {
+                for (int ss = 0; ss < NS; ++ss)
 #pragma unroll
-                        for (int j = 1; j < G; ++j)
+                    for (int i = 0; i < NTOP; ++i) tl[(ss * 512 + rec0) * 8 + i] = st[ss].top[i];
+                named_bar_sync(bar_id, bar_n);
+                if (leader) {
 #pragma unroll
-                            for (int i = 0; i < NTOP; ++i) topn_insert<NTOP>(top, st[((e + j * RT) * 128 + r) * 8 + i]);
+                    for (int ss = 0; ss < NS; ++ss) {
+#pragma unroll
+                        for (int pp = 0; pp < NP; ++pp)
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh) {
+                                const int w2 = quarter + 4 * hh + 8 * ((RT == 1) ? pp : pair);
+                                if (w2 == warp) continue;
+#pragma unroll
+                                for (int i = 0; i < NTOP; ++i)
+                                    topn_insert<NTOP>(st[ss].top, tl[(ss * 512 + w2 * 32 + lane) * 8 + i]);
+                            }
+                        if (st[ss].valid) {
+                            float kth = st[ss].top[0];
+#pragma unroll
+                            for (int i = 1; i < NTOP; ++i)
+                                if (i < p.topk) kth = st[ss].top[i];
+                            p.best_val[st[ss].row] = kth;
+                        }
                     }
-                    if (valid) {
-                        float kth = top[0];
-#pragma unroll
-                        for (int i = 1; i < NTOP; ++i)
-                            if (i < p.topk) kth = top[i];
-                        p.best_val[row] = kth;
-                    }
                 }
-                if (G > 1) named_bar_sync(1 + g, G * 128);
+                named_bar_sync(bar_id, bar_n);
             }
         }
-    } else if (warp < kLoadWarp0 + 4) {
+    } else if (warp < kLoadWarp0 + kLoadWarps) {
         // ---------------------------------- A LOADER --------------------------------------------
+        // one thread per row.  The exact reference-order norm goes to `denom` (later kernels divide by
+        // it); the fp16 MMA operand itself only needs to be inside the coarse error bound, so it is
+        // produced with one reciprocal and a multiply per element instead of an IEEE division.
         const int r = threadIdx.x - kLoadWarp0 * 32;
         uint32_t bi = 0;
         for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x, ++bi) {
+            const bool skip = (p.debug_flags & 4) && bi > 0;          // timing experiment only
             for (int g = 0; g < RT; ++g) {
                 const int64_t pos = (int64_t)blk * rows_blk + g * kTileRows + r;
-                const bool valid = pos < nrows;
+                const bool valid = pos < nrows && !skip;
                 const int64_t row = valid ? (p.row_list ? (int64_t)p.row_list[pos] : pos) : 0;
-                const float* zr = p.z + row * d;
-                float den = 1.0f;
+                const float4* zr4 = reinterpret_cast<const float4*>(p.z + row * d);
+                float rden = 0.0f;
                 if (valid) {
-                    den = canon_denom([&](int i) { return __ldg(zr + i); }, d, p.norm_mode);
+                    float den;
+                    if (p.norm_mode == 0) {
+                        // canon_norm8 on float4 loads: lane v accumulates x[8c+v]^2 in order of c
+                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f;
+                        for (int j = 0; j < nplanes; ++j) {
+                            const float4 x0 = __ldg(zr4 + 2 * j), x1 = __ldg(zr4 + 2 * j + 1);
+                            a0 = __fadd_rn(a0, __fmul_rn(x0.x, x0.x)); a1 = __fadd_rn(a1, __fmul_rn(x0.y, x0.y));
+                            a2 = __fadd_rn(a2, __fmul_rn(x0.z, x0.z)); a3 = __fadd_rn(a3, __fmul_rn(x0.w, x0.w));
+                            a4 = __fadd_rn(a4, __fmul_rn(x1.x, x1.x)); a5 = __fadd_rn(a5, __fmul_rn(x1.y, x1.y));
+                            a6 = __fadd_rn(a6, __fmul_rn(x1.z, x1.z)); a7 = __fadd_rn(a7, __fmul_rn(x1.w, x1.w));
+                        }
+                        float s = a0;
+                        s = __fadd_rn(s, a1); s = __fadd_rn(s, a2); s = __fadd_rn(s, a3);
+                        s = __fadd_rn(s, a4); s = __fadd_rn(s, a5); s = __fadd_rn(s, a6); s = __fadd_rn(s, a7);
+                        den = __fsqrt_rn(s);
+                    } else {
+                        const float* zp = p.z + row * d;
+                        den = canon_norm_seq([&](int i) { return __ldg(zp + i); }, d);
+                    }
+                    den = den < kNormEps ? kNormEps : den;
                     if (p.denom) p.denom[row] = den;
+                    rden = __frcp_rn(den);
                 }
-                mbar_wait(&bars.a_empty[g], (bi & 1) ^ 1);
-                unsigned char* tile = smem + kOffA + g * a_tile_b + r * 16;
-                for (int j = 0; j < nplanes; ++j) {
+                auto pack8 = [&](int j) {
                     uint4 q = make_uint4(0, 0, 0, 0);
                     if (valid) {
-                        const float4 x0 = __ldg(reinterpret_cast<const float4*>(zr + 8 * j));
-                        const float4 x1 = __ldg(reinterpret_cast<const float4*>(zr + 8 * j + 4));
-                        __half2 h0 = __floats2half2_rn(__fdiv_rn(x0.x, den), __fdiv_rn(x0.y, den));
-                        __half2 h1 = __floats2half2_rn(__fdiv_rn(x0.z, den), __fdiv_rn(x0.w, den));
-                        __half2 h2 = __floats2half2_rn(__fdiv_rn(x1.x, den), __fdiv_rn(x1.y, den));
-                        __half2 h3 = __floats2half2_rn(__fdiv_rn(x1.z, den), __fdiv_rn(x1.w, den));
+                        const float4 x0 = __ldg(zr4 + 2 * j), x1 = __ldg(zr4 + 2 * j + 1);
+                        __half2 h0 = __floats2half2_rn(x0.x * rden, x0.y * rden);
+                        __half2 h1 = __floats2half2_rn(x0.z * rden, x0.w * rden);
+                        __half2 h2 = __floats2half2_rn(x1.x * rden, x1.y * rden);
+                        __half2 h3 = __floats2half2_rn(x1.z * rden, x1.w * rden);
                         q.x = *reinterpret_cast<uint32_t*>(&h0);
                         q.y = *reinterpret_cast<uint32_t*>(&h1);
                         q.z = *reinterpret_cast<uint32_t*>(&h2);
                         q.w = *reinterpret_cast<uint32_t*>(&h3);
                     }
-                    *reinterpret_cast<uint4*>(tile + j * kPlaneBytes) = q;
+                    return q;
+                };
+                unsigned char* tile = smem + kOffA + g * a_tile_b + r * 16;
+                if (nplanes <= 8) {
+                    // D <= 64: the row is converted into registers BEFORE waiting for the tile to be
+                    // released, so the global-load latency overlaps the previous block's MMAs
+                    uint4 q[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) q[j] = (j < nplanes) ? pack8(j) : make_uint4(0, 0, 0, 0);
+                    mbar_wait(&bars.a_empty[g], (bi & 1) ^ 1);
+                    if (!skip) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (j < nplanes) *reinterpret_cast<uint4*>(tile + j * kPlaneBytes) = q[j];
+                    }
+                } else {
+                    mbar_wait(&bars.a_empty[g], (bi & 1) ^ 1);
+                    if (!skip)
+                        for (int j = 0; j < nplanes; ++j) *reinterpret_cast<uint4*>(tile + j * kPlaneBytes) = pack8(j);
                 }
                 fence_proxy_async_smem();
-                mbar_arrive(&bars.a_full[g]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars.a_full[g]);
             }
         }
     } else if (warp == kProdWarp) {
@@ -421,27 +542,35 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
             const uint32_t tacc = tmem_base + (uint32_t)(j * kTileCodes);
             uint32_t uses = 0, bi = 0;
             uint32_t chunk0 = 0;                     // chunks issued by the CTA before this block
+            const bool no_bias = (p.debug_flags & 2) != 0;
+            const bool tracing = (p.trace != nullptr) && blockIdx.x == 0 && j == 0;
             for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x, ++bi, chunk0 += nchunks) {
-                if (j / RT >= nchunks) {
-                    // fewer chunks than issuers: nothing to issue, but the row tile's release barrier
-                    // still expects this issuer once per block (paced by the tile's own arrival)
-                    mbar_wait(&bars.a_full[g], bi & 1);
-                    mbar_arrive(&bars.a_empty[g]);
-                    continue;
-                }
+                // Every issuer walks EVERY chunk so that each shared barrier sees all four issuers once per
+                // phase (an mbarrier parity wait is only meaningful within one phase of the barrier);
+                // it issues MMAs only for the tiles it owns: c % G == j / RT.
                 bool first = true;
-                for (int c = j / RT; c < nchunks; c += G) {
+                for (int c = 0; c < nchunks; ++c) {
+                    const bool own = (c % G) == (j / RT);
                     const uint32_t gc = chunk0 + c;                       // running chunk number
-                    mbar_wait(&bars.acc_empty[j], (uses & 1u) ^ 1u);
-                    ++uses;
-                    if (first) { mbar_wait(&bars.a_full[g], bi & 1); first = false; }
-                    tc_fence_after();
                     const uint32_t itD = gc * nkblk;
+                    const uint32_t sb = gc % kBiasStages;
+                    // operands first, accumulator last: when the epilogue hands the slot back, every MMA of
+                    // the tile is issued back to back
+                    for (int kb = 0; kb < nkblk; ++kb)
+                        mbar_wait(&bars.bd_full[(itD + kb) % kDataStages], ((itD + kb) / kDataStages) & 1);
+                    mbar_wait(&bars.bb_full[sb], (gc / kBiasStages) & 1);
+                    if (!own) {
+                        for (int kb = 0; kb < nkblk; ++kb) mbar_arrive(&bars.bd_empty[(itD + kb) % kDataStages]);
+                        mbar_arrive(&bars.bb_empty[sb]);
+                        continue;
+                    }
+                    if (first) { mbar_wait(&bars.a_full[g], bi & 1); first = false; }
+                    mbar_wait(&bars.acc_empty[j], (uses & 1u) ^ 1u);
+                    if (tracing && uses < 512) p.trace[uses * 8 + 0] = clock64();
+                    ++uses;
+                    tc_fence_after();
                     for (int kb = 0; kb < nkblk; ++kb) {
-                        const uint32_t it = itD + kb;
-                        const uint32_t st = it % kDataStages;
-                        mbar_wait(&bars.bd_full[st], (it / kDataStages) & 1);
-                        tc_fence_after();
+                        const uint32_t st = (itD + kb) % kDataStages;
                         const int nsteps = min(8, nplanes - 8 * kb) >> 1;
                         uint64_t da = dA + (uint64_t)(kb * (kKblkBytes >> 4));
                         uint64_t db = dBD0 + (uint64_t)(st * (kKblkBytes >> 4));
@@ -452,13 +581,17 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                         }
                         umma_commit(&bars.bd_empty[st]);
                     }
-                    const uint32_t sb = gc % kBiasStages;
-                    mbar_wait(&bars.bb_full[sb], (gc / kBiasStages) & 1);
-                    tc_fence_after();
-                    umma_f16(tacc, dOnes, dBB0 + (uint64_t)(sb * (kBiasBytes >> 4)), idesc, 1u);
-                    umma_commit(&bars.bb_empty[sb]);
+                    if (!no_bias) umma_f16(tacc, dOnes, dBB0 + (uint64_t)(sb * (kBiasBytes >> 4)), idesc, 1u);
                     umma_commit(&bars.acc_full[j]);
+                    umma_commit(&bars.bb_empty[sb]);
                     if (c + G >= nchunks) umma_commit(&bars.a_empty[g]);   // this issuer's last tile of the block
+                    if (tracing && uses <= 512) p.trace[(uses - 1) * 8 + 1] = clock64();
+                }
+                if (first) {
+                    // fewer chunks than issuers: this issuer owned no tile, but the row tile's release
+                    // barrier still expects it once per block (paced by the tile's own arrival)
+                    mbar_wait(&bars.a_full[g], bi & 1);
+                    mbar_arrive(&bars.a_empty[g]);
                 }
             }
         }

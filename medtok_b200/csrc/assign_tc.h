@@ -37,6 +37,9 @@ struct CoarseParams {
     // shared-memory descriptor strides (kept as parameters so tests can probe the encoding)
     uint32_t     lbo_bytes;  // 2048
     uint32_t     sbo_bytes;  // 128
+    long long*   trace;       // optional clock64 trace of slot 0 of CTA 0 (mtvq_debug_set_trace), 8 x int64 per tile
+    int          debug_flags; // timing experiments only (MTVQ_DBG): 1 = epilogue does no work, 2 = no bias K-step,
+                              // 4 = A tiles loaded once per CTA; results are wrong when set
 };
 
 // rows per CTA block = 128 * row_tiles; bounded by shared memory (row_tiles * d <= 256)

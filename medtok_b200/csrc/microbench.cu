@@ -52,38 +52,64 @@ __global__ void __launch_bounds__(1024, 1) fmnmx_bench_kernel(int iters, const f
     if (best == 123.456f) sink[threadIdx.x] = best;
 }
 
-// which = 2: back-to-back tcgen05.mma (M=128, N=warps*8 in {64,128,256}, K=16, fp16, operands in smem)
-__global__ void __launch_bounds__(128, 1) umma_bench_kernel(int iters, int n_cols, float* sink) {
+// which = 2: back-to-back tcgen05.mma (M=128, N in {64,128,256}, K=16, fp16, operands in smem).
+// which = 3: the same while 16 more warps stream tcgen05.ld.32x32b.x32 from the OTHER half of tensor memory
+//            (contention between accumulator read-modify-write and epilogue loads).
+// which = 4: the same while 16 more warps stream 16-byte shared-memory stores (operand-fetch contention).
+__global__ void __launch_bounds__(640, 1) umma_bench_kernel(int iters, int n_cols, int mode, float* sink) {
     extern __shared__ __align__(1024) unsigned char sm[];
     __shared__ uint32_t tmem_ptr;
     __shared__ uint64_t bar;
+    __shared__ volatile int done;
     const int warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < 49152 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = 0x3c003c00u;  // 1.0h
-    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); done = 0; }
     fence_proxy_async_smem();
     if (warp == 0) { tmem_alloc(&tmem_ptr, 512); tmem_relinquish(); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (warp == 1 && elect_one()) {
-        const uint32_t idesc = umma_idesc_f16(128, n_cols);
-        const uint64_t da = umma_smem_desc(smem_u32(sm), 2048, 128);
-        const uint64_t db = umma_smem_desc(smem_u32(sm + 16384), 4096, 128);
-        for (int it = 0; it < iters; ++it) {
-            // 4 K-steps into alternating accumulators, like one tile of the real kernel
-            const uint32_t tacc = tmem_ptr + (uint32_t)((it & 1) * 256);
-            umma_f16(tacc, da, db, idesc, 0);
-            umma_f16(tacc, da + 256, db + 512, idesc, 1);
-            umma_f16(tacc, da + 512, db + 1024, idesc, 1);
-            umma_f16(tacc, da + 768, db + 1536, idesc, 1);
+    float acc = 0.f;
+    if (warp == 1) {
+        if (elect_one()) {
+            const uint32_t idesc = umma_idesc_f16(128, n_cols);
+            const uint64_t da = umma_smem_desc(smem_u32(sm), 2048, 128);
+            const uint64_t db = umma_smem_desc(smem_u32(sm + 16384), 4096, 128);
+            for (int it = 0; it < iters; ++it) {
+                // 4 K-steps into one accumulator, like one tile of the real kernel (accumulators in columns 0..255)
+                const uint32_t tacc = tmem_ptr + (uint32_t)((it & 1) * (256 - n_cols > 0 ? n_cols : 0));
+                umma_f16(tacc, da, db, idesc, 0);
+                umma_f16(tacc, da + 256, db + 512, idesc, 1);
+                umma_f16(tacc, da + 512, db + 1024, idesc, 1);
+                umma_f16(tacc, da + 768, db + 1536, idesc, 1);
+            }
+            umma_commit(&bar);
+            mbar_wait(&bar, 0);
+            done = 1;
         }
-        umma_commit(&bar);
-        mbar_wait(&bar, 0);
+    } else if (warp >= 4 && mode == 3) {
+        const uint32_t base = tmem_ptr + ((uint32_t)((warp & 3) * 32) << 16) + 256;   // columns 256..511
+        while (!done) {
+#pragma unroll 1
+            for (int c = 0; c < 256; c += 32) {
+                float v[32];
+                tmem_ld32(base + c, v);
+                tmem_ld_wait();
+                acc += v[0] + v[31];
+            }
+        }
+    } else if (warp >= 4 && mode == 4) {
+        uint4* dst = reinterpret_cast<uint4*>(sm + 49152) + (threadIdx.x - 128);
+        uint4 val = make_uint4(threadIdx.x, 1, 2, 3);
+        while (!done) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { dst[0] = val; val.x += 1; }
+        }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_ptr, 512); }
-    if (sink == nullptr) sm[0] = 1;
+    if (acc == 123.456f) sink[threadIdx.x] = acc;
 }
 
 cudaError_t run_microbench(int which, int warps, int iters, int num_sms, double* result_host, cudaStream_t stream) {
@@ -98,9 +124,9 @@ cudaError_t run_microbench(int which, int warps, int iters, int num_sms, double*
     cudaEventCreate(&t0); cudaEventCreate(&t1);
     for (int rep = 0; rep < 2; ++rep) {
         cudaEventRecord(t0, stream);
-        if (which == 2) {
+        if (which >= 2) {
             cudaFuncSetAttribute(umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
-            umma_bench_kernel<<<num_sms, 128, 65536, stream>>>(iters, warps * 8, buf + 1024);
+            umma_bench_kernel<<<num_sms, which == 2 ? 128 : 640, 65536, stream>>>(iters, warps * 8, which, buf + 1024);
         } else if (which == 0) tmem_ld_bench_kernel<<<num_sms, warps * 32, 0, stream>>>(iters, buf + 1024);
         else fmnmx_bench_kernel<<<num_sms, warps * 32, 0, stream>>>(iters, buf, buf + 1024);
         cudaEventRecord(t1, stream);
@@ -109,7 +135,7 @@ cudaError_t run_microbench(int which, int warps, int iters, int num_sms, double*
     float ms = 0.f;
     cudaEventElapsedTime(&ms, t0, t1);
     result_host[0] = ms;
-    if (which == 2) result_host[1] = (double)num_sms * iters * 4.0 * 128.0 * (warps * 8) * 16.0 * 2.0;   // flops
+    if (which >= 2) result_host[1] = (double)num_sms * iters * 4.0 * 128.0 * (warps * 8) * 16.0 * 2.0;   // flops
     else if (which == 0) result_host[1] = (double)num_sms * warps * iters * 16.0 * 32.0 * 32.0 * 4.0;   // bytes
     else result_host[1] = (double)num_sms * warps * 32.0 * iters * 32.0;                               // scores
     cudaEventDestroy(t0); cudaEventDestroy(t1);

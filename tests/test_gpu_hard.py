@@ -76,7 +76,10 @@ def test_coarse_scores_match_fp16_model(dev):
         ref = zf.half().double() @ w.half().double().t() - 0.5 * (w.double() ** 2).sum(1)
         got = scores[:, :k].double()
         err = (got - ref).abs().max().item()
-        assert err < 2e-5, f"(n={n}, d={d}, k={k}) coarse score mismatch, max err {err}"
+        # the loader forms the fp16 operand as fp16(x * (1/den)); against fp16(x / den) an element can land on
+        # the neighbouring fp16 value (<= 2^-11 |z_i w_i| each), far inside the kernel's error bound eps ~ 1e-3
+        assert err < 2e-4, f"(n={n}, d={d}, k={k}) coarse score mismatch, max err {err}"
+        assert (got - ref).abs().mean().item() < 2e-6
         assert (scores[:, k:] < -1e4).all()            # padding codes can never win
 
 

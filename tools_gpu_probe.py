@@ -28,9 +28,10 @@ if what in ("all", "micro"):
         for warps in (4, 8, 16, 32):
             _lib.check(L.mtvq_microbench(which, warps, 2000, res, st), "microbench")
             mb[f"{label}_w{warps}"] = res[1] / (res[0] * 1e-3) / 1e9
-    for ncols in (64, 128, 256):
-        _lib.check(L.mtvq_microbench(2, ncols // 8, 20000, res, st), "microbench umma")
-        mb[f"umma_TFLOPs_n{ncols}"] = res[1] / (res[0] * 1e-3) / 1e12
+    for which, tag in ((2, "alone"), (3, "with_tmem_ld"), (4, "with_sts")):
+        for ncols in (128, 256):
+            _lib.check(L.mtvq_microbench(which, ncols // 8, 20000, res, st), "microbench umma")
+            mb[f"umma_TFLOPs_n{ncols}_{tag}"] = res[1] / (res[0] * 1e-3) / 1e12
     out["microbench"] = mb
     print(json.dumps(mb, indent=1))
 
@@ -79,6 +80,45 @@ if what in ("all", "time"):
     out["time_c2_ms"] = ms
     out["c2_counters"] = _lib.debug_counters(q._ws.buf, n, d, k)
     print("hard forward C2 ms:", ms, out["c2_counters"])
+
+if what == "kern":
+    # time only the dominant kernel (coarse ARGMAX) through the profiling hook; MTVQ_DBG selects experiments
+    from medtok_b200.norm_ema_quantizer import hard_assign
+    n, d, k = 1 << 20, int(os.environ.get("PROBE_D", "64")), int(os.environ.get("PROBE_K", "8192"))
+    torch.manual_seed(0)
+    z = torch.randn(n, d, device=dev)
+    w = torch.nn.functional.normalize(torch.randn(k, d, device=dev), dim=-1)
+    wsx = _lib.Workspace()
+    ms = []
+    for i in range(6):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); b.record(); torch.cuda.synchronize()
+        _lib.set_profile_events(a, b)
+        hard_assign(z, w, workspace=wsx)
+        torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b))
+    # slot-loop trace of CTA 0 / slot 0 (clock64 stamps)
+    tr = torch.zeros(512 * 8, dtype=torch.int64, device=dev)
+    _lib.check(L.mtvq_debug_set_trace(_lib.ptr(tr)), "set_trace")
+    hard_assign(z, w, workspace=wsx)
+    torch.cuda.synchronize()
+    _lib.check(L.mtvq_debug_set_trace(None), "set_trace")
+    t = tr.view(512, 8).cpu().numpy()[8:200]
+    import numpy as np
+    def med(a): return float(np.median(a))
+    out["trace"] = {
+        "issue_span (got slot -> commits issued)": med(t[:, 1] - t[:, 0]),
+        "mma_done_seen (got slot -> epilogue sees tile)": med(t[:, 2] - t[:, 0]),
+        "epi_to_release (sees tile -> slot released)": med(t[:, 3] - t[:, 2]),
+        "release_to_reissue (slot released -> issuer got slot again)": med(t[1:, 0] - t[:-1, 3]),
+        "last_granule (release -> tile reduced)": med(t[:, 4] - t[:, 3]),
+        "slot_loop (issuer got slot -> next got slot)": med(t[1:, 0] - t[:-1, 0]),
+    }
+    print("TRACE", json.dumps(out["trace"]))
+    out["kern_ms"] = ms
+    out["dbg"] = os.environ.get("MTVQ_DBG", "0")
+    print("DBG", out["dbg"], "d", d, "k", k, "coarse kernel ms:", [round(x, 3) for x in ms], "TFLOP/s:",
+          round(2.0 * n * k * d / (min(ms) * 1e-3) / 1e12, 1), _lib.debug_counters(wsx.buf, n, d, k))
 
 os.makedirs("gpurun_out", exist_ok=True)
 tag = what + ("_swap" if os.environ.get("MTVQ_DESC_SWAP") == "1" else "")
