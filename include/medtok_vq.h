@@ -103,13 +103,14 @@ MTVQ_API int mtvq_hard_assign(const float *z, int64_t n, int d, int norm_mode, c
 MTVQ_API int mtvq_hard_assign_exact(const float *z, int64_t n, int d, int norm_mode, const float *weight, int k,
                            int64_t *idx, float *denom, void *workspace, size_t workspace_bytes, void *stream);
 
-/* z_q = zf + (w[idx] - zf), sse += sum (w[idx]-zf)^2 (fp64), bins[idx] += 1 (F.embedding :117-118,
- * one_hot/sum :183-194 without the N x K one-hot).  denom as written by mtvq_hard_assign. */
+/* z_q = zf + (w[idx] - zf) and sse += sum (w[idx]-zf)^2 (fp64) into `stats` (F.embedding :117-118,
+ * mse/straight-through :212-214).  denom as written by mtvq_hard_assign. */
 MTVQ_API int mtvq_gather_ste(const float *z, const float *denom, const float *weight, const int64_t *idx,
                     int64_t n, int d, int k, float *z_q, double *stats, void *stream);
 
-/* embed_sum[k,d] += sum_{n: idx_n = k} zf_n  (replaces the second N x K GEMM, :202): counting sort of
- * the rows by code + fp64 segmented sums.  Needs bins in `stats` (mtvq_gather_ste). */
+/* bins[k] += #{n: idx_n = k} (one_hot/sum :183-194 without the N x K one-hot), rows += n, and
+ * embed_sum[k,d] += sum_{n: idx_n = k} zf_n (replaces the second N x K GEMM, :202): warp-aggregated
+ * histogram, counting sort of the rows by code, fp64 segmented sums. */
 MTVQ_API int mtvq_code_sums(const float *z, const float *denom, const int64_t *idx, int64_t n, int d, int k,
                    double *stats, void *workspace, size_t workspace_bytes, void *stream);
 

@@ -151,7 +151,7 @@ static int hard_assign_impl(const float* z, int64_t n, int d, int norm_mode, con
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float* den = denom ? denom : ws.denom;
     if (int r = assign_into_ws(z, n, d, norm_mode, weight, k, den, ws, di, exact_only, st)) return r;
-    if (n > 0) MTVQ_CUDA(launch_emit_idx(ws.best_col, n, idx, di.num_sms, st), "emit_idx");
+    if (n > 0) MTVQ_CUDA(launch_emit_idx(ws.best_col, n, idx, ws.bins_i32, k, di.num_sms, st), "emit_idx");
     return 0;
 }
 
@@ -185,9 +185,11 @@ int mtvq_code_sums(const float* z, const float* denom, const int64_t* idx, int64
     if (int r = device_info(&di)) return r;
     Workspace ws = carve(workspace, n, d, k, 1);
     if (ws.total_bytes > workspace_bytes) return fail(MTVQ_ERR_WORKSPACE, "workspace too small%s", "");
-    if (n > 0)
-        MTVQ_CUDA(launch_code_sums(z, denom, idx, n, d, k, stats, ws, di.num_sms, static_cast<cudaStream_t>(stream)),
-                  "code_sums");
+    if (n > 0) {
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        MTVQ_CUDA(launch_hist_idx64(idx, n, ws.bins_i32, k, di.num_sms, st), "hist");
+        MTVQ_CUDA(launch_code_sums(z, denom, idx, n, d, k, stats, ws, true, di.num_sms, st), "code_sums");
+    }
     return 0;
 }
 
@@ -226,9 +228,9 @@ int mtvq_hard_forward(const float* z, int64_t n, int d, int norm_mode, float* we
     MTVQ_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * mtvq_stats_len(d, k), st), "memset stats");
     if (int r = assign_into_ws(z, n, d, norm_mode, weight, k, ws.denom, ws, di, false, st)) return r;
     if (n > 0) {
-        MTVQ_CUDA(launch_emit_idx(ws.best_col, n, idx, di.num_sms, st), "emit_idx");
+        MTVQ_CUDA(launch_emit_idx(ws.best_col, n, idx, ws.bins_i32, k, di.num_sms, st), "emit_idx");
         MTVQ_CUDA(launch_gather_ste(z, ws.denom, weight, idx, n, d, k, z_q, stats, di.num_sms, st), "gather_ste");
-        if (upd_w) MTVQ_CUDA(launch_code_sums(z, ws.denom, idx, n, d, k, stats, ws, di.num_sms, st), "code_sums");
+        MTVQ_CUDA(launch_code_sums(z, ws.denom, idx, n, d, k, stats, ws, upd_w, di.num_sms, st), "code_sums");
     }
     if (flags & MTVQ_F_SKIP_FINALIZE) {
         MTVQ_CUDA(launch_loss(stats, k, d, beta, loss, st), "loss");

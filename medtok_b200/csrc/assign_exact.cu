@@ -37,6 +37,15 @@ __global__ void codebook_prep_kernel(const float* __restrict__ w, int k, int kpa
     auto elem = [&](int i) { return normalize ? __fdiv_rn(__ldg(wr + i), den) : __ldg(wr + i); };
     const float c2 = canon_sumsq(elem, d);
     cc[code] = c2;
+    {   // spread of the squared norms around code 0's: if it is negligible the kernels drop the bias K-step
+        const float* w0 = w;
+        float den0 = 1.0f;
+        if (normalize) den0 = canon_denom([&](int i) { return __ldg(w0 + i); }, d, 0);
+        const float c0 = canon_sumsq([&](int i) { return normalize ? __fdiv_rn(__ldg(w0 + i), den0) : __ldg(w0 + i); }, d);
+        const float spread = 0.5f * fabsf(c2 - c0);
+        if (spread == spread) atomicMax(reinterpret_cast<int*>(meta + META_SPREAD), __float_as_int(spread));
+        else meta[META_SPREAD] = INFINITY;
+    }
     for (int j = 0; j < nplanes; ++j) {
         __half h[8];
 #pragma unroll
@@ -61,7 +70,7 @@ __global__ void codebook_prep_kernel(const float* __restrict__ w, int k, int kpa
     //   fp16 rounding of both operands: (2^-10 + 2^-22) * ||w||     (Cauchy-Schwarz)
     //   fp16 subnormal flush + fp32 accumulation in the tensor core: 2^-18 * (1 + ||w|| + ||w||^2/2)
     const float nw = sqrtf(c2) * 1.001f;
-    const float eps = 9.7704e-4f * nw + 3.8147e-6f * (1.0f + nw + 0.5f * c2) + 1e-6f;
+    const float eps = 9.7704e-4f * nw + 3.8147e-6f * (1.0f + nw + 0.5f * c2) + 1e-6f + kBiasSkipTol;
     if (eps == eps) {   // positive floats order like ints
         atomicMax(reinterpret_cast<int*>(meta + META_EPS), __float_as_int(eps));
         atomicMax(reinterpret_cast<int*>(meta + META_MARGIN), __float_as_int(2.0f * eps));
@@ -89,16 +98,24 @@ __global__ void resolve_kernel(const float* __restrict__ z, int d, int norm_mode
         atomicAdd(&counters[CNT_CANDS], cnt);
         const float* zr = z + (size_t)row * d;
         const float den = canon_denom([&](int i) { return __ldg(zr + i); }, d, norm_mode);
-        const float zz = canon_sumsq([&](int i) { return __fdiv_rn(__ldg(zr + i), den); }, d);
+        float zf[kMaxDim];                       // normalised row, divided once (local memory, L1 resident)
+        for (int i = 0; i < d; ++i) zf[i] = __fdiv_rn(__ldg(zr + i), den);
+        const float zz = canon_sumsq([&](int i) { return zf[i]; }, d);
         float best = INFINITY;
         int bcol = 0x7fffffff;
         bool any = false;
         for (int j = 0; j < cnt; ++j) {
             const int col = cand[(size_t)p * cand_cap + j];
             if (col >= k) continue;
-            const float* wr = w + (size_t)col * d;
+            const float4* wr = reinterpret_cast<const float4*>(w + (size_t)col * d);
             float dot = 0.0f;
-            for (int i = 0; i < d; ++i) dot = __fmaf_rn(__fdiv_rn(__ldg(zr + i), den), __ldg(wr + i), dot);
+            for (int i = 0; i < d; i += 4) {
+                const float4 wv = __ldg(wr + (i >> 2));
+                dot = __fmaf_rn(zf[i], wv.x, dot);
+                dot = __fmaf_rn(zf[i + 1], wv.y, dot);
+                dot = __fmaf_rn(zf[i + 2], wv.z, dot);
+                dot = __fmaf_rn(zf[i + 3], wv.w, dot);
+            }
             const float dist = canon_dist(zz, cc[col], dot);
             // torch.argmin: smallest value, first index on ties; NaN counts as the minimum
             if (!any || dist < best || (dist == best && col < bcol) || (dist != dist && !(best != best))) {
@@ -247,7 +264,7 @@ cudaError_t launch_codebook_prep(const float* w, int k, int d, int normalize, co
     cudaError_t e = cudaMemsetAsync(ws.meta, 0, sizeof(float) * META_COUNT, stream);
     if (e != cudaSuccess) return e;
     const int kpad = pad_codes(k);
-    codebook_prep_kernel<<<(kpad + 127) / 128, 128, 0, stream>>>(w, k, kpad, d, normalize,
+    codebook_prep_kernel<<<(kpad + 31) / 32, 32, 0, stream>>>(w, k, kpad, d, normalize,
                                                                   static_cast<unsigned char*>(ws.b_image), ws.cc,
                                                                   ws.codes_n, ws.meta);
     return cudaGetLastError();
@@ -255,7 +272,7 @@ cudaError_t launch_codebook_prep(const float* w, int k, int d, int normalize, co
 
 cudaError_t launch_resolve(const float* z, int d, int norm_mode, const float* w, int k, const Workspace& ws,
                            int cand_cap, int num_sms, cudaStream_t stream) {
-    resolve_kernel<<<num_sms * 4, 128, 0, stream>>>(z, d, norm_mode, w, k, ws.cc, ws.flag_rows, ws.cand, ws.cand_cnt,
+    resolve_kernel<<<num_sms * 8, 64, 0, stream>>>(z, d, norm_mode, w, k, ws.cc, ws.flag_rows, ws.cand, ws.cand_cnt,
                                                     cand_cap, ws.best_col, ws.full_rows, ws.counters);
     return cudaGetLastError();
 }

@@ -214,6 +214,14 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
     const int64_t nrows = p.n_rows_dev ? (int64_t)(*p.n_rows_dev) : p.n;
     const int rows_blk  = RT * kTileRows;
     const int nblocks   = (int)((nrows + rows_blk - 1) / rows_blk);
+    // the 64 KB A area holds nreg = 4, 2 or 1 row tiles (D <= 64, <= 128, <= 256); they form a ring over
+    // (block, row tile) so that with RT < nreg the loader runs ahead of the MMAs by whole blocks
+    const uint32_t nreg = (uint32_t)(65536 / a_tile_b) >= 4u ? 4u : ((uint32_t)(65536 / a_tile_b) >= 2u ? 2u : 1u);
+
+    // bias K-step (-||w||^2/2): needed unless every code has the same squared norm (then it is a constant
+    // shift of all scores); padding codes rely on it to lose, so it stays on when K is not a tile multiple
+    const bool use_bias = !(p.debug_flags & 2) &&
+                          (MODE == MODE_DUMP || p.k != p.kpad || !(p.meta[META_SPREAD] <= kBiasSkipTol));
 
     Bars bars = carve_bars(smem);
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kOffTmem);
@@ -476,27 +484,28 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                     }
                     return q;
                 };
-                unsigned char* tile = smem + kOffA + g * a_tile_b + r * 16;
+                const uint32_t aq = bi * RT + g, areg = aq % nreg, apar = (aq / nreg) & 1;   // A region ring
+                unsigned char* tile = smem + kOffA + areg * a_tile_b + r * 16;
                 if (nplanes <= 8) {
                     // D <= 64: the row is converted into registers BEFORE waiting for the tile to be
                     // released, so the global-load latency overlaps the previous block's MMAs
                     uint4 q[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) q[j] = (j < nplanes) ? pack8(j) : make_uint4(0, 0, 0, 0);
-                    mbar_wait(&bars.a_empty[g], (bi & 1) ^ 1);
+                    mbar_wait(&bars.a_empty[areg], apar ^ 1);
                     if (!skip) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
                             if (j < nplanes) *reinterpret_cast<uint4*>(tile + j * kPlaneBytes) = q[j];
                     }
                 } else {
-                    mbar_wait(&bars.a_empty[g], (bi & 1) ^ 1);
+                    mbar_wait(&bars.a_empty[areg], apar ^ 1);
                     if (!skip)
                         for (int j = 0; j < nplanes; ++j) *reinterpret_cast<uint4*>(tile + j * kPlaneBytes) = pack8(j);
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bars.a_full[g]);
+                if (lane == 0) mbar_arrive(&bars.a_full[areg]);
             }
         }
     } else if (warp == kProdWarp) {
@@ -515,12 +524,14 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                         bulk_g2s(smem + kOffBData + st * kKblkBytes, tile + (size_t)kb * kKblkBytes, bytes,
                                  &bars.bd_full[st]);
                     }
-                    const int sb = itB % kBiasStages;
-                    mbar_wait(&bars.bb_empty[sb], ((itB / kBiasStages) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&bars.bb_full[sb], kBiasBytes);
-                    bulk_g2s(smem + kOffBBias + sb * kBiasBytes, tile + (size_t)nplanes * kPlaneBytes, kBiasBytes,
-                             &bars.bb_full[sb]);
-                    ++itB;
+                    if (use_bias) {
+                        const int sb = itB % kBiasStages;
+                        mbar_wait(&bars.bb_empty[sb], ((itB / kBiasStages) & 1) ^ 1);
+                        mbar_arrive_expect_tx(&bars.bb_full[sb], kBiasBytes);
+                        bulk_g2s(smem + kOffBBias + sb * kBiasBytes, tile + (size_t)nplanes * kPlaneBytes, kBiasBytes,
+                                 &bars.bb_full[sb]);
+                        ++itB;
+                    }
                 }
             }
         }
@@ -535,20 +546,21 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
             const uint32_t lbo = p.lbo_bytes, sbo = p.sbo_bytes;
             // descriptors are built once; per MMA only the 14-bit start-address field moves
             // (units of 16 B: one K-step = 2 planes = 256, one K-block / data stage = 1024)
-            const uint64_t dA = umma_smem_desc(smem_u32(smem + kOffA + g * a_tile_b), lbo, sbo);
+            const uint64_t dA0 = umma_smem_desc(smem_u32(smem + kOffA), lbo, sbo);
             const uint64_t dOnes = umma_smem_desc(smem_u32(smem + kOffOnes), lbo, sbo);
             const uint64_t dBD0 = umma_smem_desc(smem_u32(smem + kOffBData), lbo, sbo);
             const uint64_t dBB0 = umma_smem_desc(smem_u32(smem + kOffBBias), lbo, sbo);
             const uint32_t tacc = tmem_base + (uint32_t)(j * kTileCodes);
             uint32_t uses = 0, bi = 0;
             uint32_t chunk0 = 0;                     // chunks issued by the CTA before this block
-            const bool no_bias = (p.debug_flags & 2) != 0;
             const bool tracing = (p.trace != nullptr) && blockIdx.x == 0 && j == 0;
             for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x, ++bi, chunk0 += nchunks) {
                 // Every issuer walks EVERY chunk so that each shared barrier sees all four issuers once per
                 // phase (an mbarrier parity wait is only meaningful within one phase of the barrier);
                 // it issues MMAs only for the tiles it owns: c % G == j / RT.
                 bool first = true;
+                const uint32_t aq = bi * RT + g, areg = aq % nreg, apar = (aq / nreg) & 1;   // A region ring
+                const uint64_t dA = dA0 + (uint64_t)(areg * ((uint32_t)a_tile_b >> 4));
                 for (int c = 0; c < nchunks; ++c) {
                     const bool own = (c % G) == (j / RT);
                     const uint32_t gc = chunk0 + c;                       // running chunk number
@@ -558,13 +570,13 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                     // the tile is issued back to back
                     for (int kb = 0; kb < nkblk; ++kb)
                         mbar_wait(&bars.bd_full[(itD + kb) % kDataStages], ((itD + kb) / kDataStages) & 1);
-                    mbar_wait(&bars.bb_full[sb], (gc / kBiasStages) & 1);
+                    if (use_bias) mbar_wait(&bars.bb_full[sb], (gc / kBiasStages) & 1);
                     if (!own) {
                         for (int kb = 0; kb < nkblk; ++kb) mbar_arrive(&bars.bd_empty[(itD + kb) % kDataStages]);
-                        mbar_arrive(&bars.bb_empty[sb]);
+                        if (use_bias) mbar_arrive(&bars.bb_empty[sb]);
                         continue;
                     }
-                    if (first) { mbar_wait(&bars.a_full[g], bi & 1); first = false; }
+                    if (first) { mbar_wait(&bars.a_full[areg], apar); first = false; }
                     mbar_wait(&bars.acc_empty[j], (uses & 1u) ^ 1u);
                     if (tracing && uses < 512) p.trace[uses * 8 + 0] = clock64();
                     ++uses;
@@ -581,17 +593,17 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                         }
                         umma_commit(&bars.bd_empty[st]);
                     }
-                    if (!no_bias) umma_f16(tacc, dOnes, dBB0 + (uint64_t)(sb * (kBiasBytes >> 4)), idesc, 1u);
+                    if (use_bias) umma_f16(tacc, dOnes, dBB0 + (uint64_t)(sb * (kBiasBytes >> 4)), idesc, 1u);
                     umma_commit(&bars.acc_full[j]);
-                    umma_commit(&bars.bb_empty[sb]);
-                    if (c + G >= nchunks) umma_commit(&bars.a_empty[g]);   // this issuer's last tile of the block
+                    if (use_bias) umma_commit(&bars.bb_empty[sb]);
+                    if (c + G >= nchunks) umma_commit(&bars.a_empty[areg]);   // this issuer's last tile of the block
                     if (tracing && uses <= 512) p.trace[(uses - 1) * 8 + 1] = clock64();
                 }
                 if (first) {
                     // fewer chunks than issuers: this issuer owned no tile, but the row tile's release
                     // barrier still expects it once per block (paced by the tile's own arrival)
-                    mbar_wait(&bars.a_full[g], bi & 1);
-                    mbar_arrive(&bars.a_empty[g]);
+                    mbar_wait(&bars.a_full[areg], apar);
+                    mbar_arrive(&bars.a_empty[areg]);
                 }
             }
         }

@@ -11,13 +11,29 @@
 
 namespace mtvq {
 
-__global__ void emit_idx_kernel(const int* __restrict__ best_col, int64_t n, int64_t* __restrict__ idx) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        idx[i] = (int64_t)best_col[i];
+// int32 winners -> int64 indices (torch.argmin dtype) and, in the same pass, the per-code counts
+// (F.one_hot(...).sum(0) of the reference, :183-194): equal codes inside a warp are merged with
+// match.any so a hot code costs one 32-bit RED per warp instead of 32.
+template <typename IdxT, bool WRITE_IDX>
+__global__ void __launch_bounds__(256) emit_hist_kernel(const IdxT* __restrict__ src, int64_t n,
+                                                         int64_t* __restrict__ idx, int* __restrict__ bins) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x - lane; base < n; base += nthreads) {
+        const int64_t row = base + lane;
+        const bool valid = row < n;
+        const int code = valid ? (int)src[row] : -1;
+        if (WRITE_IDX && valid) idx[row] = (int64_t)code;
+        const unsigned act = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const unsigned same = __match_any_sync(act, code);
+            if (lane == __ffs(same) - 1) atomicAdd(&bins[code], __popc(same));
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
-// gather + straight-through + SSE + histogram
+// gather + straight-through + SSE
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gather_ste_kernel(const float* __restrict__ z, const float* __restrict__ denom,
                                                           const float* __restrict__ w, const int64_t* __restrict__ idx,
@@ -27,20 +43,7 @@ __global__ void __launch_bounds__(256) gather_ste_kernel(const float* __restrict
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
 
-    // phase A: per-code counts, one thread per row, equal codes inside a warp aggregated
-    for (int64_t base = tid - lane; base < n; base += nthreads) {
-        const int64_t row = base + lane;
-        const bool valid = row < n;
-        const int code = valid ? (int)idx[row] : -1;
-        const unsigned act = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
-            const unsigned same = __match_any_sync(act, code);
-            if (lane == __ffs(same) - 1) atomicAdd(&stats[code], (double)__popc(same));
-        }
-    }
-    if (tid == 0) atomicAdd(&stats[(size_t)k + (size_t)k * d + 1], (double)n);
-
-    // phase B: one float4 per thread per step; a row's d/4 vectors sit in adjacent lanes
+    // one float4 per thread per step; a row's d/4 vectors sit in adjacent lanes
     const int vec_per_row = d >> 2;
     const int64_t nvec = n * vec_per_row;
     double sse = 0.0;
@@ -75,13 +78,14 @@ __global__ void __launch_bounds__(256) gather_ste_kernel(const float* __restrict
 // ------------------------------------------------------------------------------------------------
 // counting sort of rows by code
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) scan_bins_kernel(const double* __restrict__ bins, int k,
-                                                          int* __restrict__ offsets, int* __restrict__ cursor) {
+__global__ void __launch_bounds__(1024) scan_bins_kernel(const int* __restrict__ bins, int k, int64_t n, int d,
+                                                          int* __restrict__ offsets, int* __restrict__ cursor,
+                                                          double* __restrict__ stats) {
     __shared__ int part[1024];
     const int per = (k + 1023) / 1024;
     const int lo = threadIdx.x * per, hi = min(k, lo + per);
     int s = 0;
-    for (int i = lo; i < hi; ++i) s += (int)bins[i];
+    for (int i = lo; i < hi; ++i) s += bins[i];
     part[threadIdx.x] = s;
     __syncthreads();
     for (int off = 1; off < 1024; off <<= 1) {   // Hillis-Steele inclusive scan
@@ -92,11 +96,14 @@ __global__ void __launch_bounds__(1024) scan_bins_kernel(const double* __restric
     }
     int run = part[threadIdx.x] - s;
     for (int i = lo; i < hi; ++i) {
+        const int b = bins[i];
         offsets[i] = run;
         cursor[i] = run;
-        run += (int)bins[i];
+        stats[i] += (double)b;                    // packed statistics: bins as doubles (exact)
+        run += b;
     }
     if (threadIdx.x == 1023) offsets[k] = part[1023];
+    if (threadIdx.x == 0) stats[(size_t)k + (size_t)k * d + 1] += (double)n;
 }
 
 __global__ void scatter_rows_kernel(const int64_t* __restrict__ idx, int64_t n, int* __restrict__ cursor,
@@ -120,54 +127,61 @@ __global__ void scatter_rows_kernel(const int64_t* __restrict__ idx, int64_t n, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// segmented fp64 sums over the code-sorted rows: one warp per 32 consecutive sorted rows
+// segmented fp64 sums over the code-sorted rows.  Work item = (range of kSegRows consecutive sorted rows,
+// float4 column c4): the d/4 threads of a group read one 4*d-byte row together (coalesced) and walk the
+// range 4 rows at a time (independent loads in flight); a group flushes with fp64 REDs when the code
+// changes, so each code costs ~ (rows/kSegRows + 1) * d atomics whatever the skew.
 // ------------------------------------------------------------------------------------------------
-template <int SLOTS>   // d <= 32 * SLOTS
+constexpr int kSegRows = 32;
+
 __global__ void __launch_bounds__(256) segsum_kernel(const float* __restrict__ z, const float* __restrict__ denom,
                                                       const int64_t* __restrict__ idx, const int* __restrict__ perm,
                                                       int64_t n, int d, double* __restrict__ embed_sum) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t p0 = warp * 32; p0 < n; p0 += nwarps * 32) {
-        const int cnt = (int)min((int64_t)32, n - p0);
-        int my_row = 0, my_code = -1;
-        float my_den = 1.0f;
-        if (lane < cnt) {
-            my_row = perm[p0 + lane];
-            my_code = (int)idx[my_row];
-            my_den = denom[my_row];
-        }
-        double acc[SLOTS];
+    const int vpr = d >> 2;                                   // float4 per row
+    const int64_t nranges = (n + kSegRows - 1) / kSegRows;
+    const int64_t items = nranges * vpr;
+    for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t range = it / vpr;
+        const int c4 = (int)(it - range * vpr);
+        const int64_t p0 = range * kSegRows;
+        const int cnt = (int)min((int64_t)kSegRows, n - p0);
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int cur = -1;
+        auto flush = [&]() {
+            if (cur >= 0) {
+                double* dst = embed_sum + (size_t)cur * d + 4 * c4;
+                atomicAdd(dst + 0, a0); atomicAdd(dst + 1, a1); atomicAdd(dst + 2, a2); atomicAdd(dst + 3, a3);
+            }
+            a0 = a1 = a2 = a3 = 0.0;
+        };
+        for (int j0 = 0; j0 < cnt; j0 += 4) {
+            int rows[4], codes[4];
+            float dens[4];
+            float4 x[4];
 #pragma unroll
-        for (int s = 0; s < SLOTS; ++s) acc[s] = 0.0;
-        int cur = __shfl_sync(0xffffffffu, my_code, 0);
-#pragma unroll 4
-        for (int j = 0; j < cnt; ++j) {
-            const int row = __shfl_sync(0xffffffffu, my_row, j);
-            const int code = __shfl_sync(0xffffffffu, my_code, j);
-            const float den = __shfl_sync(0xffffffffu, my_den, j);
-            if (code != cur) {
+            for (int u = 0; u < 4; ++u) {
+                const bool ok = j0 + u < cnt;
+                rows[u] = ok ? perm[p0 + j0 + u] : 0;
+            }
 #pragma unroll
-                for (int s = 0; s < SLOTS; ++s) {
-                    const int c = s * 32 + lane;
-                    if (c < d) atomicAdd(&embed_sum[(size_t)cur * d + c], acc[s]);
-                    acc[s] = 0.0;
+            for (int u = 0; u < 4; ++u) {
+                const bool ok = j0 + u < cnt;
+                codes[u] = ok ? (int)__ldg(idx + rows[u]) : -1;
+                dens[u] = ok ? __ldg(denom + rows[u]) : 1.0f;
+                x[u] = ok ? __ldg(reinterpret_cast<const float4*>(z + (size_t)rows[u] * d) + c4) : make_float4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (j0 + u < cnt) {
+                    if (codes[u] != cur) { flush(); cur = codes[u]; }
+                    a0 += (double)__fdiv_rn(x[u].x, dens[u]);
+                    a1 += (double)__fdiv_rn(x[u].y, dens[u]);
+                    a2 += (double)__fdiv_rn(x[u].z, dens[u]);
+                    a3 += (double)__fdiv_rn(x[u].w, dens[u]);
                 }
-                cur = code;
-            }
-            const float* zr = z + (size_t)row * d;
-#pragma unroll
-            for (int s = 0; s < SLOTS; ++s) {
-                const int c = s * 32 + lane;
-                if (c < d) acc[s] += (double)__fdiv_rn(__ldg(zr + c), den);
             }
         }
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s) {
-            const int c = s * 32 + lane;
-            if (c < d && cnt > 0) atomicAdd(&embed_sum[(size_t)cur * d + c], acc[s]);
-        }
+        flush();
     }
 }
 
@@ -223,8 +237,18 @@ static int grid_for(int64_t work, int per_block, int num_sms, int max_waves) {
     return (int)(b < 1 ? 1 : b);
 }
 
-cudaError_t launch_emit_idx(const int* best_col, int64_t n, int64_t* idx, int num_sms, cudaStream_t s) {
-    emit_idx_kernel<<<grid_for(n, 256, num_sms, 8), 256, 0, s>>>(best_col, n, idx);
+cudaError_t launch_emit_idx(const int* best_col, int64_t n, int64_t* idx, int* bins_i32, int k, int num_sms,
+                            cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(bins_i32, 0, sizeof(int) * k, s);
+    if (e != cudaSuccess) return e;
+    emit_hist_kernel<int, true><<<grid_for(n, 256, num_sms, 8), 256, 0, s>>>(best_col, n, idx, bins_i32);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hist_idx64(const int64_t* idx, int64_t n, int* bins_i32, int k, int num_sms, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(bins_i32, 0, sizeof(int) * k, s);
+    if (e != cudaSuccess) return e;
+    emit_hist_kernel<int64_t, false><<<grid_for(n, 256, num_sms, 8), 256, 0, s>>>(idx, n, nullptr, bins_i32);
     return cudaGetLastError();
 }
 
@@ -234,23 +258,22 @@ cudaError_t launch_gather_ste(const float* z, const float* denom, const float* w
     return cudaGetLastError();
 }
 
+// bins (int32, from launch_emit_idx / launch_hist_idx64) -> stats bins + row count; when want_sums also the
+// counting sort and the per-code sums
 cudaError_t launch_code_sums(const float* z, const float* denom, const int64_t* idx, int64_t n, int d, int k,
-                             double* stats, const Workspace& ws, int num_sms, cudaStream_t s) {
-    scan_bins_kernel<<<1, 1024, 0, s>>>(stats, k, ws.offsets, ws.cursor);
+                             double* stats, const Workspace& ws, bool want_sums, int num_sms, cudaStream_t s) {
+    scan_bins_kernel<<<1, 1024, 0, s>>>(ws.bins_i32, k, n, d, ws.offsets, ws.cursor, stats);
+    if (!want_sums) return cudaGetLastError();
     scatter_rows_kernel<<<grid_for(n, 256, num_sms, 8), 256, 0, s>>>(idx, n, ws.cursor, ws.perm);
-    const int g = grid_for(n, 8 * 32, num_sms, 16);
-    double* es = stats + k;
-    if (d <= 32) segsum_kernel<1><<<g, 256, 0, s>>>(z, denom, idx, ws.perm, n, d, es);
-    else if (d <= 64) segsum_kernel<2><<<g, 256, 0, s>>>(z, denom, idx, ws.perm, n, d, es);
-    else if (d <= 128) segsum_kernel<4><<<g, 256, 0, s>>>(z, denom, idx, ws.perm, n, d, es);
-    else segsum_kernel<8><<<g, 256, 0, s>>>(z, denom, idx, ws.perm, n, d, es);
+    const int64_t items = ((n + kSegRows - 1) / kSegRows) * (d / 4);
+    segsum_kernel<<<grid_for(items, 256, num_sms, 32), 256, 0, s>>>(z, denom, idx, ws.perm, n, d, stats + k);
     return cudaGetLastError();
 }
 
 cudaError_t launch_ema_finalize(float* weight, float* cluster_size, const double* stats, int k, int d, double beta,
                                 double decay, int update_cs, int update_w, float* loss, cudaStream_t s) {
     // python: mul_(decay).add_(new, alpha=1-decay): both scalars are doubles cast to fp32
-    ema_finalize_kernel<<<(k + 127) / 128, 128, 0, s>>>(weight, cluster_size, stats, k, d, (float)beta, (float)decay,
+    ema_finalize_kernel<<<(k + 31) / 32, 32, 0, s>>>(weight, cluster_size, stats, k, d, (float)beta, (float)decay,
                                                         (float)(1.0 - decay), update_cs, update_w, loss);
     return cudaGetLastError();
 }

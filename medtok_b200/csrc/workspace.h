@@ -8,7 +8,9 @@ namespace mtvq {
 constexpr int kMaxDim = 256;   // D must be a multiple of 16 and <= kMaxDim
 
 // meta block written by the codebook prep kernel (floats)
-enum MetaSlot { META_MARGIN = 0, META_EPS = 1, META_MAXNORM = 2, META_COUNT = 8 };
+enum MetaSlot { META_MARGIN = 0, META_EPS = 1, META_MAXNORM = 2, META_SPREAD = 3, META_COUNT = 8 };
+// the -||w||^2/2 K-step is skipped when max_k | ||w_k||^2 - ||w_0||^2 | / 2 <= kBiasSkipTol (eps carries the slack)
+constexpr float kBiasSkipTol = 1.0e-6f;
 // counters (ints), zeroed at the start of every assign
 enum Counter { CNT_FLAGGED = 0, CNT_FULL = 1, CNT_CANDS = 2, CNT_LAUNCHES = 3, CNT_COUNT = 8 };
 

@@ -60,7 +60,7 @@ def hard_assign(z_rows: torch.Tensor, weight: torch.Tensor, norm_mode: int = _li
     return idx, denom
 
 
-def code_statistics(z_rows, denom, weight, idx, want_sums=True, workspace: _lib.Workspace | None = None):
+def code_statistics(z_rows, denom, weight, idx, workspace: _lib.Workspace | None = None):
     """Packed fp64 statistics [bins(k) | embed_sum(k*d) | sse | rows] and z_q for given indices
     (reference :181-202 without the one-hot)."""
     z_rows, weight = _rows_f32(z_rows), _rows_f32(weight)
@@ -73,9 +73,8 @@ def code_statistics(z_rows, denom, weight, idx, want_sums=True, workspace: _lib.
     L = _lib.lib()
     _lib.check(L.mtvq_gather_ste(_lib.ptr(z_rows), _lib.ptr(denom), _lib.ptr(weight), _lib.ptr(idx), n, d, k,
                                  _lib.ptr(z_q), _lib.ptr(stats), _lib.stream_ptr(dev)), "mtvq_gather_ste")
-    if want_sums:
-        _lib.check(L.mtvq_code_sums(_lib.ptr(z_rows), _lib.ptr(denom), _lib.ptr(idx), n, d, k, _lib.ptr(stats),
-                                    _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "mtvq_code_sums")
+    _lib.check(L.mtvq_code_sums(_lib.ptr(z_rows), _lib.ptr(denom), _lib.ptr(idx), n, d, k, _lib.ptr(stats),
+                                _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "mtvq_code_sums")
     return z_q, stats
 
 

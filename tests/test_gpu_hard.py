@@ -104,6 +104,25 @@ def test_assign_matches_oracle_and_exact_kernel(oracle, dev, n, d, k):
     assert cnt["full_scan_rows"] == 0 and cnt["near_tie_rows"] < 0.3 * n
 
 
+@pytest.mark.parametrize("n,d,k", [(60000, 256, 384), (120000, 128, 640), (80000, 64, 1100), (50000, 32, 256)])
+def test_many_blocks_per_cta_match_exact_kernel(dev, n, d, k):
+    """Several row blocks per CTA for every tile-shape variant (RT = 1, 2, 4; A-region ring sizes 1, 2, 4):
+    the tensor-core path must equal the exact CUDA-core kernel on every row."""
+    from medtok_b200 import _lib
+    from medtok_b200.norm_ema_quantizer import hard_assign
+    g = torch.Generator().manual_seed(7 * n + d)
+    z = torch.randn(n, d, generator=g).to(dev)
+    w = torch.nn.functional.normalize(torch.randn(k, d, generator=g), dim=-1).to(dev)
+    wsx = _lib.Workspace()
+    idx, den = hard_assign(z, w, workspace=wsx)
+    cnt = _lib.debug_counters(wsx.buf, n, d, k)
+    idx_x, den_x = hard_assign(z, w, exact=True)
+    assert torch.equal(den, den_x)
+    bad = (idx != idx_x).nonzero().flatten()
+    assert bad.numel() == 0, f"{bad.numel()} rows differ, first {bad[:8].tolist()}"
+    assert cnt["full_scan_rows"] == 0
+
+
 def test_degenerate_codebooks(oracle, dev):
     """all-zero codebook (k-means pending: every code ties -> index 0) and massive duplication
     (candidate list overflows -> exact full scan fallback)."""
