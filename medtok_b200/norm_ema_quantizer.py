@@ -15,6 +15,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
+from .distributed import all_reduce_stats
 
 
 def l2norm(t):
@@ -265,7 +266,7 @@ class NormEMAVectorQuantizer(nn.Module):
             upd_w = self.training and self.embedding.update
             upd_cs = has_cs and ((not self.training) or self.embedding.update)
             if distributed_on and (upd_w or upd_cs):
-                self.all_reduce_fn(stats)          # ONE packed all-reduce (reference: :188 / :195 + :203)
+                all_reduce_stats(stats, self.all_reduce_fn)   # ONE packed all-reduce (reference: :188 / :195 + :203)
             if upd_w or upd_cs:
                 _lib.check(L.mtvq_ema_finalize(_lib.ptr(weight), _lib.ptr(cs), _lib.ptr(stats), k, d,
                                                float(self.beta), float(self.decay), int(upd_cs), int(upd_w),
