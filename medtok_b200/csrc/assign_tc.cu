@@ -199,11 +199,14 @@ __device__ __forceinline__ void consume(const float (&v)[32], int chunk, RowStat
 
 }  // namespace
 
-template <int RT, int MODE, int NTOP>
+template <int RT, int MODE, int NTOP, bool DBG>
 __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
+    // thread id through a volatile read: ptxas otherwise re-derives warp/lane (S2R + shifts) inside the hot loops
+    uint32_t tid_x;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid_x));
+    const int warp = (int)(tid_x >> 5);
+    const int lane = (int)(tid_x & 31);
 
     const int d         = p.d;
     const int nplanes   = d >> 3;
@@ -220,14 +223,14 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
 
     // bias K-step (-||w||^2/2): needed unless every code has the same squared norm (then it is a constant
     // shift of all scores); padding codes rely on it to lose, so it stays on when K is not a tile multiple
-    const bool use_bias = !(p.debug_flags & 2) &&
+    const bool use_bias = !(DBG && (p.debug_flags & 2)) &&
                           (MODE == MODE_DUMP || p.k != p.kpad || !(p.meta[META_SPREAD] <= kBiasSkipTol));
 
     Bars bars = carve_bars(smem);
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kOffTmem);
 
     // ---- one-time setup ------------------------------------------------------------------------
-    if (threadIdx.x == 0) {
+    if (tid_x == 0) {
         // every codebook stage is released by all four issuers (owners via tcgen05.commit, the others arrive)
         for (int i = 0; i < kDataStages; ++i) { mbar_init(&bars.bd_full[i], 1); mbar_init(&bars.bd_empty[i], 4); }
         for (int i = 0; i < kBiasStages; ++i) { mbar_init(&bars.bb_full[i], 1); mbar_init(&bars.bb_empty[i], 4); }
@@ -241,7 +244,7 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
     }
     if (warp >= kLoadWarp0 && warp < kLoadWarp0 + kLoadWarps) {
         // constant A-side planes of the bias K-step: row = (1, 1, 1, 0, 0, 0, 0, 0 | 0 x 8)
-        const int r = threadIdx.x - kLoadWarp0 * 32;
+        const int r = (int)tid_x - kLoadWarp0 * 32;
         const __half one = __float2half(1.0f), zero = __float2half(0.0f);
         __half2 h01 = __halves2half2(one, one), h23 = __halves2half2(one, zero), hz = __halves2half2(zero, zero);
         uint4 q0, qz;
@@ -286,7 +289,15 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
         float4* state = reinterpret_cast<float4*>(smem + kOffState);
         const int rec0 = warp * 32 + lane;          // record of state set ss = ss * 512 + rec0
         uint32_t uses[2] = {0, 0};
-        const bool tracing = (p.trace != nullptr) && blockIdx.x == 0 && warp == 0 && lane == 0;
+        const bool tracing = DBG && (p.trace != nullptr) && blockIdx.x == 0 && warp == 0 && lane == 0;
+        // everything the per-tile critical path needs, computed once
+        uint32_t full_addr[2]  = {smem_u32(&bars.acc_full[pair]), smem_u32(&bars.acc_full[pair + 2])};
+        uint32_t empty_addr[2] = {smem_u32(&bars.acc_empty[pair]), smem_u32(&bars.acc_empty[pair + 2])};
+        uint32_t tld[2] = {t_lane + (uint32_t)(pair * kTileCodes), t_lane + (uint32_t)((pair + 2) * kTileCodes)};
+        uint32_t is_lane0 = (lane == 0) ? 1u : 0u;
+        // make the values opaque so ptxas keeps them in registers instead of re-deriving them from the thread id
+        asm volatile("" : "+r"(full_addr[0]), "+r"(full_addr[1]), "+r"(empty_addr[0]), "+r"(empty_addr[1]),
+                          "+r"(tld[0]), "+r"(tld[1]), "+r"(is_lane0));
 
         for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
             RowState<NTOP> st[NS];
@@ -311,25 +322,25 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                     if (((s - c * RT) & 3) >= RT) continue;      // no tile of this chunk lives in slot s
                     constexpr int kZero = 0;
                     const int ss = (RT == 4) ? si : kZero;
-                    mbar_wait(&bars.acc_full[s], uses[si] & 1);
-                    if (tracing && si == 0 && uses[0] < 512) p.trace[uses[0] * 8 + 2] = clock64();
+                    mbar_wait_addr(full_addr[si], uses[si] & 1);
+                    if (DBG && tracing && si == 0 && uses[0] < 512) p.trace[uses[0] * 8 + 2] = clock64();
                     ++uses[si];
                     tc_fence_after();
                     float va[32], vb[32];
-                    if (!(p.debug_flags & 1)) {
-                        tmem_ld32(t_lane + (uint32_t)(s * kTileCodes), va);
-                        tmem_ld32(t_lane + (uint32_t)(s * kTileCodes + kChunk), vb);
+                    if (!(DBG && (p.debug_flags & 1))) {
+                        tmem_ld32(tld[si], va);
+                        tmem_ld32(tld[si] + kChunk, vb);
                         tmem_ld_wait();
                     }
                     // both granules are in registers: hand the accumulator back before reducing them
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&bars.acc_empty[s]);
-                    if (tracing && si == 0 && uses[0] <= 512) p.trace[(uses[0] - 1) * 8 + 3] = clock64();
-                    if (p.debug_flags & 1) continue;             // timing experiment: no epilogue work
+                    if (is_lane0) mbar_arrive_addr(empty_addr[si]);
+                    if (DBG && tracing && si == 0 && uses[0] <= 512) p.trace[(uses[0] - 1) * 8 + 3] = clock64();
+                    if (DBG && (p.debug_flags & 1)) continue;    // timing experiment: no epilogue work
                     consume<MODE, NTOP>(va, c * 4 + 2 * half, st[ss], margin, p, slots, ss * 512 + rec0);
                     consume<MODE, NTOP>(vb, c * 4 + 2 * half + 1, st[ss], margin, p, slots, ss * 512 + rec0);
-                    if (tracing && si == 0 && uses[0] <= 512) p.trace[(uses[0] - 1) * 8 + 4] = clock64();
+                    if (DBG && tracing && si == 0 && uses[0] <= 512) p.trace[(uses[0] - 1) * 8 + 4] = clock64();
                 }
             }
 
@@ -435,10 +446,10 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
         // one thread per row.  The exact reference-order norm goes to `denom` (later kernels divide by
         // it); the fp16 MMA operand itself only needs to be inside the coarse error bound, so it is
         // produced with one reciprocal and a multiply per element instead of an IEEE division.
-        const int r = threadIdx.x - kLoadWarp0 * 32;
+        const int r = (int)tid_x - kLoadWarp0 * 32;
         uint32_t bi = 0;
         for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x, ++bi) {
-            const bool skip = (p.debug_flags & 4) && bi > 0;          // timing experiment only
+            const bool skip = DBG && (p.debug_flags & 4) && bi > 0;   // timing experiment only
             for (int g = 0; g < RT; ++g) {
                 const int64_t pos = (int64_t)blk * rows_blk + g * kTileRows + r;
                 const bool valid = pos < nrows && !skip;
@@ -553,7 +564,7 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
             const uint32_t tacc = tmem_base + (uint32_t)(j * kTileCodes);
             uint32_t uses = 0, bi = 0;
             uint32_t chunk0 = 0;                     // chunks issued by the CTA before this block
-            const bool tracing = (p.trace != nullptr) && blockIdx.x == 0 && j == 0;
+            const bool tracing = DBG && (p.trace != nullptr) && blockIdx.x == 0 && j == 0;
             for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x, ++bi, chunk0 += nchunks) {
                 // Every issuer walks EVERY chunk so that each shared barrier sees all four issuers once per
                 // phase (an mbarrier parity wait is only meaningful within one phase of the barrier);
@@ -578,7 +589,7 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                     }
                     if (first) { mbar_wait(&bars.a_full[areg], apar); first = false; }
                     mbar_wait(&bars.acc_empty[j], (uses & 1u) ^ 1u);
-                    if (tracing && uses < 512) p.trace[uses * 8 + 0] = clock64();
+                    if (DBG && tracing && uses < 512) p.trace[uses * 8 + 0] = clock64();
                     ++uses;
                     tc_fence_after();
                     for (int kb = 0; kb < nkblk; ++kb) {
@@ -597,7 +608,7 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                     umma_commit(&bars.acc_full[j]);
                     if (use_bias) umma_commit(&bars.bb_empty[sb]);
                     if (c + G >= nchunks) umma_commit(&bars.a_empty[areg]);   // this issuer's last tile of the block
-                    if (tracing && uses <= 512) p.trace[(uses - 1) * 8 + 1] = clock64();
+                    if (DBG && tracing && uses <= 512) p.trace[(uses - 1) * 8 + 1] = clock64();
                 }
                 if (first) {
                     // fewer chunks than issuers: this issuer owned no tile, but the row tile's release
@@ -621,9 +632,9 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
 // ------------------------------------------------------------------------------------------------
 // host launcher
 // ------------------------------------------------------------------------------------------------
-template <int RT, int MODE, int NTOP>
+template <int RT, int MODE, int NTOP, bool DBG>
 static cudaError_t launch_one(const CoarseParams& p, int grid, cudaStream_t stream) {
-    auto kern = coarse_kernel<RT, MODE, NTOP>;
+    auto kern = coarse_kernel<RT, MODE, NTOP, DBG>;
     static bool configured = false;   // one per instantiation
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
@@ -644,8 +655,13 @@ int coarse_row_tiles(int d, int64_t nrows, int num_sms) {
 cudaError_t launch_coarse(const CoarseParams& p, int mode, int row_tiles, int num_sms, cudaStream_t stream) {
     // NTOP only matters in THRESH mode (size of the per-row top list): 5 covers MedTok's k = 5
     const int ntop = (mode == MODE_THRESH && p.topk > 5) ? 8 : 5;
-#define MTVQ_CASE(RT_, MODE_, NTOP_) \
-    if (row_tiles == RT_ && mode == MODE_ && ntop == NTOP_) return launch_one<RT_, MODE_, NTOP_>(p, num_sms, stream);
+    // timing knobs / pipeline trace live in a separate instantiation so that the production kernels carry none of it
+    const bool dbg = (mode == MODE_ARGMAX) && (p.trace != nullptr || p.debug_flags != 0);
+#define MTVQ_CASE(RT_, MODE_, NTOP_)                                                                   \
+    if (row_tiles == RT_ && mode == MODE_ && ntop == NTOP_) {                                           \
+        if (MODE_ == MODE_ARGMAX && dbg) return launch_one<RT_, MODE_ARGMAX, 5, true>(p, num_sms, stream); \
+        return launch_one<RT_, MODE_, NTOP_, false>(p, num_sms, stream);                                \
+    }
 #define MTVQ_MODES(RT_)             \
     MTVQ_CASE(RT_, MODE_ARGMAX, 5)  \
     MTVQ_CASE(RT_, MODE_COLLECT, 5) \

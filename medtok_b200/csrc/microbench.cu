@@ -112,7 +112,45 @@ __global__ void __launch_bounds__(640, 1) umma_bench_kernel(int iters, int n_col
     if (acc == 123.456f) sink[threadIdx.x] = acc;
 }
 
+// which = 5: `nissue` (1, 2 or 4) issuer warps, each feeding its own 128-column accumulator with 4-MMA tiles and
+// waiting for its own tcgen05.commit before the next tile (the slot loop of the real kernel without an epilogue).
+// result: aggregate TFLOP/s and, via result_host[1], flops.  Tells whether MMAs from different warps pipeline.
+__global__ void __launch_bounds__(256, 1) umma_multi_issuer_kernel(int iters, int nissue, int wait_each, float* sink) {
+    extern __shared__ __align__(1024) unsigned char sm[];
+    __shared__ uint32_t tmem_ptr;
+    __shared__ uint64_t bar[4];
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 49152 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = 0x3c003c00u;
+    if (threadIdx.x == 0) { for (int i = 0; i < 4; ++i) mbar_init(&bar[i], 1); fence_mbar_init(); }
+    fence_proxy_async_smem();
+    if (warp == 0) { tmem_alloc(&tmem_ptr, 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp >= 4 && warp < 4 + nissue && elect_one()) {
+        const int j = warp - 4;
+        const uint32_t idesc = umma_idesc_f16(128, 128);
+        const uint64_t da = umma_smem_desc(smem_u32(sm), 2048, 128);
+        const uint64_t db = umma_smem_desc(smem_u32(sm + 16384), 2048, 128);
+        const uint32_t tacc = tmem_ptr + (uint32_t)(j * 128);
+        const int my_iters = iters / nissue;
+        for (int it = 0; it < my_iters; ++it) {
+            umma_f16(tacc, da, db, idesc, 0);
+            umma_f16(tacc, da + 256, db + 256, idesc, 1);
+            umma_f16(tacc, da + 512, db + 512, idesc, 1);
+            umma_f16(tacc, da + 768, db + 768, idesc, 1);
+            if (wait_each) { umma_commit(&bar[j]); mbar_wait(&bar[j], it & 1, 0u); }
+        }
+        if (!wait_each) { umma_commit(&bar[j]); mbar_wait(&bar[j], 0, 0u); }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_ptr, 512); }
+    if (sink == nullptr) sm[0] = 1;
+}
+
 cudaError_t run_microbench(int which, int warps, int iters, int num_sms, double* result_host, cudaStream_t stream) {
+    const int warps_raw = warps;
     if (warps < 4) warps = 4;
     if (warps > 32) warps = 32;
     warps &= ~3;
@@ -124,7 +162,10 @@ cudaError_t run_microbench(int which, int warps, int iters, int num_sms, double*
     cudaEventCreate(&t0); cudaEventCreate(&t1);
     for (int rep = 0; rep < 2; ++rep) {
         cudaEventRecord(t0, stream);
-        if (which >= 2) {
+        if (which == 5 || which == 6) {
+            cudaFuncSetAttribute(umma_multi_issuer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+            umma_multi_issuer_kernel<<<num_sms, 256, 65536, stream>>>(iters, warps_raw, which == 6, buf + 1024);
+        } else if (which >= 2) {
             cudaFuncSetAttribute(umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
             umma_bench_kernel<<<num_sms, which == 2 ? 128 : 640, 65536, stream>>>(iters, warps * 8, which, buf + 1024);
         } else if (which == 0) tmem_ld_bench_kernel<<<num_sms, warps * 32, 0, stream>>>(iters, buf + 1024);
@@ -135,7 +176,8 @@ cudaError_t run_microbench(int which, int warps, int iters, int num_sms, double*
     float ms = 0.f;
     cudaEventElapsedTime(&ms, t0, t1);
     result_host[0] = ms;
-    if (which >= 2) result_host[1] = (double)num_sms * iters * 4.0 * 128.0 * (warps * 8) * 16.0 * 2.0;   // flops
+    if (which == 5 || which == 6) result_host[1] = (double)num_sms * (iters / warps_raw) * warps_raw * 4.0 * 128.0 * 128.0 * 16.0 * 2.0;
+    else if (which >= 2) result_host[1] = (double)num_sms * iters * 4.0 * 128.0 * (warps * 8) * 16.0 * 2.0;   // flops
     else if (which == 0) result_host[1] = (double)num_sms * warps * iters * 16.0 * 32.0 * 32.0 * 4.0;   // bytes
     else result_host[1] = (double)num_sms * warps * 32.0 * iters * 32.0;                               // scores
     cudaEventDestroy(t0); cudaEventDestroy(t1);

@@ -9,6 +9,8 @@ There is no CPU / PyTorch fallback: CPU tensors raise.
 """
 from __future__ import annotations
 
+import sys
+
 import torch
 import torch.distributed as distributed
 import torch.nn as nn
@@ -223,7 +225,7 @@ class NormEMAVectorQuantizer(nn.Module):
             self.register_buffer('cluster_size', torch.zeros(n_embed))
         # like the reference (:155-159) the exchange is bound at construction time
         if distributed.is_available() and distributed.is_initialized():
-            print("ddp is enable, so use ddp_reduce to sync the statistic_code_usage for each gpu!")
+            print("ddp is enable, so use ddp_reduce to sync the statistic_code_usage for each gpu!", file=sys.stderr)
             self.all_reduce_fn = distributed.all_reduce
         else:
             self.all_reduce_fn = nn.Identity()

@@ -32,6 +32,10 @@ if what in ("all", "micro"):
         for ncols in (128, 256):
             _lib.check(L.mtvq_microbench(which, ncols // 8, 20000, res, st), "microbench umma")
             mb[f"umma_TFLOPs_n{ncols}_{tag}"] = res[1] / (res[0] * 1e-3) / 1e12
+    for which, tag in ((5, "free_running"), (6, "commit_wait_each_tile")):
+        for ni in (1, 2, 4):
+            _lib.check(L.mtvq_microbench(which, ni, 40000, res, st), "microbench multi issuer")
+            mb[f"umma_TFLOPs_{ni}issuers_{tag}"] = res[1] / (res[0] * 1e-3) / 1e12
     out["microbench"] = mb
     print(json.dumps(mb, indent=1))
 
