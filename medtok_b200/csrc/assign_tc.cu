@@ -197,6 +197,29 @@ __device__ __forceinline__ void consume(const float (&v)[32], int chunk, RowStat
     }
 }
 
+// ARGMAX on a thread's whole 64-column half-tile: one trigger test per 64 scores.  `va` holds granule `chunk`,
+// `vb` granule `chunk + 1`.
+template <int NTOP>
+__device__ __forceinline__ void consume_argmax64(const float (&va)[32], const float (&vb)[32], int chunk,
+                                                 RowState<NTOP>& st, float margin, unsigned char* slots, int rec) {
+    const float ma = max32(va), mb = max32(vb);
+    const float cmax = fmaxf(ma, mb);
+    const bool trig = cmax >= st.thr;
+    if (__any_sync(0xffffffffu, trig)) {
+        if (trig) {
+            if (cmax > st.m1) {          // new record: remember the better granule; the other one counts as "other"
+                st.m2 = fmaxf(fmaxf(st.m2, st.m1), fminf(ma, mb));
+                st.m1 = cmax;
+                st.thr = cmax - margin;
+                if (mb > ma) { st.best_chunk = chunk + 1; record_store(slots, rec, vb); }
+                else         { st.best_chunk = chunk;     record_store(slots, rec, va); }
+            } else {                      // granule(s) within the margin of the record
+                st.m2 = fmaxf(st.m2, cmax);
+            }
+        }
+    }
+}
+
 }  // namespace
 
 template <int RT, int MODE, int NTOP, bool DBG>
@@ -287,7 +310,8 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 64);
         unsigned char* slots = smem + kOffSlots;
         float4* state = reinterpret_cast<float4*>(smem + kOffState);
-        const int rec0 = warp * 32 + lane;          // record of state set ss = ss * 512 + rec0
+        int rec0 = warp * 32 + lane;                // record of state set ss = ss * 512 + rec0
+        asm volatile("" : "+r"(rec0));
         uint32_t uses[2] = {0, 0};
         const bool tracing = DBG && (p.trace != nullptr) && blockIdx.x == 0 && warp == 0 && lane == 0;
         // everything the per-tile critical path needs, computed once
@@ -338,8 +362,12 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                     if (is_lane0) mbar_arrive_addr(empty_addr[si]);
                     if (DBG && tracing && si == 0 && uses[0] <= 512) p.trace[(uses[0] - 1) * 8 + 3] = clock64();
                     if (DBG && (p.debug_flags & 1)) continue;    // timing experiment: no epilogue work
-                    consume<MODE, NTOP>(va, c * 4 + 2 * half, st[ss], margin, p, slots, ss * 512 + rec0);
-                    consume<MODE, NTOP>(vb, c * 4 + 2 * half + 1, st[ss], margin, p, slots, ss * 512 + rec0);
+                    if (MODE == MODE_ARGMAX) {
+                        consume_argmax64<NTOP>(va, vb, c * 4 + 2 * half, st[ss], margin, slots, ss * 512 + rec0);
+                    } else {
+                        consume<MODE, NTOP>(va, c * 4 + 2 * half, st[ss], margin, p, slots, ss * 512 + rec0);
+                        consume<MODE, NTOP>(vb, c * 4 + 2 * half + 1, st[ss], margin, p, slots, ss * 512 + rec0);
+                    }
                     if (DBG && tracing && si == 0 && uses[0] <= 512) p.trace[(uses[0] - 1) * 8 + 4] = clock64();
                 }
             }

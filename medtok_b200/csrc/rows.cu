@@ -43,26 +43,46 @@ __global__ void __launch_bounds__(256) gather_ste_kernel(const float* __restrict
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
 
-    // one float4 per thread per step; a row's d/4 vectors sit in adjacent lanes
-    const int vec_per_row = d >> 2;
-    const int64_t nvec = n * vec_per_row;
+    // one float4 per thread per stream, kU independent streams in flight; a row's d/4 vectors sit in adjacent
+    // lanes (coalesced).  z and z_q are touched once -> streaming loads/stores keep the codebook in L2.
+    constexpr int kU = 4;
+    const int vpr = d >> 2;
+    const int64_t nvec = n * vpr;
+    const float4* z4 = reinterpret_cast<const float4*>(z);
+    float4* q4 = reinterpret_cast<float4*>(z_q);
     double sse = 0.0;
-    for (int64_t v = tid; v < nvec; v += nthreads) {
-        const int64_t row = v / vec_per_row;
-        const int c4 = (int)(v - row * vec_per_row);
-        const float den = __ldg(denom + row);
-        const int64_t code = __ldg(idx + row);
-        const float4 x = __ldg(reinterpret_cast<const float4*>(z) + v);
-        const float4 q = __ldg(reinterpret_cast<const float4*>(w + code * d) + c4);
-        const float zf0 = __fdiv_rn(x.x, den), zf1 = __fdiv_rn(x.y, den), zf2 = __fdiv_rn(x.z, den),
-                    zf3 = __fdiv_rn(x.w, den);
-        const float d0 = __fsub_rn(q.x, zf0), d1 = __fsub_rn(q.y, zf1), d2 = __fsub_rn(q.z, zf2),
-                    d3 = __fsub_rn(q.w, zf3);
-        sse += (double)__fmul_rn(d0, d0) + (double)__fmul_rn(d1, d1) + (double)__fmul_rn(d2, d2) +
-               (double)__fmul_rn(d3, d3);
-        float4 o;
-        o.x = __fadd_rn(zf0, d0); o.y = __fadd_rn(zf1, d1); o.z = __fadd_rn(zf2, d2); o.w = __fadd_rn(zf3, d3);
-        reinterpret_cast<float4*>(z_q)[v] = o;
+    for (int64_t v0 = tid; v0 < nvec; v0 += nthreads * kU) {
+        float4 x[kU], c[kU];
+        float den[kU];
+        int64_t code[kU];
+        int c4[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int64_t v = v0 + (int64_t)u * nthreads;
+            const bool ok = v < nvec;
+            const int64_t row = ok ? v / vpr : 0;
+            c4[u] = ok ? (int)(v - row * vpr) : 0;
+            den[u] = __ldg(denom + row);
+            code[u] = __ldg(idx + row);
+            x[u] = ok ? __ldcs(z4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) c[u] = __ldg(reinterpret_cast<const float4*>(w + code[u] * d) + c4[u]);
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int64_t v = v0 + (int64_t)u * nthreads;
+            if (v < nvec) {
+                const float zf0 = __fdiv_rn(x[u].x, den[u]), zf1 = __fdiv_rn(x[u].y, den[u]),
+                            zf2 = __fdiv_rn(x[u].z, den[u]), zf3 = __fdiv_rn(x[u].w, den[u]);
+                const float d0 = __fsub_rn(c[u].x, zf0), d1 = __fsub_rn(c[u].y, zf1), d2 = __fsub_rn(c[u].z, zf2),
+                            d3 = __fsub_rn(c[u].w, zf3);
+                sse += (double)__fmul_rn(d0, d0) + (double)__fmul_rn(d1, d1) + (double)__fmul_rn(d2, d2) +
+                       (double)__fmul_rn(d3, d3);
+                float4 o;
+                o.x = __fadd_rn(zf0, d0); o.y = __fadd_rn(zf1, d1); o.z = __fadd_rn(zf2, d2); o.w = __fadd_rn(zf3, d3);
+                __stcs(q4 + v, o);
+            }
+        }
     }
     sse = warp_sum(sse);
     __shared__ double part[8];
@@ -254,7 +274,7 @@ cudaError_t launch_hist_idx64(const int64_t* idx, int64_t n, int* bins_i32, int 
 
 cudaError_t launch_gather_ste(const float* z, const float* denom, const float* w, const int64_t* idx, int64_t n, int d,
                               int k, float* z_q, double* stats, int num_sms, cudaStream_t s) {
-    gather_ste_kernel<<<grid_for(n * (d / 4), 256 * 4, num_sms, 8), 256, 0, s>>>(z, denom, w, idx, n, d, k, z_q, stats);
+    gather_ste_kernel<<<grid_for(n * (d / 4), 256 * 4, num_sms, 6), 256, 0, s>>>(z, denom, w, idx, n, d, k, z_q, stats);
     return cudaGetLastError();
 }
 
