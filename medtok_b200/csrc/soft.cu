@@ -35,16 +35,22 @@ __global__ void __launch_bounds__(256) soft_resolve_kernel(
     const int* __restrict__ cand_cnt, int cand_cap, int64_t* __restrict__ idx_out, float* __restrict__ val_out,
     float* __restrict__ wts_out, float* __restrict__ zq_out, float* __restrict__ out, double* __restrict__ sse_out,
     int* __restrict__ counters) {
+    __shared__ __align__(16) float xn_s[8][kMaxDim];          // one normalised row per warp
     const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float* xs = xn_s[wib];
     double sse = 0.0;
 
     for (int64_t row = warp; row < n; row += nwarps) {
         const float* xr = x + row * d;
         const float den = denom[row];
-        // ||xn||^2 in the reference's cascade order (every lane redundantly; loads broadcast)
-        const float xx = canon_sumsq([&](int i) { return __fdiv_rn(__ldg(xr + i), den); }, d);
+        __syncwarp();
+        for (int i = lane; i < d; i += 32) xs[i] = __fdiv_rn(__ldg(xr + i), den);   // xn, divided once
+        __syncwarp();
+        // ||xn||^2 in the reference's cascade order (every lane the same value; shared-memory broadcasts)
+        const float xx = canon_sumsq([&](int i) { return xs[i]; }, d);
         const int cnt = cand_cnt[row];
         const bool full = (cnt < topk) || (cnt > cand_cap);
 
@@ -57,9 +63,16 @@ __global__ void __launch_bounds__(256) soft_resolve_kernel(
         for (int j = lane; j < total; j += 32) {
             const int col = full ? j : cand[row * cand_cap + j];
             if (col >= k) continue;
-            const float* cr = cn + (size_t)col * d;
+            const float4* cr = reinterpret_cast<const float4*>(cn + (size_t)col * d);
             float dot = 0.0f;
-            for (int i = 0; i < d; ++i) dot = __fmaf_rn(__fdiv_rn(__ldg(xr + i), den), __ldg(cr + i), dot);
+            for (int i = 0; i < d; i += 4) {                       // sequential fmaf chain over d (reference order)
+                const float4 cv = __ldg(cr + (i >> 2));
+                const float4 xv = *reinterpret_cast<const float4*>(xs + i);
+                dot = __fmaf_rn(xv.x, cv.x, dot);
+                dot = __fmaf_rn(xv.y, cv.y, dot);
+                dot = __fmaf_rn(xv.z, cv.z, dot);
+                dot = __fmaf_rn(xv.w, cv.w, dot);
+            }
             float v = canon_dist(xx, cc[col], dot);
             int ci = col;
             // insertion keeping (value, index) ascending

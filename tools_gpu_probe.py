@@ -124,6 +124,27 @@ if what == "kern":
     print("DBG", out["dbg"], "d", d, "k", k, "coarse kernel ms:", [round(x, 3) for x in ms], "TFLOP/s:",
           round(2.0 * n * k * d / (min(ms) * 1e-3) / 1e12, 1), _lib.debug_counters(wsx.buf, n, d, k))
 
+if what == "soft":
+    # soft-one quantisation at BASELINE config 3 shape: N = 2^20 rows, D = 128, K' = 16384 codes per codebook, k = 5
+    from medtok_b200.vector_quantization_soft_one_new import _SoftQuantizeFn
+    n, d, k, kk = int(os.environ.get("PROBE_N", str(1 << 20))), 128, 16384, 5
+    torch.manual_seed(0)
+    x = torch.randn(n, d, device=dev)
+    table = torch.randn(k, d, device=dev)
+    wsx = _lib.Workspace()
+    ms = []
+    with torch.no_grad():
+        for i in range(5):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            out_, vq, commit, idx, wts = _SoftQuantizeFn.apply(x, table, 0, k, kk, 0.25, True, wsx)
+            b.record(); torch.cuda.synchronize()
+            ms.append(a.elapsed_time(b))
+    cnt = _lib.debug_counters(wsx.buf, n, d, k, kk)
+    flops = 2.0 * n * k * d
+    out["soft_c3"] = {"ms": ms, "TFLOPs_algorithmic": flops / (min(ms) * 1e-3) / 1e12, "emb_per_s": n / (min(ms) * 1e-3), "counters": cnt}
+    print("SOFT", json.dumps(out["soft_c3"]))
+
 os.makedirs("gpurun_out", exist_ok=True)
 tag = what + ("_swap" if os.environ.get("MTVQ_DESC_SWAP") == "1" else "")
 json.dump(out, open(f"gpurun_out/probe_{tag}.json", "w"), indent=1)
