@@ -80,11 +80,11 @@ bool desc_swap() {
 }
 
 void fill_coarse(CoarseParams& p, const float* z, int64_t n, int d, int norm_mode, int k, const Workspace& ws,
-                 float* denom, int topk) {
+                 float* denom, int topk, int64_t* idx_out = nullptr) {
     memset(&p, 0, sizeof(p));
     p.z = z; p.n = n; p.d = d; p.norm_mode = norm_mode;
     p.b_image = ws.b_image; p.kpad = pad_codes(k); p.k = k; p.meta = ws.meta;
-    p.denom = denom; p.best_col = ws.best_col; p.best_val = ws.best_val;
+    p.denom = denom; p.idx_out = idx_out; p.bins = ws.bins_i32; p.best_val = ws.best_val;
     p.flag_rows = ws.flag_rows; p.counters = ws.counters;
     p.cand = ws.cand; p.cand_cnt = ws.cand_cnt; p.cand_cap = cand_capacity(topk); p.topk = topk;
     p.trace = g_trace;
@@ -93,20 +93,22 @@ void fill_coarse(CoarseParams& p, const float* z, int64_t n, int d, int norm_mod
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MTVQ_DBG"); dbg = e ? atoi(e) : 0; } p.debug_flags = dbg; }
 }
 
-// hard assignment into ws.best_col (+ denom); `codes` are the rows the distances are taken against
-int assign_into_ws(const float* z, int64_t n, int d, int norm_mode, const float* codes, int k, float* denom,
-                   const Workspace& ws, const DeviceInfo& di, bool exact_only, cudaStream_t st) {
+// hard assignment: idx[n] (int64, first-index argmin) + ws.bins_i32 (per-code row counts) + denom;
+// `codes` are the rows the distances are taken against
+int assign_rows(const float* z, int64_t n, int d, int norm_mode, const float* codes, int k, float* denom, int64_t* idx,
+                const Workspace& ws, const DeviceInfo& di, bool exact_only, cudaStream_t st) {
     MTVQ_CUDA(cudaMemsetAsync(ws.counters, 0, sizeof(int) * CNT_COUNT, st), "memset counters");
+    MTVQ_CUDA(cudaMemsetAsync(ws.bins_i32, 0, sizeof(int) * k, st), "memset bins");
     MTVQ_CUDA(launch_codebook_prep(codes, k, d, 0, ws, st), "codebook_prep");
     if (n == 0) return 0;
     if (exact_only) {
-        MTVQ_CUDA(launch_exact_scan(z, n, d, norm_mode, codes, k, ws.cc, nullptr, nullptr, ws.best_col, denom,
+        MTVQ_CUDA(launch_exact_scan(z, n, d, norm_mode, codes, k, ws.cc, nullptr, nullptr, idx, ws.bins_i32, denom,
                                     di.num_sms, st), "exact_scan");
         return 0;
     }
     MTVQ_CUDA(cudaMemsetAsync(ws.cand_cnt, 0, sizeof(int) * n, st), "memset cand_cnt");
     CoarseParams p;
-    fill_coarse(p, z, n, d, norm_mode, k, ws, denom, 1);
+    fill_coarse(p, z, n, d, norm_mode, k, ws, denom, 1, idx);
     if (g_ev_before) cudaEventRecord(g_ev_before, st);
     MTVQ_CUDA(launch_coarse(p, MODE_ARGMAX, coarse_row_tiles(d, n, di.num_sms), di.num_sms, st), "coarse argmax");
     if (g_ev_after) cudaEventRecord(g_ev_after, st);
@@ -116,9 +118,11 @@ int assign_into_ws(const float* z, int64_t n, int d, int norm_mode, const float*
     c.row_list = ws.flag_rows;
     c.n_rows_dev = ws.counters + CNT_FLAGGED;
     c.denom = nullptr;
-    MTVQ_CUDA(launch_coarse(c, MODE_COLLECT, 1, di.num_sms, st), "coarse collect");
-    MTVQ_CUDA(launch_resolve(z, d, norm_mode, codes, k, ws, p.cand_cap, di.num_sms, st), "resolve");
-    MTVQ_CUDA(launch_exact_scan(z, n, d, norm_mode, codes, k, ws.cc, ws.full_rows, ws.counters + CNT_FULL, ws.best_col,
+    // the row count is only known on the device: the kernel takes the widest row block the A area holds and
+    // splits the codebook over CTAs when that leaves SMs idle (assign_tc.cu "work items")
+    MTVQ_CUDA(launch_coarse(c, MODE_COLLECT, coarse_row_tiles(d, (int64_t)1 << 40, di.num_sms), di.num_sms, st), "coarse collect");
+    MTVQ_CUDA(launch_resolve(z, d, norm_mode, codes, k, ws, p.cand_cap, idx, di.num_sms, st), "resolve");
+    MTVQ_CUDA(launch_exact_scan(z, n, d, norm_mode, codes, k, ws.cc, ws.full_rows, ws.counters + CNT_FULL, idx, ws.bins_i32,
                                 nullptr, di.num_sms, st), "exact_scan(overflow)");
     return 0;
 }
@@ -150,9 +154,7 @@ static int hard_assign_impl(const float* z, int64_t n, int d, int norm_mode, con
                     (long)workspace_bytes);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float* den = denom ? denom : ws.denom;
-    if (int r = assign_into_ws(z, n, d, norm_mode, weight, k, den, ws, di, exact_only, st)) return r;
-    if (n > 0) MTVQ_CUDA(launch_emit_idx(ws.best_col, n, idx, ws.bins_i32, k, di.num_sms, st), "emit_idx");
-    return 0;
+    return assign_rows(z, n, d, norm_mode, weight, k, den, idx, ws, di, exact_only, st);
 }
 
 int mtvq_hard_assign(const float* z, int64_t n, int d, int norm_mode, const float* weight, int k, int64_t* idx,
@@ -226,9 +228,8 @@ int mtvq_hard_forward(const float* z, int64_t n, int d, int norm_mode, float* we
         return fail(MTVQ_ERR_BAD_ARG, "cluster_size is null%s", "");
 
     MTVQ_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * mtvq_stats_len(d, k), st), "memset stats");
-    if (int r = assign_into_ws(z, n, d, norm_mode, weight, k, ws.denom, ws, di, false, st)) return r;
+    if (int r = assign_rows(z, n, d, norm_mode, weight, k, ws.denom, idx, ws, di, false, st)) return r;
     if (n > 0) {
-        MTVQ_CUDA(launch_emit_idx(ws.best_col, n, idx, ws.bins_i32, k, di.num_sms, st), "emit_idx");
         MTVQ_CUDA(launch_gather_ste(z, ws.denom, weight, idx, n, d, k, z_q, stats, di.num_sms, st), "gather_ste");
         MTVQ_CUDA(launch_code_sums(z, ws.denom, idx, n, d, k, stats, ws, upd_w, di.num_sms, st), "code_sums");
     }

@@ -83,10 +83,12 @@ __global__ void codebook_prep_kernel(const float* __restrict__ w, int k, int kpa
 // ------------------------------------------------------------------------------------------------
 // near-tie resolve: one thread per flagged row, exact distances of <= cand_cap candidates
 // ------------------------------------------------------------------------------------------------
-__global__ void resolve_kernel(const float* __restrict__ z, int d, int norm_mode, const float* __restrict__ w, int k,
-                               const float* __restrict__ cc, const int* __restrict__ flag_rows,
-                               const int* __restrict__ cand, const int* __restrict__ cand_cnt, int cand_cap,
-                               int* __restrict__ best_col, int* __restrict__ full_rows, int* __restrict__ counters) {
+__global__ void __launch_bounds__(128) resolve_kernel(const float* __restrict__ z, int d, int norm_mode,
+                                                      const float* __restrict__ w, int k, const float* __restrict__ cc,
+                                                      const int* __restrict__ flag_rows, const int* __restrict__ cand,
+                                                      const int* __restrict__ cand_cnt, int cand_cap,
+                                                      int64_t* __restrict__ idx, int* __restrict__ bins,
+                                                      int* __restrict__ full_rows, int* __restrict__ counters) {
     const int nflag = counters[CNT_FLAGGED];
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nflag; p += gridDim.x * blockDim.x) {
         const int row = flag_rows[p];
@@ -96,11 +98,11 @@ __global__ void resolve_kernel(const float* __restrict__ z, int d, int norm_mode
             continue;
         }
         atomicAdd(&counters[CNT_CANDS], cnt);
+        // the normalised row is re-formed element by element (x / den is a pure function of x and den), so
+        // nothing is staged in local memory; the row itself stays in L1 across the candidates
         const float* zr = z + (size_t)row * d;
         const float den = canon_denom([&](int i) { return __ldg(zr + i); }, d, norm_mode);
-        float zf[kMaxDim];                       // normalised row, divided once (local memory, L1 resident)
-        for (int i = 0; i < d; ++i) zf[i] = __fdiv_rn(__ldg(zr + i), den);
-        const float zz = canon_sumsq([&](int i) { return zf[i]; }, d);
+        const float zz = canon_sumsq([&](int i) { return __fdiv_rn(__ldg(zr + i), den); }, d);
         float best = INFINITY;
         int bcol = 0x7fffffff;
         bool any = false;
@@ -108,13 +110,15 @@ __global__ void resolve_kernel(const float* __restrict__ z, int d, int norm_mode
             const int col = cand[(size_t)p * cand_cap + j];
             if (col >= k) continue;
             const float4* wr = reinterpret_cast<const float4*>(w + (size_t)col * d);
+            const float4* zr4 = reinterpret_cast<const float4*>(zr);
             float dot = 0.0f;
-            for (int i = 0; i < d; i += 4) {
-                const float4 wv = __ldg(wr + (i >> 2));
-                dot = __fmaf_rn(zf[i], wv.x, dot);
-                dot = __fmaf_rn(zf[i + 1], wv.y, dot);
-                dot = __fmaf_rn(zf[i + 2], wv.z, dot);
-                dot = __fmaf_rn(zf[i + 3], wv.w, dot);
+            for (int i = 0; i < (d >> 2); ++i) {
+                const float4 wv = __ldg(wr + i);
+                const float4 xv = __ldg(zr4 + i);
+                dot = __fmaf_rn(__fdiv_rn(xv.x, den), wv.x, dot);
+                dot = __fmaf_rn(__fdiv_rn(xv.y, den), wv.y, dot);
+                dot = __fmaf_rn(__fdiv_rn(xv.z, den), wv.z, dot);
+                dot = __fmaf_rn(__fdiv_rn(xv.w, den), wv.w, dot);
             }
             const float dist = canon_dist(zz, cc[col], dot);
             // torch.argmin: smallest value, first index on ties; NaN counts as the minimum
@@ -122,8 +126,12 @@ __global__ void resolve_kernel(const float* __restrict__ z, int d, int norm_mode
                 best = dist; bcol = col; any = true;
             }
         }
-        if (any) best_col[row] = bcol;
-        else full_rows[atomicAdd(&counters[CNT_FULL], 1)] = row;
+        if (any) {
+            idx[row] = (int64_t)bcol;
+            atomicAdd(&bins[bcol], 1);
+        } else {
+            full_rows[atomicAdd(&counters[CNT_FULL], 1)] = row;
+        }
     }
 }
 
@@ -141,7 +149,8 @@ __global__ void __launch_bounds__(256) exact_scan_kernel(const float* __restrict
                                                           const float* __restrict__ cc,
                                                           const int* __restrict__ row_list,
                                                           const int* __restrict__ n_rows_dev,
-                                                          int* __restrict__ best_col, float* __restrict__ denom_out) {
+                                                          int64_t* __restrict__ idx, int* __restrict__ bins,
+                                                          float* __restrict__ denom_out) {
     extern __shared__ float xs[];
     float* As  = xs;                       // [d][XR]   normalised rows, d-major
     float* Bs  = As + (size_t)d * XR;      // [XD][XC+1]
@@ -250,7 +259,8 @@ __global__ void __launch_bounds__(256) exact_scan_kernel(const float* __restrict
                     if (take) { bv = v; bi = ii; }
                 }
                 const int64_t row = row_list ? (int64_t)row_list[pos] : pos;
-                best_col[row] = bi;
+                idx[row] = (int64_t)bi;
+                if (bins != nullptr && bi >= 0 && bi < k) atomicAdd(&bins[bi], 1);
             }
         }
     }
@@ -271,14 +281,14 @@ cudaError_t launch_codebook_prep(const float* w, int k, int d, int normalize, co
 }
 
 cudaError_t launch_resolve(const float* z, int d, int norm_mode, const float* w, int k, const Workspace& ws,
-                           int cand_cap, int num_sms, cudaStream_t stream) {
-    resolve_kernel<<<num_sms * 8, 64, 0, stream>>>(z, d, norm_mode, w, k, ws.cc, ws.flag_rows, ws.cand, ws.cand_cnt,
-                                                    cand_cap, ws.best_col, ws.full_rows, ws.counters);
+                           int cand_cap, int64_t* idx, int num_sms, cudaStream_t stream) {
+    resolve_kernel<<<num_sms * 4, 128, 0, stream>>>(z, d, norm_mode, w, k, ws.cc, ws.flag_rows, ws.cand, ws.cand_cnt,
+                                                     cand_cap, idx, ws.bins_i32, ws.full_rows, ws.counters);
     return cudaGetLastError();
 }
 
 cudaError_t launch_exact_scan(const float* z, int64_t n, int d, int norm_mode, const float* w, int k,
-                              const float* cc, const int* row_list, const int* n_rows_dev, int* best_col,
+                              const float* cc, const int* row_list, const int* n_rows_dev, int64_t* idx, int* bins,
                               float* denom_out, int num_sms, cudaStream_t stream) {
     const size_t smem = sizeof(float) * ((size_t)d * XR + XD * (XC + 1) + XR + XR * 16) + sizeof(int) * XR * 16;
     static bool configured = false;
@@ -290,7 +300,7 @@ cudaError_t launch_exact_scan(const float* z, int64_t n, int d, int norm_mode, c
     int64_t blocks = n_rows_dev ? (int64_t)num_sms * 2 : (n + XR - 1) / XR;
     if (blocks > (int64_t)num_sms * 8) blocks = (int64_t)num_sms * 8;
     if (blocks < 1) blocks = 1;
-    exact_scan_kernel<<<(int)blocks, 256, smem, stream>>>(z, n, d, norm_mode, w, k, cc, row_list, n_rows_dev, best_col,
+    exact_scan_kernel<<<(int)blocks, 256, smem, stream>>>(z, n, d, norm_mode, w, k, cc, row_list, n_rows_dev, idx, bins,
                                                           denom_out);
     return cudaGetLastError();
 }

@@ -12,14 +12,15 @@ namespace mtvq {
 cudaError_t launch_codebook_prep(const float* w, int k, int d, int normalize, const Workspace& ws,
                                  cudaStream_t stream);
 
-// near-tie rows (ws.flag_rows / counters[CNT_FLAGGED]) x their collected candidates -> ws.best_col;
-// rows whose candidate list is empty or overflowed go to ws.full_rows / counters[CNT_FULL]
+// near-tie rows (ws.flag_rows / counters[CNT_FLAGGED]) x their collected candidates -> idx[row] (int64) and
+// ws.bins_i32; rows whose candidate list is empty or overflowed go to ws.full_rows / counters[CNT_FULL]
 cudaError_t launch_resolve(const float* z, int d, int norm_mode, const float* w, int k, const Workspace& ws,
-                           int cand_cap, int num_sms, cudaStream_t stream);
+                           int cand_cap, int64_t* idx, int num_sms, cudaStream_t stream);
 
-// exact first-index argmin over ALL k codes for the rows in row_list (or rows [0,n) when null)
+// exact first-index argmin over ALL k codes for the rows in row_list (or rows [0,n) when null) -> idx[row]
+// (int64) and, when bins != nullptr, the per-code counts of those rows
 cudaError_t launch_exact_scan(const float* z, int64_t n, int d, int norm_mode, const float* w, int k,
-                              const float* cc, const int* row_list, const int* n_rows_dev, int* best_col,
+                              const float* cc, const int* row_list, const int* n_rows_dev, int64_t* idx, int* bins,
                               float* denom_out, int num_sms, cudaStream_t stream);
 
 }  // namespace mtvq

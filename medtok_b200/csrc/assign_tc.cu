@@ -39,6 +39,8 @@
 #include "assign_tc.h"
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace mtvq {
 
 namespace {
@@ -55,6 +57,7 @@ constexpr int kKblkBytes  = 8 * kPlaneBytes;         // 16384: 64 fp16 per row
 constexpr int kBiasBytes  = 2 * kPlaneBytes;         // 4096
 constexpr int kDataStages = 4;
 constexpr int kBiasStages = 3;
+constexpr int kMinSplitChunks = 16;                  // COLLECT: fewest 128-code chunks per (row block, range) item
 constexpr int kRecords    = 1024;                    // 512 epilogue threads x up to 2 row tiles each
 
 // dynamic shared memory map
@@ -244,6 +247,24 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
     // (block, row tile) so that with RT < nreg the loader runs ahead of the MMAs by whole blocks
     const uint32_t nreg = (uint32_t)(65536 / a_tile_b) >= 4u ? 4u : ((uint32_t)(65536 / a_tile_b) >= 2u ? 2u : 1u);
 
+    // Work items.  ARGMAX / THRESH / DUMP reduce over a row's whole codebook, so an item is a row block.  COLLECT
+    // compares every column with a per-row threshold known up front, so columns are independent too: when the
+    // (device-side) row count leaves SMs idle -- the near-tie rows of the hard path are a few percent of N -- the
+    // codebook is split into `ksplit` chunk ranges and an item is (row block, chunk range).  ksplit minimises
+    // rounds x chunks-per-item, with >= kMinSplitChunks chunks per item so the A-tile load stays amortised.
+    int ksplit = 1;
+    if (MODE == MODE_COLLECT) {
+        int best_cost = ((nblocks + (int)gridDim.x - 1) / (int)gridDim.x) * nchunks;
+        for (int ks = 2; ks * kMinSplitChunks <= nchunks && ks <= 16; ++ks) {
+            const int cps_ = (nchunks + ks - 1) / ks;
+            if ((ks - 1) * cps_ >= nchunks) continue;            // would leave an empty range
+            const int cost = ((nblocks * ks + (int)gridDim.x - 1) / (int)gridDim.x) * cps_;
+            if (cost < best_cost) { best_cost = cost; ksplit = ks; }
+        }
+    }
+    const int cps    = (nchunks + ksplit - 1) / ksplit;          // chunks per item (the last range may be shorter)
+    const int nitems = nblocks * ksplit;
+
     // bias K-step (-||w||^2/2): needed unless every code has the same squared norm (then it is a constant
     // shift of all scores); padding codes rely on it to lose, so it stays on when K is not a tile multiple
     const bool use_bias = !(DBG && (p.debug_flags & 2)) &&
@@ -323,7 +344,10 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
         asm volatile("" : "+r"(full_addr[0]), "+r"(full_addr[1]), "+r"(empty_addr[0]), "+r"(empty_addr[1]),
                           "+r"(tld[0]), "+r"(tld[1]), "+r"(is_lane0));
 
-        for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const int blk = (MODE == MODE_COLLECT) ? item / ksplit : item;
+            const int cbeg = (MODE == MODE_COLLECT) ? (item - blk * ksplit) * cps : 0;
+            const int cend = min(nchunks, cbeg + cps);
             RowState<NTOP> st[NS];
 #pragma unroll
             for (int ss = 0; ss < NS; ++ss) {
@@ -339,7 +363,7 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                 if (MODE == MODE_COLLECT && st[ss].valid) st[ss].T = p.best_val[st[ss].row] - margin;
             }
 
-            for (int c = 0; c < nchunks; ++c) {
+            for (int c = cbeg; c < cend; ++c) {
 #pragma unroll
                 for (int si = 0; si < 2; ++si) {
                     const int s = pair + 2 * si;                 // accumulator slot
@@ -423,9 +447,15 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                                 }
                             }
                         const bool flagged = st[ss].valid && ((cnt != 1) || (m2all >= thrF) || (col >= p.k));
-                        if (st[ss].valid) {
-                            p.best_val[st[ss].row] = M;
-                            p.best_col[st[ss].row] = flagged ? -1 : col;
+                        if (st[ss].valid) p.best_val[st[ss].row] = M;
+                        // decided rows leave the kernel as final int64 indices + histogram counts (one RED per
+                        // distinct code in the warp), spread over the whole tensor pass instead of a row kernel
+                        const bool decided = st[ss].valid && !flagged;
+                        const unsigned dall = __ballot_sync(0xffffffffu, decided);
+                        if (decided) {
+                            p.idx_out[st[ss].row] = (int64_t)col;
+                            const unsigned same = __match_any_sync(dall, col);
+                            if (lane == __ffs(same) - 1) atomicAdd(&p.bins[col], __popc(same));
                         }
                         const unsigned ball = __ballot_sync(0xffffffffu, flagged);
                         if (ball) {
@@ -476,7 +506,8 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
         // produced with one reciprocal and a multiply per element instead of an IEEE division.
         const int r = (int)tid_x - kLoadWarp0 * 32;
         uint32_t bi = 0;
-        for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x, ++bi) {
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++bi) {
+            const int blk = (MODE == MODE_COLLECT) ? item / ksplit : item;
             const bool skip = DBG && (p.debug_flags & 4) && bi > 0;   // timing experiment only
             for (int g = 0; g < RT; ++g) {
                 const int64_t pos = (int64_t)blk * rows_blk + g * kTileRows + r;
@@ -531,14 +562,14 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                     uint4 q[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) q[j] = (j < nplanes) ? pack8(j) : make_uint4(0, 0, 0, 0);
-                    mbar_wait(&bars.a_empty[areg], apar ^ 1);
+                    mbar_wait_backoff(&bars.a_empty[areg], apar ^ 1, 400);
                     if (!skip) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
                             if (j < nplanes) *reinterpret_cast<uint4*>(tile + j * kPlaneBytes) = q[j];
                     }
                 } else {
-                    mbar_wait(&bars.a_empty[areg], apar ^ 1);
+                    mbar_wait_backoff(&bars.a_empty[areg], apar ^ 1, 400);
                     if (!skip)
                         for (int j = 0; j < nplanes; ++j) *reinterpret_cast<uint4*>(tile + j * kPlaneBytes) = pack8(j);
                 }
@@ -552,8 +583,10 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
         if (elect_one()) {
             const unsigned char* img = static_cast<const unsigned char*>(p.b_image);
             uint32_t itD = 0, itB = 0;
-            for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
-                for (int c = 0; c < nchunks; ++c) {
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const int cbeg = (MODE == MODE_COLLECT) ? (item % ksplit) * cps : 0;
+                const int cend = min(nchunks, cbeg + cps);
+                for (int c = cbeg; c < cend; ++c) {
                     const unsigned char* tile = img + (size_t)c * tile_b;
                     for (int kb = 0; kb < nkblk; ++kb, ++itD) {
                         const int st = itD % kDataStages;
@@ -593,16 +626,18 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
             uint32_t uses = 0, bi = 0;
             uint32_t chunk0 = 0;                     // chunks issued by the CTA before this block
             const bool tracing = DBG && (p.trace != nullptr) && blockIdx.x == 0 && j == 0;
-            for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x, ++bi, chunk0 += nchunks) {
+            int cbeg = 0, cend = nchunks;
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++bi, chunk0 += (uint32_t)(cend - cbeg)) {
+                if (MODE == MODE_COLLECT) { cbeg = (item % ksplit) * cps; cend = min(nchunks, cbeg + cps); }
                 // Every issuer walks EVERY chunk so that each shared barrier sees all four issuers once per
                 // phase (an mbarrier parity wait is only meaningful within one phase of the barrier);
                 // it issues MMAs only for the tiles it owns: c % G == j / RT.
                 bool first = true;
                 const uint32_t aq = bi * RT + g, areg = aq % nreg, apar = (aq / nreg) & 1;   // A region ring
                 const uint64_t dA = dA0 + (uint64_t)(areg * ((uint32_t)a_tile_b >> 4));
-                for (int c = 0; c < nchunks; ++c) {
+                for (int c = cbeg; c < cend; ++c) {
                     const bool own = (c % G) == (j / RT);
-                    const uint32_t gc = chunk0 + c;                       // running chunk number
+                    const uint32_t gc = chunk0 + (uint32_t)(c - cbeg);    // running chunk number
                     const uint32_t itD = gc * nkblk;
                     const uint32_t sb = gc % kBiasStages;
                     // operands first, accumulator last: when the epilogue hands the slot back, every MMA of
@@ -635,7 +670,7 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                     if (use_bias) umma_f16(tacc, dOnes, dBB0 + (uint64_t)(sb * (kBiasBytes >> 4)), idesc, 1u);
                     umma_commit(&bars.acc_full[j]);
                     if (use_bias) umma_commit(&bars.bb_empty[sb]);
-                    if (c + G >= nchunks) umma_commit(&bars.a_empty[areg]);   // this issuer's last tile of the block
+                    if (c + G >= cend) umma_commit(&bars.a_empty[areg]);   // this issuer's last tile of the block
                     if (DBG && tracing && uses <= 512) p.trace[(uses - 1) * 8 + 1] = clock64();
                 }
                 if (first) {
@@ -675,6 +710,11 @@ static cudaError_t launch_one(const CoarseParams& p, int grid, cudaStream_t stre
 
 int coarse_row_tiles(int d, int64_t nrows, int num_sms) {
     int rt = d <= 64 ? 4 : (d <= 128 ? 2 : 1);
+    {   // tuning experiments only: MTVQ_ROW_TILES caps the rows per block
+        static int cap = -1;
+        if (cap < 0) { const char* e = getenv("MTVQ_ROW_TILES"); cap = e ? atoi(e) : 0; }
+        if (cap == 1 || cap == 2) rt = rt < cap ? rt : cap;
+    }
     // keep every SM busy when there are few rows: shrink the block until there are >= 2 waves
     while (rt > 1 && (nrows + rt * 128 - 1) / (rt * 128) < 2 * (int64_t)num_sms) rt >>= 1;
     return rt;

@@ -24,7 +24,9 @@ struct CoarseParams {
     const float* meta;       // META_MARGIN ...
     // outputs / state
     float*       denom;      // [n] or nullptr
-    int*         best_col;   // [n]
+    int64_t*     idx_out;    // [n]  ARGMAX: winning code of every decided row (torch.argmin dtype); near-tie rows
+                             //      are written by the resolve kernels
+    int*         bins;       // [k]  ARGMAX: per-code row counts of the decided rows (zeroed by the caller)
     float*       best_val;   // [n]
     int*         flag_rows;  // [n]
     int*         counters;   // [CNT_COUNT]

@@ -169,6 +169,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
     } while (!ok);
 }
 
+// long waits off the critical path (the A loader waits ~a whole row block for its tile to be released): poll with
+// an explicit sleep in between, so the polling loop stops competing with the epilogue warps for issue slots
+// (it was 13% of all warp instructions of the coarse kernel, profiles/r02)
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t sleep_ns) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) break;
+        __nanosleep(sleep_ns);
+    }
+}
+
 // same, on a precomputed shared-space address (keeps address arithmetic out of hot loops)
 __device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity, uint32_t hint_ns = 20000u) {
     uint32_t ok;

@@ -1,6 +1,6 @@
 // rows.cu -- the HBM-bound row kernels around the assignment (all coalesced / vectorised, no N x K
 // intermediate anywhere):
-//   emit_idx_kernel     int32 winners -> int64 indices (torch.argmin dtype)
+//   hist_kernel         per-code row counts of caller-provided indices
 //   gather_ste_kernel   z_q = zf + (w[idx] - zf), SSE (fp64), per-code counts         (:181,183-194,212-214)
 //   scan / scatter      counting sort of the rows by code
 //   segsum_kernel       embed_sum[k,:] = sum of the rows of code k, fp64 accumulation      (:202)
@@ -11,19 +11,16 @@
 
 namespace mtvq {
 
-// int32 winners -> int64 indices (torch.argmin dtype) and, in the same pass, the per-code counts
-// (F.one_hot(...).sum(0) of the reference, :183-194): equal codes inside a warp are merged with
-// match.any so a hot code costs one 32-bit RED per warp instead of 32.
-template <typename IdxT, bool WRITE_IDX>
-__global__ void __launch_bounds__(256) emit_hist_kernel(const IdxT* __restrict__ src, int64_t n,
-                                                         int64_t* __restrict__ idx, int* __restrict__ bins) {
+// per-code row counts of a given index vector (F.one_hot(...).sum(0) of the reference, :183-194; the assign kernels
+// count their own winners, this serves mtvq_code_sums on caller-provided indices): equal codes inside a warp are
+// merged with match.any so a hot code costs one 32-bit RED per warp instead of 32.
+__global__ void __launch_bounds__(256) hist_kernel(const int64_t* __restrict__ src, int64_t n, int* __restrict__ bins) {
     const int lane = threadIdx.x & 31;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x - lane; base < n; base += nthreads) {
         const int64_t row = base + lane;
         const bool valid = row < n;
         const int code = valid ? (int)src[row] : -1;
-        if (WRITE_IDX && valid) idx[row] = (int64_t)code;
         const unsigned act = __ballot_sync(0xffffffffu, valid);
         if (valid) {
             const unsigned same = __match_any_sync(act, code);
@@ -257,18 +254,10 @@ static int grid_for(int64_t work, int per_block, int num_sms, int max_waves) {
     return (int)(b < 1 ? 1 : b);
 }
 
-cudaError_t launch_emit_idx(const int* best_col, int64_t n, int64_t* idx, int* bins_i32, int k, int num_sms,
-                            cudaStream_t s) {
-    cudaError_t e = cudaMemsetAsync(bins_i32, 0, sizeof(int) * k, s);
-    if (e != cudaSuccess) return e;
-    emit_hist_kernel<int, true><<<grid_for(n, 256, num_sms, 8), 256, 0, s>>>(best_col, n, idx, bins_i32);
-    return cudaGetLastError();
-}
-
 cudaError_t launch_hist_idx64(const int64_t* idx, int64_t n, int* bins_i32, int k, int num_sms, cudaStream_t s) {
     cudaError_t e = cudaMemsetAsync(bins_i32, 0, sizeof(int) * k, s);
     if (e != cudaSuccess) return e;
-    emit_hist_kernel<int64_t, false><<<grid_for(n, 256, num_sms, 8), 256, 0, s>>>(idx, n, nullptr, bins_i32);
+    hist_kernel<<<grid_for(n, 256, num_sms, 8), 256, 0, s>>>(idx, n, bins_i32);
     return cudaGetLastError();
 }
 

@@ -7,8 +7,6 @@
 
 namespace mtvq {
 
-cudaError_t launch_emit_idx(const int* best_col, int64_t n, int64_t* idx, int* bins_i32, int k, int num_sms,
-                            cudaStream_t s);
 cudaError_t launch_hist_idx64(const int64_t* idx, int64_t n, int* bins_i32, int k, int num_sms, cudaStream_t s);
 cudaError_t launch_gather_ste(const float* z, const float* denom, const float* w, const int64_t* idx, int64_t n, int d,
                               int k, float* z_q, double* stats, int num_sms, cudaStream_t s);

@@ -22,7 +22,6 @@ struct Workspace {
     float*   meta;         // [META_COUNT]
     // row side
     float*   denom;        // [n]
-    int*     best_col;     // [n]   winning code, -1 while unresolved
     float*   best_val;     // [n]   best coarse score
     int*     flag_rows;    // [n]   rows needing exact re-scoring
     int*     cand;         // [n * kCandMax]  (soft: [n * cand_cap])
@@ -59,7 +58,6 @@ inline Workspace carve(void* base, int64_t n, int d, int k, int topk) {
     w.codes_n   = (float*)take(topk > 1 ? sizeof(float) * (size_t)k * d : 0);
     w.meta      = (float*)take(sizeof(float) * META_COUNT);
     w.denom     = (float*)take(sizeof(float) * n);
-    w.best_col  = (int*)take(sizeof(int) * n);
     w.best_val  = (float*)take(sizeof(float) * n);
     w.flag_rows = (int*)take(sizeof(int) * n);
     w.cand      = (int*)take(sizeof(int) * n * cand_cap);

@@ -148,3 +148,76 @@ if what == "soft":
 os.makedirs("gpurun_out", exist_ok=True)
 tag = what + ("_swap" if os.environ.get("MTVQ_DESC_SWAP") == "1" else "")
 json.dump(out, open(f"gpurun_out/probe_{tag}.json", "w"), indent=1)
+
+if what == "pcie":
+    # pinned host <-> device copy bandwidth of this box (what bounds bench.py's e2e leg)
+    res = {}
+    for mb in (16, 64, 256):
+        nbytes = mb << 20
+        h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        dbuf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        for direction in ("h2d", "d2h"):
+            best = 1e9
+            for _ in range(5):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                if direction == "h2d":
+                    dbuf.copy_(h, non_blocking=True)
+                else:
+                    h.copy_(dbuf, non_blocking=True)
+                b.record(); torch.cuda.synchronize()
+                best = min(best, a.elapsed_time(b))
+            res[f"{direction}_{mb}MiB_GBps"] = nbytes / (best * 1e-3) / 1e9
+    # both directions at once on two streams
+    h1 = torch.empty(256 << 20, dtype=torch.uint8).pin_memory(); h2 = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+    d1 = torch.empty(256 << 20, dtype=torch.uint8, device=dev); d2 = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    with torch.cuda.stream(s1):
+        d1.copy_(h1, non_blocking=True)
+    with torch.cuda.stream(s2):
+        h2.copy_(d2, non_blocking=True)
+    torch.cuda.synchronize()
+    res["duplex_256MiB_each_GBps_per_dir"] = (256 << 20) / (time.perf_counter() - t0) / 1e9
+    out["pcie"] = res
+    print("PCIE", json.dumps(res))
+    json.dump(out, open("gpurun_out/probe_pcie.json", "w"), indent=1)
+
+if what == "e2e":
+    # where the host-buffer pipeline's time goes: sustained H2D (1 stream / 2 streams x half batches), then the pipeline
+    from medtok_b200.host_pipeline import HostStream
+    from medtok_b200.norm_ema_quantizer import NormEMAVectorQuantizer
+    n, d, k = 1 << 20, 64, 8192
+    res = {}
+    host = [torch.randn(n, d).pin_memory() for _ in range(2)]
+    dbuf = [torch.empty(n, d, device=dev) for _ in range(2)]
+    def timed(fn, reps=20):
+        torch.cuda.synchronize(); t0 = time.perf_counter(); fn(reps); torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps * 1e3
+    def one_stream(reps):
+        for i in range(reps):
+            dbuf[i % 2].copy_(host[i % 2], non_blocking=True)
+    streams = [torch.cuda.Stream() for _ in range(4)]
+    def multi(ns):
+        def run(reps):
+            per = n // ns
+            for i in range(reps):
+                for s in range(ns):
+                    with torch.cuda.stream(streams[s]):
+                        dbuf[i % 2][s * per:(s + 1) * per].copy_(host[i % 2][s * per:(s + 1) * per], non_blocking=True)
+        return run
+    res["h2d_ms_1stream"] = timed(one_stream)
+    res["h2d_ms_2streams"] = timed(multi(2))
+    res["h2d_ms_4streams"] = timed(multi(4))
+    q = NormEMAVectorQuantizer(k, d, 0.25).to(dev).train()
+    with torch.no_grad():
+        for depth in (2, 3):
+            hs = HostStream(q, n, d, dev, depth=depth)
+            hs.run(host[i % 2] for i in range(3)); hs.finish()
+            def pipe(reps):
+                hs.run(host[i % 2] for i in range(reps)); hs.finish()
+            res[f"pipeline_ms_depth{depth}"] = timed(pipe)
+    out["e2e"] = res
+    print("E2E", json.dumps(res))
+    json.dump(out, open("gpurun_out/probe_e2e.json", "w"), indent=1)
