@@ -85,7 +85,7 @@ void fill_coarse(CoarseParams& p, const float* z, int64_t n, int d, int norm_mod
     p.z = z; p.n = n; p.d = d; p.norm_mode = norm_mode;
     p.b_image = ws.b_image; p.kpad = pad_codes(k); p.k = k; p.meta = ws.meta;
     p.denom = denom; p.idx_out = idx_out; p.bins = ws.bins_i32; p.best_val = ws.best_val;
-    p.flag_rows = ws.flag_rows; p.counters = ws.counters;
+    p.flag_rows = ws.flag_rows; p.over_rows = ws.full_rows; p.counters = ws.counters;
     p.cand = ws.cand; p.cand_cnt = ws.cand_cnt; p.cand_cap = cand_capacity(topk); p.topk = topk;
     p.trace = g_trace;
     p.lbo_bytes = desc_swap() ? 128 : 2048;
@@ -113,14 +113,14 @@ int assign_rows(const float* z, int64_t n, int d, int norm_mode, const float* co
     MTVQ_CUDA(launch_coarse(p, MODE_ARGMAX, coarse_row_tiles(d, n, di.num_sms), di.num_sms, st), "coarse argmax");
     if (g_ev_after) cudaEventRecord(g_ev_after, st);
     g_ev_before = g_ev_after = nullptr;
-    // near-tie rows: collect every code within the margin, then decide in exact fp32
+    // near-tie rows (a few percent) carry a candidate list out of the tensor pass; the few whose list is incomplete
+    // (a third granule within the margin) get it from a COLLECT pass -- the row count is only known on the device,
+    // the kernel splits the codebook over CTAs to fill the SMs (assign_tc.cu "work items").  Exact fp32 decides.
     CoarseParams c = p;
-    c.row_list = ws.flag_rows;
-    c.n_rows_dev = ws.counters + CNT_FLAGGED;
+    c.row_list = ws.full_rows;                    // the over list (consumed before resolve reuses the buffer)
+    c.n_rows_dev = ws.counters + CNT_OVER;
     c.denom = nullptr;
-    // the row count is only known on the device: the kernel takes the widest row block the A area holds and
-    // splits the codebook over CTAs when that leaves SMs idle (assign_tc.cu "work items")
-    MTVQ_CUDA(launch_coarse(c, MODE_COLLECT, coarse_row_tiles(d, (int64_t)1 << 40, di.num_sms), di.num_sms, st), "coarse collect");
+    MTVQ_CUDA(launch_coarse(c, MODE_COLLECT, 1, di.num_sms, st), "coarse collect");   // few rows: 128-row items
     MTVQ_CUDA(launch_resolve(z, d, norm_mode, codes, k, ws, p.cand_cap, idx, di.num_sms, st), "resolve");
     MTVQ_CUDA(launch_exact_scan(z, n, d, norm_mode, codes, k, ws.cc, ws.full_rows, ws.counters + CNT_FULL, idx, ws.bins_i32,
                                 nullptr, di.num_sms, st), "exact_scan(overflow)");
@@ -230,8 +230,12 @@ int mtvq_hard_forward(const float* z, int64_t n, int d, int norm_mode, float* we
     MTVQ_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * mtvq_stats_len(d, k), st), "memset stats");
     if (int r = assign_rows(z, n, d, norm_mode, weight, k, ws.denom, idx, ws, di, false, st)) return r;
     if (n > 0) {
-        MTVQ_CUDA(launch_gather_ste(z, ws.denom, weight, idx, n, d, k, z_q, stats, di.num_sms, st), "gather_ste");
-        MTVQ_CUDA(launch_code_sums(z, ws.denom, idx, n, d, k, stats, ws, upd_w, di.num_sms, st), "code_sums");
+        if (upd_w) {   // per-code sums wanted: one fused pass over the rows in code-sorted order
+            MTVQ_CUDA(launch_sorted_rows(z, ws.denom, weight, idx, n, d, k, z_q, stats, ws, di.num_sms, st), "sorted_rows");
+        } else {       // streaming gather/STE/SSE + bins only
+            MTVQ_CUDA(launch_gather_ste(z, ws.denom, weight, idx, n, d, k, z_q, stats, di.num_sms, st), "gather_ste");
+            MTVQ_CUDA(launch_code_sums(z, ws.denom, idx, n, d, k, stats, ws, false, di.num_sms, st), "code_sums");
+        }
     }
     if (flags & MTVQ_F_SKIP_FINALIZE) {
         MTVQ_CUDA(launch_loss(stats, k, d, beta, loss, st), "loss");

@@ -81,58 +81,171 @@ __global__ void codebook_prep_kernel(const float* __restrict__ w, int k, int kpa
 }
 
 // ------------------------------------------------------------------------------------------------
-// near-tie resolve: one thread per flagged row, exact distances of <= cand_cap candidates
+// near-tie resolve: one WARP per flagged row.  The row's candidate list holds single columns (>= 0) and whole
+// 32-column granules (-(granule + 1)).  The normalised row sits in shared memory (formed once, coalesced); a
+// granule's 32 codes are staged through shared memory in 32-dimension slabs with coalesced loads, lane l then
+// runs the sequential fmaf chain of code l.  Single columns are spread over the lanes and read their code directly.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) resolve_kernel(const float* __restrict__ z, int d, int norm_mode,
-                                                      const float* __restrict__ w, int k, const float* __restrict__ cc,
-                                                      const int* __restrict__ flag_rows, const int* __restrict__ cand,
-                                                      const int* __restrict__ cand_cnt, int cand_cap,
-                                                      int64_t* __restrict__ idx, int* __restrict__ bins,
-                                                      int* __restrict__ full_rows, int* __restrict__ counters) {
+namespace {
+constexpr int kResWarps = 8;     // warps (rows in flight) per CTA
+constexpr int kResSlab  = 32;    // dimensions staged per step
+
+// lexicographic (NaN first, then value, then index) minimum: torch.argmin semantics
+__device__ __forceinline__ bool better(float v, int i, float bv, int bi) {
+    const bool vn = v != v, bn = bv != bv;
+    if (bi == 0x7fffffff) return i != 0x7fffffff;
+    if (i == 0x7fffffff) return false;
+    if (vn != bn) return vn;
+    if (vn) return i < bi;
+    return v < bv || (v == bv && i < bi);
+}
+}  // namespace
+
+__global__ void __launch_bounds__(kResWarps * 32, 4) resolve_kernel(
+    const float* __restrict__ z, int d, int norm_mode, const float* __restrict__ w, int k, const float* __restrict__ cc,
+    const int* __restrict__ flag_rows, const int* __restrict__ cand, const int* __restrict__ cand_cnt, int cand_cap,
+    int64_t* __restrict__ idx, int* __restrict__ bins, int* __restrict__ full_rows, int* __restrict__ counters) {
+    __shared__ __align__(16) float xs[kResWarps][kMaxDim];                  // normalised row per warp
+    // granule slab per warp; row stride 36 floats keeps 16-byte accesses aligned and conflict free: within a
+    // quarter-warp phase the 8 lanes' rows (or 8 consecutive float4 of a row) fall into 8 different bank quads
+    __shared__ __align__(16) float ws_[kResWarps][32][kResSlab + 4];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int nflag = counters[CNT_FLAGGED];
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nflag; p += gridDim.x * blockDim.x) {
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    int ncands = 0;
+    for (int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < nflag; p += nwarps) {
         const int row = flag_rows[p];
-        const int cnt = cand_cnt[p];
+        const int cnt = cand_cnt[row];            // candidate lists are indexed by row
         if (cnt <= 0 || cnt > cand_cap) {
-            full_rows[atomicAdd(&counters[CNT_FULL], 1)] = row;
+            if (lane == 0) full_rows[atomicAdd(&counters[CNT_FULL], 1)] = row;
             continue;
         }
-        atomicAdd(&counters[CNT_CANDS], cnt);
-        // the normalised row is re-formed element by element (x / den is a pure function of x and den), so
-        // nothing is staged in local memory; the row itself stays in L1 across the candidates
         const float* zr = z + (size_t)row * d;
-        const float den = canon_denom([&](int i) { return __ldg(zr + i); }, d, norm_mode);
-        const float zz = canon_sumsq([&](int i) { return __fdiv_rn(__ldg(zr + i), den); }, d);
-        float best = INFINITY;
+        __syncwarp();
+        for (int i = lane; i < d; i += 32) xs[wib][i] = __ldg(zr + i);      // raw row, one coalesced round trip
+        __syncwarp();
+        // canonical norm and squared norm with their independent accumulator chains spread over the lanes: the
+        // additions inside each chain and the order in which the chains are folded are exactly those of
+        // canon_norm8 / canon_sumsq (common.cuh), only the chains run side by side
+        float den;
+        if (norm_mode == 0) {
+            const int v = lane & 7;
+            float a = 0.f;
+            for (int c = 0; c < d; c += 8) { const float x = xs[wib][c + v]; a = __fadd_rn(a, __fmul_rn(x, x)); }
+            float sm = __shfl_sync(0xffffffffu, a, 0);
+#pragma unroll
+            for (int t = 1; t < 8; ++t) sm = __fadd_rn(sm, __shfl_sync(0xffffffffu, a, t));
+            den = __fsqrt_rn(sm);
+            den = den < kNormEps ? kNormEps : den;
+        } else {
+            den = canon_denom([&](int i) { return xs[wib][i]; }, d, norm_mode);
+        }
+        __syncwarp();
+        for (int i = lane; i < d; i += 32) xs[wib][i] = __fdiv_rn(xs[wib][i], den);
+        __syncwarp();
+        float zz;
+        {
+            const int u = lane >> 3, v = lane & 7;
+            const int nvec = d >> 3, n4 = nvec >> 2;
+            float a = 0.f;
+            for (int c = 0; c < n4; ++c) { const float e = xs[wib][(c * 4 + u) * 8 + v]; a = __fadd_rn(a, __fmul_rn(e, e)); }
+            if (u == 0)
+                for (int i = n4 * 4; i < nvec; ++i) { const float e = xs[wib][i * 8 + v]; a = __fadd_rn(a, __fmul_rn(e, e)); }
+            float f = __shfl_sync(0xffffffffu, a, v);                                 // acc[0][v]
+            f = __fadd_rn(f, __shfl_sync(0xffffffffu, a, 8 + v));
+            f = __fadd_rn(f, __shfl_sync(0xffffffffu, a, 16 + v));
+            f = __fadd_rn(f, __shfl_sync(0xffffffffu, a, 24 + v));
+            float fin = 0.f;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) fin = __fadd_rn(fin, __shfl_sync(0xffffffffu, f, t));
+            zz = fin;
+        }
+        float best = 0.0f;
         int bcol = 0x7fffffff;
-        bool any = false;
-        for (int j = 0; j < cnt; ++j) {
-            const int col = cand[(size_t)p * cand_cap + j];
-            if (col >= k) continue;
-            const float4* wr = reinterpret_cast<const float4*>(w + (size_t)col * d);
-            const float4* zr4 = reinterpret_cast<const float4*>(zr);
+        const int mine = lane < cnt ? cand[(size_t)row * cand_cap + lane] : 0x7fffffff;   // cand_cap <= 32
+        // single columns: lane j scores entry j
+        if (lane < cnt && mine >= 0 && mine < k) {
+            const float4* wr = reinterpret_cast<const float4*>(w + (size_t)mine * d);
             float dot = 0.0f;
-            for (int i = 0; i < (d >> 2); ++i) {
-                const float4 wv = __ldg(wr + i);
-                const float4 xv = __ldg(zr4 + i);
-                dot = __fmaf_rn(__fdiv_rn(xv.x, den), wv.x, dot);
-                dot = __fmaf_rn(__fdiv_rn(xv.y, den), wv.y, dot);
-                dot = __fmaf_rn(__fdiv_rn(xv.z, den), wv.z, dot);
-                dot = __fmaf_rn(__fdiv_rn(xv.w, den), wv.w, dot);
+            for (int i0 = 0; i0 < (d >> 2); i0 += 4) {     // d % 16 == 0: four 16-byte loads in flight per step
+                float4 wv[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) wv[t] = __ldg(wr + i0 + t);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const float4 xv = *reinterpret_cast<const float4*>(&xs[wib][4 * (i0 + t)]);
+                    dot = __fmaf_rn(xv.x, wv[t].x, dot);
+                    dot = __fmaf_rn(xv.y, wv[t].y, dot);
+                    dot = __fmaf_rn(xv.z, wv[t].z, dot);
+                    dot = __fmaf_rn(xv.w, wv[t].w, dot);
+                }
             }
-            const float dist = canon_dist(zz, cc[col], dot);
-            // torch.argmin: smallest value, first index on ties; NaN counts as the minimum
-            if (!any || dist < best || (dist == best && col < bcol) || (dist != dist && !(best != best))) {
-                best = dist; bcol = col; any = true;
+            best = canon_dist(zz, cc[mine], dot);
+            bcol = mine;
+            ++ncands;
+        }
+        // whole granules: lane l scores code 32 * granule + l.  A slab = 32 codes x 32 dims: lane t loads float4
+        // (t & 7) of codes (t >> 3) + 4 r; the next slab's loads are in flight while this one's chain runs.
+        for (int j = 0; j < cnt; ++j) {
+            const int e = __shfl_sync(0xffffffffu, mine, j);
+            if (e >= 0) continue;
+            const int code0 = (-e - 1) * 32;
+            const int code = code0 + lane;
+            float4 pre[8];
+            auto issue = [&](int d0) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const int cl = (lane >> 3) + 4 * r;
+                    pre[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (code0 + cl < k && d0 + 4 * (lane & 7) < d)
+                        pre[r] = __ldg(reinterpret_cast<const float4*>(w + (size_t)(code0 + cl) * d + d0) + (lane & 7));
+                }
+            };
+            issue(0);
+            float dot = 0.0f;
+            for (int d0 = 0; d0 < d; d0 += kResSlab) {
+                __syncwarp();
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    *reinterpret_cast<float4*>(&ws_[wib][(lane >> 3) + 4 * r][4 * (lane & 7)]) = pre[r];
+                __syncwarp();
+                if (d0 + kResSlab < d) issue(d0 + kResSlab);
+                const int dl4 = min(kResSlab, d - d0) >> 2;   // d is a multiple of 16, not necessarily of 32
+#pragma unroll 4
+                for (int i = 0; i < dl4; ++i) {
+                    const float4 xv = *reinterpret_cast<const float4*>(&xs[wib][d0 + 4 * i]);
+                    const float4 wv = *reinterpret_cast<const float4*>(&ws_[wib][lane][4 * i]);
+                    dot = __fmaf_rn(xv.x, wv.x, dot);
+                    dot = __fmaf_rn(xv.y, wv.y, dot);
+                    dot = __fmaf_rn(xv.z, wv.z, dot);
+                    dot = __fmaf_rn(xv.w, wv.w, dot);
+                }
+            }
+            if (code < k) {
+                const float dist = canon_dist(zz, cc[code], dot);
+                if (better(dist, code, best, bcol)) { best = dist; bcol = code; }
+                ++ncands;
             }
         }
-        if (any) {
-            idx[row] = (int64_t)bcol;
-            atomicAdd(&bins[bcol], 1);
-        } else {
-            full_rows[atomicAdd(&counters[CNT_FULL], 1)] = row;
+        // warp-wide lexicographic minimum
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bcol, o);
+            if (better(ov, oi, best, bcol)) { best = ov; bcol = oi; }
+        }
+        if (lane == 0) {
+            if (bcol != 0x7fffffff) {
+                idx[row] = (int64_t)bcol;
+                atomicAdd(&bins[bcol], 1);
+            } else {
+                full_rows[atomicAdd(&counters[CNT_FULL], 1)] = row;
+            }
         }
     }
+    __syncwarp();
+    ncands = __reduce_add_sync(0xffffffffu, ncands);
+    if (lane == 0 && ncands) atomicAdd(&counters[CNT_CANDS], ncands);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -282,8 +395,9 @@ cudaError_t launch_codebook_prep(const float* w, int k, int d, int normalize, co
 
 cudaError_t launch_resolve(const float* z, int d, int norm_mode, const float* w, int k, const Workspace& ws,
                            int cand_cap, int64_t* idx, int num_sms, cudaStream_t stream) {
-    resolve_kernel<<<num_sms * 4, 128, 0, stream>>>(z, d, norm_mode, w, k, ws.cc, ws.flag_rows, ws.cand, ws.cand_cnt,
-                                                     cand_cap, idx, ws.bins_i32, ws.full_rows, ws.counters);
+    resolve_kernel<<<num_sms * 4, kResWarps * 32, 0, stream>>>(z, d, norm_mode, w, k, ws.cc, ws.flag_rows, ws.cand,
+                                                                ws.cand_cnt, cand_cap, idx, ws.bins_i32, ws.full_rows,
+                                                                ws.counters);
     return cudaGetLastError();
 }
 

@@ -57,7 +57,8 @@ constexpr int kKblkBytes  = 8 * kPlaneBytes;         // 16384: 64 fp16 per row
 constexpr int kBiasBytes  = 2 * kPlaneBytes;         // 4096
 constexpr int kDataStages = 4;
 constexpr int kBiasStages = 3;
-constexpr int kMinSplitChunks = 16;                  // COLLECT: fewest 128-code chunks per (row block, range) item
+constexpr int kMinSplitChunks = 2;                   // COLLECT: fewest 128-code chunks per (row block, range) item
+constexpr int kItemLoadCost   = 6;                   // COLLECT: an item's A-tile load + pipeline fill, in chunk-times
 constexpr int kRecords    = 1024;                    // 512 epilogue threads x up to 2 row tiles each
 
 // dynamic shared memory map
@@ -144,8 +145,9 @@ __device__ __forceinline__ void record_store(unsigned char* slots, int rec, cons
 // per-row running state of one row tile
 template <int NTOP>
 struct RowState {
-    float m1, m2, thr;      // ARGMAX: best granule max, best "other" max, m1 - margin
-    int   best_chunk;
+    float m1, m2, m3, thr;  // ARGMAX: best granule max (its scores are in the record), second-best granule max,
+                            //         max over every other granule seen, m1 - margin
+    int   best_chunk, chunk2;   //     granule ids of m1 and m2
     float top[NTOP];        // THRESH: largest granule maxima, descending
     float T;                // COLLECT: threshold
     int64_t pos, row;
@@ -164,22 +166,7 @@ __device__ __forceinline__ void consume(const float (&v)[32], int chunk, RowStat
         return;
     }
     const float cmax = max32(v);
-    if (MODE == MODE_ARGMAX) {
-        const bool trig = cmax >= st.thr;
-        if (__any_sync(0xffffffffu, trig)) {
-            if (trig) {
-                if (cmax > st.m1) {          // new record: remember the granule
-                    st.m2 = fmaxf(st.m2, st.m1);
-                    st.m1 = cmax;
-                    st.thr = cmax - margin;
-                    st.best_chunk = chunk;
-                    record_store(slots, rec, v);
-                } else {                      // another granule within the margin
-                    st.m2 = fmaxf(st.m2, cmax);
-                }
-            }
-        }
-    } else if (MODE == MODE_THRESH) {
+    if (MODE == MODE_THRESH) {
         topn_insert<NTOP>(st.top, cmax);
     } else if (MODE == MODE_COLLECT) {
         const bool trig = cmax >= st.T;
@@ -192,8 +179,8 @@ __device__ __forceinline__ void consume(const float (&v)[32], int chunk, RowStat
                 while (hits) {
                     const int i = __ffs(hits) - 1;
                     hits &= hits - 1;
-                    const int at = atomicAdd(&p.cand_cnt[st.pos], 1);
-                    if (at < p.cand_cap) p.cand[st.pos * p.cand_cap + at] = chunk * kChunk + i;
+                    const int at = atomicAdd(&p.cand_cnt[st.row], 1);         // candidate lists are indexed by row
+                    if (at < p.cand_cap) p.cand[st.row * p.cand_cap + at] = chunk * kChunk + i;
                 }
             }
         }
@@ -201,7 +188,9 @@ __device__ __forceinline__ void consume(const float (&v)[32], int chunk, RowStat
 }
 
 // ARGMAX on a thread's whole 64-column half-tile: one trigger test per 64 scores.  `va` holds granule `chunk`,
-// `vb` granule `chunk + 1`.
+// `vb` granule `chunk + 1`.  Per thread the best granule is kept by value (the record), the second-best by id
+// (chunk2; listed wholesale for the exact re-scoring if it ends up within the margin) and everything else only as
+// a maximum (m3; if THAT ends up within the margin the row falls back to a COLLECT pass).
 template <int NTOP>
 __device__ __forceinline__ void consume_argmax64(const float (&va)[32], const float (&vb)[32], int chunk,
                                                  RowState<NTOP>& st, float margin, unsigned char* slots, int rec) {
@@ -210,17 +199,46 @@ __device__ __forceinline__ void consume_argmax64(const float (&va)[32], const fl
     const bool trig = cmax >= st.thr;
     if (__any_sync(0xffffffffu, trig)) {
         if (trig) {
-            if (cmax > st.m1) {          // new record: remember the better granule; the other one counts as "other"
-                st.m2 = fmaxf(fmaxf(st.m2, st.m1), fminf(ma, mb));
+            const bool b_wins = mb > ma;
+            const float lo = fminf(ma, mb);
+            if (cmax > st.m1) {          // new record
+                const float nthr = cmax - margin;
+                // Only granules within the margin of the CURRENT best can matter at the end (the best only grows), so
+                // second place is tracked only in the rare case that the old record or the losing granule is that close;
+                // otherwise m2 / m3 keep stale values below nthr, which the final test ignores.
+                if (fmaxf(st.m1, lo) >= nthr) {
+                    const int lo_c = b_wins ? chunk : chunk + 1;
+                    if (lo > st.m1) { st.m3 = fmaxf(fmaxf(st.m3, st.m2), st.m1); st.m2 = lo;    st.chunk2 = lo_c; }
+                    else            { st.m3 = fmaxf(fmaxf(st.m3, st.m2), lo);    st.m2 = st.m1; st.chunk2 = st.best_chunk; }
+                }
                 st.m1 = cmax;
-                st.thr = cmax - margin;
-                if (mb > ma) { st.best_chunk = chunk + 1; record_store(slots, rec, vb); }
-                else         { st.best_chunk = chunk;     record_store(slots, rec, va); }
-            } else {                      // granule(s) within the margin of the record
-                st.m2 = fmaxf(st.m2, cmax);
+                st.thr = nthr;
+                if (b_wins) { st.best_chunk = chunk + 1; record_store(slots, rec, vb); }
+                else        { st.best_chunk = chunk;     record_store(slots, rec, va); }
+            } else {                      // rare: granule(s) within the margin of the record
+                if (cmax > st.m2) { st.m3 = fmaxf(fmaxf(st.m3, st.m2), lo); st.m2 = cmax; st.chunk2 = b_wins ? chunk + 1 : chunk; }
+                else              { st.m3 = fmaxf(st.m3, cmax); }
             }
         }
     }
+}
+
+// scan one fp16 record for columns >= ts; optionally write them to dst[n...] (capacity cap)
+__device__ __forceinline__ int scan_record(const unsigned char* slots, int rec, float ts, int col0, int* last_col,
+                                           int* dst, int n0, int cap) {
+    int n = 0;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        const uint4 q = *reinterpret_cast<const uint4*>(slots + (cc * kRecords + rec) * 16);
+        const uint32_t wds[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&wds[t]));
+            if (f.x >= ts) { const int col = col0 + cc * 8 + 2 * t;     *last_col = col; if (dst && n0 + n < cap) dst[n0 + n] = col; ++n; }
+            if (f.y >= ts) { const int col = col0 + cc * 8 + 2 * t + 1; *last_col = col; if (dst && n0 + n < cap) dst[n0 + n] = col; ++n; }
+        }
+    }
+    return n;
 }
 
 }  // namespace
@@ -250,15 +268,16 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
     // Work items.  ARGMAX / THRESH / DUMP reduce over a row's whole codebook, so an item is a row block.  COLLECT
     // compares every column with a per-row threshold known up front, so columns are independent too: when the
     // (device-side) row count leaves SMs idle -- the near-tie rows of the hard path are a few percent of N -- the
-    // codebook is split into `ksplit` chunk ranges and an item is (row block, chunk range).  ksplit minimises
-    // rounds x chunks-per-item, with >= kMinSplitChunks chunks per item so the A-tile load stays amortised.
+    // codebook is split into `ksplit` chunk ranges and an item is (row block, chunk range).
     int ksplit = 1;
     if (MODE == MODE_COLLECT) {
-        int best_cost = ((nblocks + (int)gridDim.x - 1) / (int)gridDim.x) * nchunks;
-        for (int ks = 2; ks * kMinSplitChunks <= nchunks && ks <= 16; ++ks) {
+        // cost of a CTA's share in chunk-times: rounds x (chunks per item + the A-tile load of an item)
+        const int grid = (int)gridDim.x;
+        int best_cost = ((nblocks + grid - 1) / grid) * (nchunks + kItemLoadCost);
+        for (int ks = 2; ks * kMinSplitChunks <= nchunks && ks <= 64; ++ks) {
             const int cps_ = (nchunks + ks - 1) / ks;
             if ((ks - 1) * cps_ >= nchunks) continue;            // would leave an empty range
-            const int cost = ((nblocks * ks + (int)gridDim.x - 1) / (int)gridDim.x) * cps_;
+            const int cost = ((nblocks * ks + grid - 1) / grid) * (cps_ + kItemLoadCost);
             if (cost < best_cost) { best_cost = cost; ksplit = ks; }
         }
     }
@@ -340,6 +359,8 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
         uint32_t empty_addr[2] = {smem_u32(&bars.acc_empty[pair]), smem_u32(&bars.acc_empty[pair + 2])};
         uint32_t tld[2] = {t_lane + (uint32_t)(pair * kTileCodes), t_lane + (uint32_t)((pair + 2) * kTileCodes)};
         uint32_t is_lane0 = (lane == 0) ? 1u : 0u;
+        int half2 = 2 * half;                       // first granule of the thread's column half within a chunk
+        asm volatile("" : "+r"(half2));
         // make the values opaque so ptxas keeps them in registers instead of re-deriving them from the thread id
         asm volatile("" : "+r"(full_addr[0]), "+r"(full_addr[1]), "+r"(empty_addr[0]), "+r"(empty_addr[1]),
                           "+r"(tld[0]), "+r"(tld[1]), "+r"(is_lane0));
@@ -349,14 +370,20 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
             const int cbeg = (MODE == MODE_COLLECT) ? (item - blk * ksplit) * cps : 0;
             const int cend = min(nchunks, cbeg + cps);
             RowState<NTOP> st[NS];
-#pragma unroll
-            for (int ss = 0; ss < NS; ++ss) {
+            // which row a state set belongs to: needed inside the chunk loop only by COLLECT / DUMP; ARGMAX / THRESH
+            // work it out after the loop so that it does not hold registers through it
+            auto locate = [&](int ss) {
                 const int g = (RT == 4) ? pair + 2 * ss : (RT == 2 ? pair : 0);
                 st[ss].pos = (int64_t)blk * rows_blk + g * kTileRows + rq;
                 st[ss].valid = st[ss].pos < nrows;
                 st[ss].row = st[ss].valid ? (p.row_list ? (int64_t)p.row_list[st[ss].pos] : st[ss].pos) : 0;
-                st[ss].m1 = st[ss].m2 = st[ss].thr = -INFINITY;
-                st[ss].best_chunk = 0;
+            };
+            constexpr bool kLocateEarly = (MODE == MODE_COLLECT || MODE == MODE_DUMP);
+#pragma unroll
+            for (int ss = 0; ss < NS; ++ss) {
+                if (kLocateEarly) locate(ss);
+                st[ss].m1 = st[ss].m2 = st[ss].m3 = st[ss].thr = -INFINITY;
+                st[ss].best_chunk = st[ss].chunk2 = 0;
 #pragma unroll
                 for (int i = 0; i < NTOP; ++i) st[ss].top[i] = -INFINITY;
                 st[ss].T = INFINITY;
@@ -376,9 +403,7 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                     tc_fence_after();
                     float va[32], vb[32];
                     if (!(DBG && (p.debug_flags & 1))) {
-                        tmem_ld32(tld[si], va);
-                        tmem_ld32(tld[si] + kChunk, vb);
-                        tmem_ld_wait();
+                        tmem_ld32x2_wait(tld[si], va, vb);
                     }
                     // both granules are in registers: hand the accumulator back before reducing them
                     tc_fence_before();
@@ -387,15 +412,19 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                     if (DBG && tracing && si == 0 && uses[0] <= 512) p.trace[(uses[0] - 1) * 8 + 3] = clock64();
                     if (DBG && (p.debug_flags & 1)) continue;    // timing experiment: no epilogue work
                     if (MODE == MODE_ARGMAX) {
-                        consume_argmax64<NTOP>(va, vb, c * 4 + 2 * half, st[ss], margin, slots, ss * 512 + rec0);
+                        consume_argmax64<NTOP>(va, vb, c * 4 + half2, st[ss], margin, slots, ss * 512 + rec0);
                     } else {
-                        consume<MODE, NTOP>(va, c * 4 + 2 * half, st[ss], margin, p, slots, ss * 512 + rec0);
-                        consume<MODE, NTOP>(vb, c * 4 + 2 * half + 1, st[ss], margin, p, slots, ss * 512 + rec0);
+                        consume<MODE, NTOP>(va, c * 4 + half2, st[ss], margin, p, slots, ss * 512 + rec0);
+                        consume<MODE, NTOP>(vb, c * 4 + half2 + 1, st[ss], margin, p, slots, ss * 512 + rec0);
                     }
                     if (DBG && tracing && si == 0 && uses[0] <= 512) p.trace[(uses[0] - 1) * 8 + 4] = clock64();
                 }
             }
 
+            if (!kLocateEarly) {
+#pragma unroll
+                for (int ss = 0; ss < NS; ++ss) locate(ss);
+            }
             // ---- end of row block: merge the threads that shared each row, emit ----------------------
             // a row's columns were split over 2 threads (column halves); with RT == 1 also over the 2 pairs
             constexpr int NP = (RT == 1) ? 2 : 1;
@@ -405,12 +434,13 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
             if (MODE == MODE_ARGMAX) {
 #pragma unroll
                 for (int ss = 0; ss < NS; ++ss)
-                    state[ss * 512 + rec0] = make_float4(st[ss].m1, st[ss].m2, __int_as_float(st[ss].best_chunk), 0.f);
+                    state[ss * 512 + rec0] = make_float4(st[ss].m1, st[ss].m2,
+                                                         __int_as_float(st[ss].best_chunk | (st[ss].chunk2 << 16)), st[ss].m3);
                 named_bar_sync(bar_id, bar_n);
                 if (leader) {
 #pragma unroll
                     for (int ss = 0; ss < NS; ++ss) {
-                        float M = -INFINITY, m2all = -INFINITY;
+                        float M = -INFINITY, m3all = -INFINITY;
 #pragma unroll
                         for (int pp = 0; pp < NP; ++pp)
 #pragma unroll
@@ -418,12 +448,12 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                                 const int w2 = quarter + 4 * hh + 8 * ((RT == 1) ? pp : pair);
                                 const float4 sv = state[ss * 512 + w2 * 32 + lane];
                                 M = fmaxf(M, sv.x);
-                                m2all = fmaxf(m2all, sv.y);
+                                m3all = fmaxf(m3all, sv.w);
                             }
                         const float thrF = M - margin;
                         // records are fp16: accept anything that could be >= thrF before rounding
                         const float thrS = thrF - (fmaxf(fabsf(M), fabsf(thrF)) * 4.8829e-4f + 1e-7f);
-                        int cnt = 0, col = -1;
+                        int cnt = 0, col = -1, nsec = 0;
 #pragma unroll
                         for (int pp = 0; pp < NP; ++pp)
 #pragma unroll
@@ -431,23 +461,32 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                                 const int w2 = quarter + 4 * hh + 8 * ((RT == 1) ? pp : pair);
                                 const int rec = ss * 512 + w2 * 32 + lane;
                                 const float4 sv = state[rec];
-                                if (sv.x >= thrF) {
-                                    const int cj = __float_as_int(sv.z);
-#pragma unroll
-                                    for (int cc = 0; cc < 4; ++cc) {
-                                        const uint4 q = *reinterpret_cast<const uint4*>(slots + (cc * kRecords + rec) * 16);
-                                        const uint32_t wds[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                                        for (int t = 0; t < 4; ++t) {
-                                            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&wds[t]));
-                                            if (f.x >= thrS) { ++cnt; col = cj * kChunk + cc * 8 + 2 * t; }
-                                            if (f.y >= thrS) { ++cnt; col = cj * kChunk + cc * 8 + 2 * t + 1; }
-                                        }
-                                    }
-                                }
+                                if (sv.x >= thrF) cnt += scan_record(slots, rec, thrS, (__float_as_int(sv.z) & 0xffff) * kChunk, &col, nullptr, 0, 0);
+                                if (sv.y >= thrF) ++nsec;
                             }
-                        const bool flagged = st[ss].valid && ((cnt != 1) || (m2all >= thrF) || (col >= p.k));
-                        if (st[ss].valid) p.best_val[st[ss].row] = M;
+                        // near-tie row: more than one column (or an unrecorded granule) within the margin of the best
+                        // score.  Its candidates -- recorded columns one by one, second-best granules wholesale as
+                        // -(granule + 1) -- go to the row's list for the exact fp32 re-scoring; if a granule known only
+                        // through m3 is within the margin too (or the list would overflow) a COLLECT pass finds them.
+                        const bool flagged = st[ss].valid && ((cnt != 1) || (nsec > 0) || (m3all >= thrF) || (col >= p.k));
+                        const bool over = flagged && ((m3all >= thrF) || (cnt + nsec > p.cand_cap) || !(M == M));
+                        if (flagged && !over) {
+                            int* dst = p.cand + st[ss].row * p.cand_cap;
+                            int nw = 0;
+#pragma unroll
+                            for (int pp = 0; pp < NP; ++pp)
+#pragma unroll
+                                for (int hh = 0; hh < 2; ++hh) {
+                                    const int w2 = quarter + 4 * hh + 8 * ((RT == 1) ? pp : pair);
+                                    const int rec = ss * 512 + w2 * 32 + lane;
+                                    const float4 sv = state[rec];
+                                    int dummy;
+                                    if (sv.x >= thrF) nw += scan_record(slots, rec, thrS, (__float_as_int(sv.z) & 0xffff) * kChunk, &dummy, dst, nw, p.cand_cap);
+                                    if (sv.y >= thrF) { dst[nw] = -((__float_as_int(sv.z) >> 16) + 1); ++nw; }
+                                }
+                            p.cand_cnt[st[ss].row] = nw;
+                        }
+                        if (over) p.best_val[st[ss].row] = M;      // COLLECT threshold; the row's list stays empty until then
                         // decided rows leave the kernel as final int64 indices + histogram counts (one RED per
                         // distinct code in the warp), spread over the whole tensor pass instead of a row kernel
                         const bool decided = st[ss].valid && !flagged;
@@ -463,6 +502,13 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                             if (lane == 0) base = atomicAdd(&p.counters[CNT_FLAGGED], __popc(ball));
                             base = __shfl_sync(0xffffffffu, base, 0);
                             if (flagged) p.flag_rows[base + __popc(ball & ((1u << lane) - 1))] = (int)st[ss].row;
+                        }
+                        const unsigned oall = __ballot_sync(0xffffffffu, over);
+                        if (oall) {
+                            int base = 0;
+                            if (lane == 0) base = atomicAdd(&p.counters[CNT_OVER], __popc(oall));
+                            base = __shfl_sync(0xffffffffu, base, 0);
+                            if (over) p.over_rows[base + __popc(oall & ((1u << lane) - 1))] = (int)st[ss].row;
                         }
                     }
                 }

@@ -28,7 +28,8 @@ struct CoarseParams {
                              //      are written by the resolve kernels
     int*         bins;       // [k]  ARGMAX: per-code row counts of the decided rows (zeroed by the caller)
     float*       best_val;   // [n]
-    int*         flag_rows;  // [n]
+    int*         flag_rows;  // [n]   ARGMAX: near-tie rows (exact re-scoring decides)
+    int*         over_rows;  // [n]   ARGMAX: the near-tie rows that also need a COLLECT pass (counters[CNT_OVER])
     int*         counters;   // [CNT_COUNT]
     int*         cand;       // [rows * cand_cap]   indexed by position in row_list
     int*         cand_cnt;   // [rows]

@@ -98,28 +98,57 @@ __global__ void __launch_bounds__(256) gather_ste_kernel(const float* __restrict
 __global__ void __launch_bounds__(1024) scan_bins_kernel(const int* __restrict__ bins, int k, int64_t n, int d,
                                                           int* __restrict__ offsets, int* __restrict__ cursor,
                                                           double* __restrict__ stats) {
-    __shared__ int part[1024];
+    // exclusive scan of the k counts by one CTA: contiguous slice per thread -> warp shuffles -> 32 warp totals
+    __shared__ int warp_tot[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int per = (k + 1023) / 1024;
     const int lo = threadIdx.x * per, hi = min(k, lo + per);
     int s = 0;
-    for (int i = lo; i < hi; ++i) s += bins[i];
-    part[threadIdx.x] = s;
+    for (int i0 = lo; i0 < hi; i0 += 8) {         // 8 independent loads in flight
+        int v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (i0 + u < hi) ? bins[i0 + u] : 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    int incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
     __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {   // Hillis-Steele inclusive scan
-        int v = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
-        __syncthreads();
-        part[threadIdx.x] += v;
-        __syncthreads();
+    if (wid == 0) {
+        int t = warp_tot[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, t, o);
+            if (lane >= o) t += v;
+        }
+        warp_tot[lane] = t;                       // inclusive totals of warps 0..lane
     }
-    int run = part[threadIdx.x] - s;
-    for (int i = lo; i < hi; ++i) {
-        const int b = bins[i];
-        offsets[i] = run;
-        cursor[i] = run;
-        stats[i] += (double)b;                    // packed statistics: bins as doubles (exact)
-        run += b;
+    __syncthreads();
+    int run = incl - s + (wid > 0 ? warp_tot[wid - 1] : 0);
+    for (int i0 = lo; i0 < hi; i0 += 8) {
+        int v[8];
+        double acc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            v[u] = (i0 + u < hi) ? bins[i0 + u] : 0;   // L1 hits
+            acc[u] = (i0 + u < hi) ? stats[i0 + u] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (i0 + u < hi) {
+                offsets[i0 + u] = run;
+                cursor[i0 + u] = run;
+                stats[i0 + u] = acc[u] + (double)v[u];   // packed statistics accumulate: bins as doubles (exact)
+                run += v[u];
+            }
+        }
     }
-    if (threadIdx.x == 1023) offsets[k] = part[1023];
+    if (threadIdx.x == 1023) offsets[k] = warp_tot[31];
     if (threadIdx.x == 0) stats[(size_t)k + (size_t)k * d + 1] += (double)n;
 }
 
@@ -203,40 +232,146 @@ __global__ void __launch_bounds__(256) segsum_kernel(const float* __restrict__ z
 }
 
 // ------------------------------------------------------------------------------------------------
+// training forward, fused: ONE pass over the rows in code-sorted order does gather + straight-through + SSE
+// (:181,212-214) AND the per-code sums (:202), so z is read once instead of twice.  Same work split as
+// segsum_kernel; a row's d/4 threads write the 4*d-byte z_q row as whole 128-byte lines.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sorted_rows_kernel(const float* __restrict__ z, const float* __restrict__ denom,
+                                                           const float* __restrict__ w, const int64_t* __restrict__ idx,
+                                                           const int* __restrict__ perm, int64_t n, int d, int k,
+                                                           float* __restrict__ z_q, double* __restrict__ stats) {
+    const int vpr = d >> 2;
+    const int lane = threadIdx.x & 31;
+    double* embed_sum = stats + k;
+    const int64_t nranges = (n + kSegRows - 1) / kSegRows;
+    const int64_t items = nranges * vpr;
+    double sse = 0.0;
+    for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t range = it / vpr;
+        const int c4 = (int)(it - range * vpr);
+        const int64_t p0 = range * kSegRows;
+        const int cnt = (int)min((int64_t)kSegRows, n - p0);
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int cur = -1;
+        auto flush = [&]() {
+            if (cur >= 0) {
+                double* dst = embed_sum + (size_t)cur * d + 4 * c4;
+                atomicAdd(dst + 0, a0); atomicAdd(dst + 1, a1); atomicAdd(dst + 2, a2); atomicAdd(dst + 3, a3);
+            }
+            a0 = a1 = a2 = a3 = 0.0;
+        };
+        for (int j0 = 0; j0 < cnt; j0 += 4) {
+            int rows[4], codes[4];
+            float dens[4];
+            float4 x[4], c[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) rows[u] = (j0 + u < cnt) ? perm[p0 + j0 + u] : 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool ok = j0 + u < cnt;
+                codes[u] = ok ? (int)__ldg(idx + rows[u]) : 0;
+                dens[u] = ok ? __ldg(denom + rows[u]) : 1.0f;
+                x[u] = ok ? __ldcs(reinterpret_cast<const float4*>(z + (size_t)rows[u] * d) + c4) : make_float4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) c[u] = __ldg(reinterpret_cast<const float4*>(w + (size_t)codes[u] * d) + c4);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (j0 + u < cnt) {
+                    if (codes[u] != cur) { flush(); cur = codes[u]; }
+                    const float zf0 = __fdiv_rn(x[u].x, dens[u]), zf1 = __fdiv_rn(x[u].y, dens[u]),
+                                zf2 = __fdiv_rn(x[u].z, dens[u]), zf3 = __fdiv_rn(x[u].w, dens[u]);
+                    a0 += (double)zf0; a1 += (double)zf1; a2 += (double)zf2; a3 += (double)zf3;
+                    const float d0 = __fsub_rn(c[u].x, zf0), d1 = __fsub_rn(c[u].y, zf1), d2 = __fsub_rn(c[u].z, zf2),
+                                d3 = __fsub_rn(c[u].w, zf3);
+                    sse += (double)__fmul_rn(d0, d0) + (double)__fmul_rn(d1, d1) + (double)__fmul_rn(d2, d2) +
+                           (double)__fmul_rn(d3, d3);
+                    float4 o;
+                    o.x = __fadd_rn(zf0, d0); o.y = __fadd_rn(zf1, d1); o.z = __fadd_rn(zf2, d2); o.w = __fadd_rn(zf3, d3);
+                    __stcs(reinterpret_cast<float4*>(z_q + (size_t)rows[u] * d) + c4, o);
+                }
+            }
+        }
+        flush();
+    }
+    sse = warp_sum(sse);
+    __shared__ double part[8];
+    if (lane == 0) part[threadIdx.x >> 5] = sse;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += part[i];
+        atomicAdd(&stats[(size_t)k + (size_t)k * d], t);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // EMA: one thread per code, every reduction in the reference's order (oracle: vqo_ema_*)
 // ------------------------------------------------------------------------------------------------
-__global__ void ema_finalize_kernel(float* __restrict__ weight, float* __restrict__ cluster_size,
-                                    const double* __restrict__ stats, int k, int d, float beta, float decay,
-                                    float alpha, int update_cs, int update_w, float* __restrict__ loss) {
-    const int code = blockIdx.x * blockDim.x + threadIdx.x;
-    if (code == 0 && loss) {
+constexpr int kEmaCodes = 32;   // codes per CTA
+
+__global__ void __launch_bounds__(128) ema_finalize_kernel(float* __restrict__ weight, float* __restrict__ cluster_size,
+                                                            const double* __restrict__ stats, int k, int d, float beta,
+                                                            float decay, float alpha, int update_cs, int update_w,
+                                                            float* __restrict__ loss) {
+    // tile[c][i] (row stride d + 1: conflict-free when 32 threads walk 32 different rows) holds, per code,
+    // first the per-code mean e = fl(fl32(sum) / bins) (or the old row of a dead code), then the updated row
+    extern __shared__ float tile[];
+    float* wold = tile + kEmaCodes * (d + 1);
+    const int code0 = blockIdx.x * kEmaCodes;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && loss) {
         const double sse = stats[(size_t)k + (size_t)k * d], rows = stats[(size_t)k + (size_t)k * d + 1];
         const float mse = (float)(sse / (rows * (double)d));
         *loss = __fmul_rn(beta, mse);
     }
-    if (code >= k) return;
-    const double bins = stats[code];
     if (update_cs) {   // ema_inplace: fl(cs*decay) then fma(new, alpha, .)
-        const float t = __fmul_rn(cluster_size[code], decay);
-        cluster_size[code] = __fmaf_rn((float)bins, alpha, t);
+        const int code = code0 + threadIdx.x;
+        if (threadIdx.x < kEmaCodes && code < k) {
+            const float t = __fmul_rn(cluster_size[code], decay);
+            cluster_size[code] = __fmaf_rn((float)stats[code], alpha, t);
+        }
     }
     if (!update_w) return;
-    float* wr = weight + (size_t)code * d;
-    const double* sr = stats + k + (size_t)code * d;
-    float e[kMaxDim];
-    if (bins == 0.0) {   // dead code keeps its row (still re-normalised below, like the reference)
-        for (int c = 0; c < d; ++c) e[c] = wr[c];
-    } else {
-        const float b = (float)bins;
-        for (int c = 0; c < d; ++c) e[c] = __fdiv_rn((float)sr[c], b);
-        float den = canon_norm_seq([&](int i) { return e[i]; }, d);   // strided (.t()) view in the reference
-        den = den < kNormEps ? kNormEps : den;
-        for (int c = 0; c < d; ++c) e[c] = __fdiv_rn(e[c], den);
+    // elementwise steps run on all threads (coalesced); only the two norms, whose summation order is part of
+    // the contract (oracle: vqo_ema_*), run one thread per code
+    __shared__ float den_s[kEmaCodes];
+    const int ncodes = min(kEmaCodes, k - code0);
+    for (int e = threadIdx.x; e < ncodes * d; e += blockDim.x) {
+        const int c = e / d, i = e - c * d;
+        const float wv = weight[(size_t)(code0 + c) * d + i];
+        const double bins = stats[code0 + c];
+        wold[c * (d + 1) + i] = wv;
+        // per-code mean; a dead code keeps its row (still re-normalised below, like the reference)
+        tile[c * (d + 1) + i] = (bins == 0.0) ? wv : __fdiv_rn((float)stats[(size_t)k + (size_t)(code0 + c) * d + i], (float)bins);
     }
-    for (int c = 0; c < d; ++c) e[c] = __fmaf_rn(e[c], alpha, __fmul_rn(wr[c], decay));
-    float den = canon_norm8([&](int i) { return e[i]; }, d);
-    den = den < kNormEps ? kNormEps : den;
-    for (int c = 0; c < d; ++c) wr[c] = __fdiv_rn(e[c], den);
+    __syncthreads();
+    if (threadIdx.x < ncodes) {
+        float den = 1.0f;
+        if (stats[code0 + threadIdx.x] != 0.0) {
+            const float* e = tile + threadIdx.x * (d + 1);
+            den = canon_norm_seq([&](int i) { return e[i]; }, d);   // strided (.t()) view in the reference
+            den = den < kNormEps ? kNormEps : den;
+        }
+        den_s[threadIdx.x] = den;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < ncodes * d; e += blockDim.x) {
+        const int c = e / d, i = e - c * d;
+        float v = tile[c * (d + 1) + i];
+        if (stats[code0 + c] != 0.0) v = __fdiv_rn(v, den_s[c]);
+        tile[c * (d + 1) + i] = __fmaf_rn(v, alpha, __fmul_rn(wold[c * (d + 1) + i], decay));
+    }
+    __syncthreads();
+    if (threadIdx.x < ncodes) {
+        const float* e = tile + threadIdx.x * (d + 1);
+        float den = canon_norm8([&](int i) { return e[i]; }, d);
+        den_s[threadIdx.x] = den < kNormEps ? kNormEps : den;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < ncodes * d; e += blockDim.x) {
+        const int c = e / d, i = e - c * d;
+        weight[(size_t)(code0 + c) * d + i] = __fdiv_rn(tile[c * (d + 1) + i], den_s[c]);
+    }
 }
 
 __global__ void loss_kernel(const double* __restrict__ stats, int k, int d, float beta, float* __restrict__ loss) {
@@ -279,11 +414,29 @@ cudaError_t launch_code_sums(const float* z, const float* denom, const int64_t* 
     return cudaGetLastError();
 }
 
+// training forward: counting sort by code, then the fused sorted-order pass (z_q, SSE, per-code sums)
+cudaError_t launch_sorted_rows(const float* z, const float* denom, const float* w, const int64_t* idx, int64_t n, int d,
+                               int k, float* z_q, double* stats, const Workspace& ws, int num_sms, cudaStream_t s) {
+    scan_bins_kernel<<<1, 1024, 0, s>>>(ws.bins_i32, k, n, d, ws.offsets, ws.cursor, stats);
+    scatter_rows_kernel<<<grid_for(n, 256, num_sms, 8), 256, 0, s>>>(idx, n, ws.cursor, ws.perm);
+    const int64_t items = ((n + kSegRows - 1) / kSegRows) * (d / 4);
+    sorted_rows_kernel<<<grid_for(items, 256, num_sms, 32), 256, 0, s>>>(z, denom, w, idx, ws.perm, n, d, k, z_q, stats);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_ema_finalize(float* weight, float* cluster_size, const double* stats, int k, int d, double beta,
                                 double decay, int update_cs, int update_w, float* loss, cudaStream_t s) {
     // python: mul_(decay).add_(new, alpha=1-decay): both scalars are doubles cast to fp32
-    ema_finalize_kernel<<<(k + 31) / 32, 32, 0, s>>>(weight, cluster_size, stats, k, d, (float)beta, (float)decay,
-                                                        (float)(1.0 - decay), update_cs, update_w, loss);
+    const size_t smem = sizeof(float) * 2 * kEmaCodes * (d + 1);   // <= 65.8 KB at d = 256
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(ema_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    ema_finalize_kernel<<<(k + kEmaCodes - 1) / kEmaCodes, 128, smem, s>>>(weight, cluster_size, stats, k, d, (float)beta,
+                                                                            (float)decay, (float)(1.0 - decay), update_cs,
+                                                                            update_w, loss);
     return cudaGetLastError();
 }
 

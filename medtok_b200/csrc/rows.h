@@ -12,6 +12,8 @@ cudaError_t launch_gather_ste(const float* z, const float* denom, const float* w
                               int k, float* z_q, double* stats, int num_sms, cudaStream_t s);
 cudaError_t launch_code_sums(const float* z, const float* denom, const int64_t* idx, int64_t n, int d, int k,
                              double* stats, const Workspace& ws, bool want_sums, int num_sms, cudaStream_t s);
+cudaError_t launch_sorted_rows(const float* z, const float* denom, const float* w, const int64_t* idx, int64_t n, int d,
+                               int k, float* z_q, double* stats, const Workspace& ws, int num_sms, cudaStream_t s);
 cudaError_t launch_ema_finalize(float* weight, float* cluster_size, const double* stats, int k, int d, double beta,
                                 double decay, int update_cs, int update_w, float* loss, cudaStream_t s);
 cudaError_t launch_loss(const double* stats, int k, int d, double beta, float* loss, cudaStream_t s);

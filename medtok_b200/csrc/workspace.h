@@ -12,7 +12,7 @@ enum MetaSlot { META_MARGIN = 0, META_EPS = 1, META_MAXNORM = 2, META_SPREAD = 3
 // the -||w||^2/2 K-step is skipped when max_k | ||w_k||^2 - ||w_0||^2 | / 2 <= kBiasSkipTol (eps carries the slack)
 constexpr float kBiasSkipTol = 1.0e-6f;
 // counters (ints), zeroed at the start of every assign
-enum Counter { CNT_FLAGGED = 0, CNT_FULL = 1, CNT_CANDS = 2, CNT_LAUNCHES = 3, CNT_COUNT = 8 };
+enum Counter { CNT_FLAGGED = 0, CNT_FULL = 1, CNT_CANDS = 2, CNT_LAUNCHES = 3, CNT_OVER = 4, CNT_COUNT = 8 };
 
 struct Workspace {
     // codebook side

@@ -221,3 +221,35 @@ if what == "e2e":
     out["e2e"] = res
     print("E2E", json.dumps(res))
     json.dump(out, open("gpurun_out/probe_e2e.json", "w"), indent=1)
+
+if what == "kernels":
+    # per-kernel device times of the hard training forward at C2, kernels running back to back (CUPTI via
+    # torch.profiler; unlike an ncu launch list the clocks stay up between the small kernels)
+    from torch.profiler import profile, ProfilerActivity
+    from medtok_b200.norm_ema_quantizer import NormEMAVectorQuantizer
+    n, d, k = int(os.environ.get("PROBE_N", str(1 << 20))), int(os.environ.get("PROBE_D", "64")), int(os.environ.get("PROBE_K", "8192"))
+    torch.manual_seed(0)
+    zs = [torch.randn(n, d, 1, 1, device=dev) for _ in range(2)]
+    q = NormEMAVectorQuantizer(k, d, 0.25).to(dev).train()
+    with torch.no_grad():
+        for i in range(3):
+            q(zs[i % 2])
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for i in range(10):
+                q(zs[i % 2])
+            torch.cuda.synchronize()
+    rows = []
+    for e in prof.key_averages():
+        t = getattr(e, "device_time_total", None)
+        if t is None:
+            t = e.cuda_time_total
+        if t > 0:
+            rows.append((e.key[:70], t / 10.0, e.count / 10.0))
+    rows.sort(key=lambda r: -r[1])
+    tot = sum(r[1] for r in rows)
+    for name, us, cnt in rows:
+        print(f"{name:70s} {us:9.1f} us/step  x{cnt:.1f}")
+    print(f"{'total device time':70s} {tot:9.1f} us/step")
+    out["kernels"] = [{"name": r[0], "us_per_step": r[1], "launches_per_step": r[2]} for r in rows]
+    json.dump(out, open("gpurun_out/probe_kernels.json", "w"), indent=1)
