@@ -16,10 +16,11 @@
 
 using namespace mtvq;
 
+namespace mtvq { thread_local long g_kernel_launches = 0; }
+
 namespace {
 
 thread_local char g_err[512] = "";
-thread_local long g_launches = 0;       // kernels enqueued by this thread (memsets not counted)
 thread_local long long* g_trace = nullptr;
 thread_local cudaEvent_t g_ev_before = nullptr, g_ev_after = nullptr;
 
@@ -34,7 +35,6 @@ int cuda_fail(cudaError_t e, const char* where) {
 #define MTVQ_CUDA(call, where)                                 \
     do {                                                       \
         cudaError_t e__ = (call);                              \
-        if (strncmp(where, "memset", 6) != 0) ++g_launches;    \
         if (e__ != cudaSuccess) return cuda_fail(e__, where);  \
     } while (0)
 
@@ -302,8 +302,8 @@ int mtvq_debug_counters(const void* workspace, int64_t n, int d, int k, int topk
     out_host[0] = h[CNT_FLAGGED];
     out_host[1] = h[CNT_FULL];
     out_host[2] = h[CNT_CANDS];
-    out_host[3] = g_launches;
-    g_launches = 0;
+    out_host[3] = g_kernel_launches;
+    g_kernel_launches = 0;
     return 0;
 }
 

@@ -390,6 +390,7 @@ cudaError_t launch_codebook_prep(const float* w, int k, int d, int normalize, co
     codebook_prep_kernel<<<(kpad + 31) / 32, 32, 0, stream>>>(w, k, kpad, d, normalize,
                                                                   static_cast<unsigned char*>(ws.b_image), ws.cc,
                                                                   ws.codes_n, ws.meta);
+    ++g_kernel_launches;
     return cudaGetLastError();
 }
 
@@ -398,6 +399,7 @@ cudaError_t launch_resolve(const float* z, int d, int norm_mode, const float* w,
     resolve_kernel<<<num_sms * 4, kResWarps * 32, 0, stream>>>(z, d, norm_mode, w, k, ws.cc, ws.flag_rows, ws.cand,
                                                                 ws.cand_cnt, cand_cap, idx, ws.bins_i32, ws.full_rows,
                                                                 ws.counters);
+    ++g_kernel_launches;
     return cudaGetLastError();
 }
 
@@ -416,6 +418,7 @@ cudaError_t launch_exact_scan(const float* z, int64_t n, int d, int norm_mode, c
     if (blocks < 1) blocks = 1;
     exact_scan_kernel<<<(int)blocks, 256, smem, stream>>>(z, n, d, norm_mode, w, k, cc, row_list, n_rows_dev, idx, bins,
                                                           denom_out);
+    ++g_kernel_launches;
     return cudaGetLastError();
 }
 

@@ -751,6 +751,7 @@ static cudaError_t launch_one(const CoarseParams& p, int grid, cudaStream_t stre
         configured = true;
     }
     kern<<<grid, kThreads, kSmemBytes, stream>>>(p);
+    ++g_kernel_launches;
     return cudaGetLastError();
 }
 

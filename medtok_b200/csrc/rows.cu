@@ -98,6 +98,8 @@ __global__ void __launch_bounds__(256) gather_ste_kernel(const float* __restrict
 __global__ void __launch_bounds__(1024) scan_bins_kernel(const int* __restrict__ bins, int k, int64_t n, int d,
                                                           int* __restrict__ offsets, int* __restrict__ cursor,
                                                           double* __restrict__ stats) {
+    // `stats` may be null: the fused sorted-rows pass then adds the counts to the packed statistics itself, and this
+    // single-CTA kernel touches one page of small arrays only (its run time is address-translation latency)
     // exclusive scan of the k counts by one CTA: contiguous slice per thread -> warp shuffles -> 32 warp totals
     __shared__ int warp_tot[32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -136,20 +138,20 @@ __global__ void __launch_bounds__(1024) scan_bins_kernel(const int* __restrict__
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             v[u] = (i0 + u < hi) ? bins[i0 + u] : 0;   // L1 hits
-            acc[u] = (i0 + u < hi) ? stats[i0 + u] : 0.0;
+            acc[u] = (stats != nullptr && i0 + u < hi) ? stats[i0 + u] : 0.0;
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             if (i0 + u < hi) {
                 offsets[i0 + u] = run;
                 cursor[i0 + u] = run;
-                stats[i0 + u] = acc[u] + (double)v[u];   // packed statistics accumulate: bins as doubles (exact)
+                if (stats != nullptr) stats[i0 + u] = acc[u] + (double)v[u];   // packed statistics accumulate: bins as doubles (exact)
                 run += v[u];
             }
         }
     }
     if (threadIdx.x == 1023) offsets[k] = warp_tot[31];
-    if (threadIdx.x == 0) stats[(size_t)k + (size_t)k * d + 1] += (double)n;
+    if (threadIdx.x == 0 && stats != nullptr) stats[(size_t)k + (size_t)k * d + 1] += (double)n;
 }
 
 __global__ void scatter_rows_kernel(const int64_t* __restrict__ idx, int64_t n, int* __restrict__ cursor,
@@ -238,11 +240,16 @@ __global__ void __launch_bounds__(256) segsum_kernel(const float* __restrict__ z
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sorted_rows_kernel(const float* __restrict__ z, const float* __restrict__ denom,
                                                            const float* __restrict__ w, const int64_t* __restrict__ idx,
-                                                           const int* __restrict__ perm, int64_t n, int d, int k,
+                                                           const int* __restrict__ perm, const int* __restrict__ bins,
+                                                           int64_t n, int d, int k,
                                                            float* __restrict__ z_q, double* __restrict__ stats) {
     const int vpr = d >> 2;
     const int lane = threadIdx.x & 31;
     double* embed_sum = stats + k;
+    // packed statistics: per-code counts as doubles (exact) and the row count, accumulated like the sums
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < k; c += (int64_t)gridDim.x * blockDim.x)
+        stats[c] += (double)bins[c];
+    if (blockIdx.x == 0 && threadIdx.x == 0) stats[(size_t)k + (size_t)k * d + 1] += (double)n;
     const int64_t nranges = (n + kSegRows - 1) / kSegRows;
     const int64_t items = nranges * vpr;
     double sse = 0.0;
@@ -336,6 +343,7 @@ __global__ void __launch_bounds__(128) ema_finalize_kernel(float* __restrict__ w
     // the contract (oracle: vqo_ema_*), run one thread per code
     __shared__ float den_s[kEmaCodes];
     const int ncodes = min(kEmaCodes, k - code0);
+#pragma unroll 4
     for (int e = threadIdx.x; e < ncodes * d; e += blockDim.x) {
         const int c = e / d, i = e - c * d;
         const float wv = weight[(size_t)(code0 + c) * d + i];
@@ -393,12 +401,14 @@ cudaError_t launch_hist_idx64(const int64_t* idx, int64_t n, int* bins_i32, int 
     cudaError_t e = cudaMemsetAsync(bins_i32, 0, sizeof(int) * k, s);
     if (e != cudaSuccess) return e;
     hist_kernel<<<grid_for(n, 256, num_sms, 8), 256, 0, s>>>(idx, n, bins_i32);
+    ++g_kernel_launches;
     return cudaGetLastError();
 }
 
 cudaError_t launch_gather_ste(const float* z, const float* denom, const float* w, const int64_t* idx, int64_t n, int d,
                               int k, float* z_q, double* stats, int num_sms, cudaStream_t s) {
     gather_ste_kernel<<<grid_for(n * (d / 4), 256 * 4, num_sms, 6), 256, 0, s>>>(z, denom, w, idx, n, d, k, z_q, stats);
+    ++g_kernel_launches;
     return cudaGetLastError();
 }
 
@@ -407,20 +417,27 @@ cudaError_t launch_gather_ste(const float* z, const float* denom, const float* w
 cudaError_t launch_code_sums(const float* z, const float* denom, const int64_t* idx, int64_t n, int d, int k,
                              double* stats, const Workspace& ws, bool want_sums, int num_sms, cudaStream_t s) {
     scan_bins_kernel<<<1, 1024, 0, s>>>(ws.bins_i32, k, n, d, ws.offsets, ws.cursor, stats);
+    ++g_kernel_launches;
     if (!want_sums) return cudaGetLastError();
     scatter_rows_kernel<<<grid_for(n, 256, num_sms, 8), 256, 0, s>>>(idx, n, ws.cursor, ws.perm);
+    ++g_kernel_launches;
     const int64_t items = ((n + kSegRows - 1) / kSegRows) * (d / 4);
     segsum_kernel<<<grid_for(items, 256, num_sms, 32), 256, 0, s>>>(z, denom, idx, ws.perm, n, d, stats + k);
+    ++g_kernel_launches;
     return cudaGetLastError();
 }
 
 // training forward: counting sort by code, then the fused sorted-order pass (z_q, SSE, per-code sums)
 cudaError_t launch_sorted_rows(const float* z, const float* denom, const float* w, const int64_t* idx, int64_t n, int d,
                                int k, float* z_q, double* stats, const Workspace& ws, int num_sms, cudaStream_t s) {
-    scan_bins_kernel<<<1, 1024, 0, s>>>(ws.bins_i32, k, n, d, ws.offsets, ws.cursor, stats);
+    scan_bins_kernel<<<1, 1024, 0, s>>>(ws.bins_i32, k, n, d, ws.offsets, ws.cursor, nullptr);
+    ++g_kernel_launches;
     scatter_rows_kernel<<<grid_for(n, 256, num_sms, 8), 256, 0, s>>>(idx, n, ws.cursor, ws.perm);
+    ++g_kernel_launches;
     const int64_t items = ((n + kSegRows - 1) / kSegRows) * (d / 4);
-    sorted_rows_kernel<<<grid_for(items, 256, num_sms, 32), 256, 0, s>>>(z, denom, w, idx, ws.perm, n, d, k, z_q, stats);
+    sorted_rows_kernel<<<grid_for(items, 256, num_sms, 32), 256, 0, s>>>(z, denom, w, idx, ws.perm, ws.bins_i32, n, d, k, z_q,
+                                                                         stats);
+    ++g_kernel_launches;
     return cudaGetLastError();
 }
 
@@ -437,11 +454,13 @@ cudaError_t launch_ema_finalize(float* weight, float* cluster_size, const double
     ema_finalize_kernel<<<(k + kEmaCodes - 1) / kEmaCodes, 128, smem, s>>>(weight, cluster_size, stats, k, d, (float)beta,
                                                                             (float)decay, (float)(1.0 - decay), update_cs,
                                                                             update_w, loss);
+    ++g_kernel_launches;
     return cudaGetLastError();
 }
 
 cudaError_t launch_loss(const double* stats, int k, int d, double beta, float* loss, cudaStream_t s) {
     loss_kernel<<<1, 1, 0, s>>>(stats, k, d, (float)beta, loss);
+    ++g_kernel_launches;
     return cudaGetLastError();
 }
 

@@ -245,6 +245,7 @@ cudaError_t launch_soft_resolve(const float* x, int64_t n, int d, int k, int top
     if (blocks > (int64_t)num_sms * 16) blocks = (int64_t)num_sms * 16;
     soft_resolve_kernel<<<(int)blocks, 256, 0, stream>>>(x, ws.denom, n, d, k, topk, ws.codes_n, ws.cc, ws.cand, ws.cand_cnt,
                                                          cand_capacity(topk), idx, vals, wts, zq, out, sse, ws.counters);
+    ++g_kernel_launches;
     return cudaGetLastError();
 }
 
@@ -254,6 +255,7 @@ cudaError_t launch_soft_backward(const float* x, int64_t n, int d, const float* 
     int64_t blocks = (n + 7) / 8;
     if (blocks > (int64_t)num_sms * 16) blocks = (int64_t)num_sms * 16;
     soft_backward_kernel<<<(int)blocks, 256, 0, stream>>>(x, n, d, codes, k, topk, idx, wts, g_zq, grad_x, grad_codes);
+    ++g_kernel_launches;
     return cudaGetLastError();
 }
 

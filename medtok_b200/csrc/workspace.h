@@ -14,6 +14,9 @@ constexpr float kBiasSkipTol = 1.0e-6f;
 // counters (ints), zeroed at the start of every assign
 enum Counter { CNT_FLAGGED = 0, CNT_FULL = 1, CNT_CANDS = 2, CNT_LAUNCHES = 3, CNT_OVER = 4, CNT_COUNT = 8 };
 
+// kernels this thread has enqueued (every launcher adds its own; reported through mtvq_debug_counters)
+extern thread_local long g_kernel_launches;
+
 struct Workspace {
     // codebook side
     void*    b_image;      // fp16 operand image, kpad/128 tiles x (d/8+2) planes x 128 rows x 16 B

@@ -253,3 +253,25 @@ if what == "kernels":
     print(f"{'total device time':70s} {tot:9.1f} us/step")
     out["kernels"] = [{"name": r[0], "us_per_step": r[1], "launches_per_step": r[2]} for r in rows]
     json.dump(out, open("gpurun_out/probe_kernels.json", "w"), indent=1)
+
+if what == "stats":
+    # the statistics kernels in isolation (mtvq_code_sums: hist -> scan -> scatter -> segsum), repeated
+    from torch.profiler import profile, ProfilerActivity
+    from medtok_b200.norm_ema_quantizer import hard_assign, code_statistics
+    n, d, k = 1 << 20, 64, 8192
+    torch.manual_seed(0)
+    z = torch.randn(n, d, device=dev)
+    w = torch.nn.functional.normalize(torch.randn(k, d, device=dev), dim=-1)
+    wsx = _lib.Workspace()
+    idx, den = hard_assign(z, w, workspace=wsx)
+    for _ in range(2):
+        code_statistics(z, den, w, idx, workspace=wsx)
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(5):
+            code_statistics(z, den, w, idx, workspace=wsx)
+        torch.cuda.synchronize()
+    for e in sorted(prof.key_averages(), key=lambda e: -getattr(e, "device_time_total", 0)):
+        t = getattr(e, "device_time_total", 0)
+        if t > 0:
+            print(f"{e.key[:70]:70s} {t / 5.0:9.1f} us/call x{e.count / 5.0:.1f}")
