@@ -53,6 +53,10 @@ extern "C" {
 #define MTVQ_F_SKIP_FINALIZE   4u   /* multi-GPU: stop after the packed statistics; the caller all-reduces
                                        `stats` and then calls mtvq_ema_finalize (replaces :188,195,203) */
 
+#define MTVQ_F_ACCUMULATE      8u   /* keep what `stats` already holds and add this call's rows to it: a pass over a
+                                       vocabulary that arrives in batches (inference.py:106-115) ends in ONE
+                                       all-reduce + mtvq_ema_finalize; use together with MTVQ_F_SKIP_FINALIZE */
+
 MTVQ_API int mtvq_abi_version(void);
 MTVQ_API const char * mtvq_last_error(void);
 
@@ -114,6 +118,13 @@ MTVQ_API int mtvq_gather_ste(const float *z, const float *denom, const float *we
 MTVQ_API int mtvq_code_sums(const float *z, const float *denom, const int64_t *idx, int64_t n, int d, int k,
                    double *stats, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Lookup-only quantizer, VectorQuantizer.forward of norm_ema_quantizer.py:222-268: z_q[n,d] = weight[idx]
+ * (F.embedding :117-118,253).  z (raw rows, b h w c order) may be NULL; otherwise *sse (fp64, may be NULL) +=
+ * sum (z_q - z)^2 for the loss of :262-264.  counts (fp32 [k], may be NULL) receives the per-code row counts the
+ * eval branch feeds to the cluster-size EMA (:257-261); it needs a workspace of mtvq_workspace_bytes(n, d, k, 1). */
+MTVQ_API int mtvq_lookup(const float *z, const float *weight, const int64_t *idx, int64_t n, int d, int k,
+                float *z_q, double *sse, float *counts, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- soft path: VectorQuantizer.specific_embedding / shared core
  *      (vector_quantization_soft_one_new.py:120-125,147-185,187-217) ------------------------- */
 
@@ -135,6 +146,13 @@ MTVQ_API int mtvq_soft_backward(const float *x, int64_t n, int d, const float *c
                        const int64_t *idx, const float *wts, const float *g_zq,
                        float *grad_x, float *grad_codes, void *workspace, size_t workspace_bytes,
                        void *stream);
+
+/* VectorQuantizer.codebook_usage (vector_quantization_soft_one_new.py:219-236): next[cap] = the last `cap`
+ * entries of concat(window[cap], float(idx[count])) and *distinct (device int) = number of distinct values in it
+ * (the reference's len(torch.unique(window)); usage = distinct / n_e on the host).  window and next must not
+ * overlap; scratch needs 4 * ((n_e + 31) / 32 + 1) bytes. */
+MTVQ_API int mtvq_codebook_usage(const float *window, const int64_t *idx, int64_t count, int cap, int n_e, float *next,
+                        void *scratch, size_t scratch_bytes, int *distinct, void *stream);
 
 /* ---- diagnostics (not part of the drop-in surface) ---------------------------------------- */
 

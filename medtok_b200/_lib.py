@@ -19,6 +19,7 @@ NORM_STRIDED = 1
 F_TRAINING = 1
 F_UPDATE = 2
 F_SKIP_FINALIZE = 4
+F_ACCUMULATE = 8
 
 _vp = ctypes.c_void_p
 _i64 = ctypes.c_int64
@@ -38,6 +39,8 @@ _SIGNATURES = {
     "mtvq_hard_assign_exact": (_int, [_vp, _i64, _int, _int, _vp, _int, _vp, _vp, _vp, _sz, _vp]),
     "mtvq_gather_ste": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _vp, _vp, _vp]),
     "mtvq_code_sums": (_int, [_vp, _vp, _vp, _i64, _int, _int, _vp, _vp, _sz, _vp]),
+    "mtvq_lookup": (_int, [_vp, _vp, _vp, _i64, _int, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mtvq_codebook_usage": (_int, [_vp, _vp, _i64, _int, _int, _vp, _vp, _sz, _vp, _vp]),
     "mtvq_soft_forward": (_int, [_vp, _i64, _int, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mtvq_soft_backward": (_int, [_vp, _i64, _int, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mtvq_debug_counters": (_int, [_vp, _i64, _int, _int, _int, ctypes.POINTER(_i64), _vp]),

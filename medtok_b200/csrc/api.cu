@@ -211,7 +211,8 @@ int mtvq_hard_forward(const float* z, int64_t n, int d, int norm_mode, float* we
                       double beta, double decay, unsigned flags, float* z_q, int64_t* idx, float* loss, double* stats,
                       void* workspace, size_t workspace_bytes, void* stream) {
     if (int r = check_dims(n, d, k)) return r;
-    if (!z || !weight || !z_q || !idx || !loss || !stats || !workspace) return fail(MTVQ_ERR_BAD_ARG, "null pointer%s", "");
+    if (!weight || !loss || !stats || !workspace || (n > 0 && (!z || !z_q || !idx)))
+        return fail(MTVQ_ERR_BAD_ARG, "null pointer%s", "");
     if (!aligned16(z) || !aligned16(weight) || !aligned16(z_q) || !aligned16(workspace))
         return fail(MTVQ_ERR_BAD_ARG, "z, weight, z_q and workspace must be 16-byte aligned%s", "");
     DeviceInfo di;
@@ -227,7 +228,8 @@ int mtvq_hard_forward(const float* z, int64_t n, int d, int norm_mode, float* we
     if (upd_cs && !cluster_size && !(flags & MTVQ_F_SKIP_FINALIZE))
         return fail(MTVQ_ERR_BAD_ARG, "cluster_size is null%s", "");
 
-    MTVQ_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * mtvq_stats_len(d, k), st), "memset stats");
+    if (!(flags & MTVQ_F_ACCUMULATE))
+        MTVQ_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * mtvq_stats_len(d, k), st), "memset stats");
     if (int r = assign_rows(z, n, d, norm_mode, weight, k, ws.denom, idx, ws, di, false, st)) return r;
     if (n > 0) {
         if (upd_w) {   // per-code sums wanted: one fused pass over the rows in code-sorted order
@@ -243,6 +245,37 @@ int mtvq_hard_forward(const float* z, int64_t n, int d, int norm_mode, float* we
         MTVQ_CUDA(launch_ema_finalize(weight, cluster_size, stats, k, d, beta, decay, upd_cs, upd_w, loss, st),
                   "ema_finalize");
     }
+    return 0;
+}
+
+int mtvq_lookup(const float* z, const float* weight, const int64_t* idx, int64_t n, int d, int k, float* z_q,
+                double* sse, float* counts, void* workspace, size_t workspace_bytes, void* stream) {
+    if (int r = check_dims(n, d, k)) return r;
+    if (!weight || !idx || !z_q) return fail(MTVQ_ERR_BAD_ARG, "null pointer%s", "");
+    if ((z && !aligned16(z)) || !aligned16(weight) || !aligned16(z_q)) return fail(MTVQ_ERR_BAD_ARG, "16-byte alignment%s", "");
+    DeviceInfo di;
+    if (int r = device_info(&di)) return r;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n > 0) MTVQ_CUDA(launch_lookup(z, weight, idx, n, d, k, z_q, sse, di.num_sms, st), "lookup");
+    if (counts) {
+        if (!workspace) return fail(MTVQ_ERR_BAD_ARG, "counts need the workspace%s", "");
+        Workspace ws = carve(workspace, n, d, k, 1);
+        if (ws.total_bytes > workspace_bytes) return fail(MTVQ_ERR_WORKSPACE, "workspace too small%s", "");
+        MTVQ_CUDA(launch_hist_idx64(idx, n, ws.bins_i32, k, di.num_sms, st), "hist");
+        MTVQ_CUDA(launch_counts_to_float(ws.bins_i32, k, counts, st), "counts");
+    }
+    return 0;
+}
+
+int mtvq_codebook_usage(const float* window, const int64_t* idx, int64_t count, int cap, int n_e, float* next,
+                        void* scratch, size_t scratch_bytes, int* distinct, void* stream) {
+    if (!window || !idx || !next || !scratch || !distinct || count <= 0 || cap <= 0 || n_e <= 0)
+        return fail(MTVQ_ERR_BAD_ARG, "bad argument%s", "");
+    if (scratch_bytes < sizeof(unsigned) * ((size_t)(n_e + 31) / 32 + 1)) return fail(MTVQ_ERR_WORKSPACE, "scratch too small%s", "");
+    DeviceInfo di;
+    if (int r = device_info(&di)) return r;
+    MTVQ_CUDA(launch_usage(window, idx, count, cap, n_e, next, static_cast<unsigned*>(scratch), distinct, di.num_sms,
+                           static_cast<cudaStream_t>(stream)), "usage");
     return 0;
 }
 

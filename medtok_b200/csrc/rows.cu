@@ -93,6 +93,77 @@ __global__ void __launch_bounds__(256) gather_ste_kernel(const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
+// lookup-only quantizer (norm_ema_quantizer.py:222-268): z_q = w[idx]; optional SSE against raw z (:262-264)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lookup_kernel(const float* __restrict__ z, const float* __restrict__ w,
+                                                      const int64_t* __restrict__ idx, int64_t n, int d, int k,
+                                                      float* __restrict__ z_q, double* __restrict__ sse_out) {
+    const int vpr = d >> 2;
+    const int64_t nvec = n * vpr;
+    const int lane = threadIdx.x & 31;
+    double sse = 0.0;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = v / vpr;
+        const int c4 = (int)(v - row * vpr);
+        const int64_t code = __ldg(idx + row);
+        if (code < 0 || code >= k) __trap();                    // F.embedding device-asserts on the same input
+        const float4 c = __ldg(reinterpret_cast<const float4*>(w + code * d) + c4);
+        __stcs(reinterpret_cast<float4*>(z_q) + v, c);
+        if (z != nullptr) {
+            const float4 x = __ldcs(reinterpret_cast<const float4*>(z) + v);
+            const float d0 = __fsub_rn(c.x, x.x), d1 = __fsub_rn(c.y, x.y), d2 = __fsub_rn(c.z, x.z), d3 = __fsub_rn(c.w, x.w);
+            sse += (double)__fmul_rn(d0, d0) + (double)__fmul_rn(d1, d1) + (double)__fmul_rn(d2, d2) + (double)__fmul_rn(d3, d3);
+        }
+    }
+    if (sse_out == nullptr) return;
+    sse = warp_sum(sse);
+    __shared__ double part[8];
+    if (lane == 0) part[threadIdx.x >> 5] = sse;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += part[i];
+        atomicAdd(sse_out, t);
+    }
+}
+
+__global__ void counts_to_float_kernel(const int* __restrict__ bins, int k, float* __restrict__ counts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < k) counts[i] = (float)bins[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// codebook usage (vector_quantization_soft_one_new.py:219-236): sliding float32 window of the last `cap` code
+// indices, usage = #distinct values in the window / n_e.  The reference shifts the window with a clone and counts with
+// sort + unique; here the shifted window is written to a second buffer while a bitmap collects the values.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) usage_shift_kernel(const float* __restrict__ window, const int64_t* __restrict__ idx,
+                                                           int64_t cur, int cap, float* __restrict__ next,
+                                                           unsigned* __restrict__ bitmap, int nbits) {
+    // window' = concat(window[cur:], idx[-min(cur, cap):]) (reference :224-232 keeps the last `cap` entries)
+    const int64_t keep = cur >= cap ? 0 : cap - cur;          // old entries that survive
+    const int64_t skip = cur >= cap ? cur - cap : 0;           // new entries that fall off immediately
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = i < keep ? window[i + (cap - keep)] : (float)idx[skip + (i - keep)];
+        next[i] = v;
+        const int b = (int)v;
+        // out-of-range / non-integral values share one extra bit (counted as one distinct value)
+        const bool in_range = b >= 0 && b < nbits && (float)b == v;
+        unsigned* word = &bitmap[in_range ? (b >> 5) : ((nbits + 31) >> 5)];
+        const unsigned bit = in_range ? 1u << (b & 31) : 1u;
+        if (!(*reinterpret_cast<volatile unsigned*>(word) & bit)) atomicOr(word, bit);
+    }
+}
+
+__global__ void __launch_bounds__(256) usage_count_kernel(const unsigned* __restrict__ bitmap, int nwords,
+                                                           int* __restrict__ distinct) {
+    int c = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += gridDim.x * blockDim.x) c += __popc(bitmap[i]);
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(distinct, c);
+}
+
+// ------------------------------------------------------------------------------------------------
 // counting sort of rows by code
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) scan_bins_kernel(const int* __restrict__ bins, int k, int64_t n, int d,
@@ -401,6 +472,33 @@ cudaError_t launch_hist_idx64(const int64_t* idx, int64_t n, int* bins_i32, int 
     cudaError_t e = cudaMemsetAsync(bins_i32, 0, sizeof(int) * k, s);
     if (e != cudaSuccess) return e;
     hist_kernel<<<grid_for(n, 256, num_sms, 8), 256, 0, s>>>(idx, n, bins_i32);
+    ++g_kernel_launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lookup(const float* z, const float* w, const int64_t* idx, int64_t n, int d, int k, float* z_q,
+                          double* sse, int num_sms, cudaStream_t s) {
+    lookup_kernel<<<grid_for(n * (d / 4), 256, num_sms, 16), 256, 0, s>>>(z, w, idx, n, d, k, z_q, sse);
+    ++g_kernel_launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_counts_to_float(const int* bins, int k, float* counts, cudaStream_t s) {
+    counts_to_float_kernel<<<(k + 255) / 256, 256, 0, s>>>(bins, k, counts);
+    ++g_kernel_launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_usage(const float* window, const int64_t* idx, int64_t cur, int cap, int n_e, float* next,
+                         unsigned* bitmap, int* distinct, int num_sms, cudaStream_t s) {
+    const int nwords = (n_e + 31) / 32 + 1;
+    cudaError_t e = cudaMemsetAsync(bitmap, 0, sizeof(unsigned) * nwords, s);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(distinct, 0, sizeof(int), s);
+    if (e != cudaSuccess) return e;
+    usage_shift_kernel<<<grid_for(cap, 256, num_sms, 4), 256, 0, s>>>(window, idx, cur, cap, next, bitmap, n_e);
+    ++g_kernel_launches;
+    usage_count_kernel<<<grid_for(nwords, 256, num_sms, 1), 256, 0, s>>>(bitmap, nwords, distinct);
     ++g_kernel_launches;
     return cudaGetLastError();
 }

@@ -8,6 +8,13 @@
 namespace mtvq {
 
 cudaError_t launch_hist_idx64(const int64_t* idx, int64_t n, int* bins_i32, int k, int num_sms, cudaStream_t s);
+cudaError_t launch_lookup(const float* z, const float* w, const int64_t* idx, int64_t n, int d, int k, float* z_q,
+                          double* sse, int num_sms, cudaStream_t s);
+cudaError_t launch_counts_to_float(const int* bins, int k, float* counts, cudaStream_t s);
+// window' = last `cap` of concat(window, idx) into `next`; *distinct = #distinct values in window'
+// (bitmap: (n_e + 31) / 32 + 1 words of scratch)
+cudaError_t launch_usage(const float* window, const int64_t* idx, int64_t cur, int cap, int n_e, float* next,
+                         unsigned* bitmap, int* distinct, int num_sms, cudaStream_t s);
 cudaError_t launch_gather_ste(const float* z, const float* denom, const float* w, const int64_t* idx, int64_t n, int d,
                               int k, float* z_q, double* stats, int num_sms, cudaStream_t s);
 cudaError_t launch_code_sums(const float* z, const float* denom, const int64_t* idx, int64_t n, int d, int k,

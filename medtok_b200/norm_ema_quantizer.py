@@ -301,3 +301,75 @@ class NormEMAVectorQuantizer(nn.Module):
         else:
             z_q = z_q.view(b, h, w, c).permute(0, 3, 1, 2)           # reference :217
         return z_q, loss, idx
+
+
+# ------------------------------------------------------------------------------------------------
+class VectorQuantizer(nn.Module):
+    """Drop-in for the lookup-only quantizer, reference :222-268: code indices in, codebook rows out
+    (`forward(bhw, encoding_indices, z=None) -> (z_q[b,c,h,w], loss, encoding_indices)`); in eval mode the
+    per-code counts replace `cluster_size` (the reference's EMA there runs with decay forced to 0, :230-231)."""
+
+    def __init__(self, n_embed, embedding_dim, beta, decay=0.99, eps=1e-5,
+                 statistic_code_usage=True, kmeans_init=False, codebook_init_path=''):
+        super().__init__()
+        self.codebook_dim = embedding_dim
+        self.num_tokens = n_embed
+        self.beta = beta
+        decay = 0.
+        self.decay = decay
+        self.embedding = EmbeddingEMA(self.num_tokens, self.codebook_dim, decay, eps, kmeans_init, codebook_init_path)
+        self.statistic_code_usage = statistic_code_usage
+        if statistic_code_usage:
+            self.register_buffer('cluster_size', torch.zeros(n_embed))
+        if distributed.is_available() and distributed.is_initialized():
+            print("ddp is enable, so use ddp_reduce to sync the statistic_code_usage for each gpu!", file=sys.stderr)
+            self.all_reduce_fn = distributed.all_reduce
+        else:
+            self.all_reduce_fn = nn.Identity()
+        self._ws = _lib.Workspace()
+
+    def reset_cluster_size(self, device):
+        if self.statistic_code_usage:
+            self.register_buffer('cluster_size', torch.zeros(self.num_tokens))
+            self.cluster_size = self.cluster_size.to(device)
+
+    def _run(self, idx: torch.Tensor, z_rows: torch.Tensor | None):
+        weight = self.embedding.weight.data
+        _lib.require_cuda(weight, "embedding.weight")
+        _lib.require_cuda(idx, "encoding_indices")
+        if weight.dtype != torch.float32 or not weight.is_contiguous():
+            raise _lib.MedTokVQError("embedding.weight must be a contiguous fp32 tensor")
+        dev = weight.device
+        k, d = weight.shape
+        flat = idx.reshape(-1)
+        if flat.dtype != torch.int64 or not flat.is_contiguous():
+            flat = flat.to(torch.int64).contiguous()
+        n = flat.shape[0]
+        z_q = torch.empty(n, d, dtype=torch.float32, device=dev)
+        sse = torch.zeros(1, dtype=torch.float64, device=dev) if z_rows is not None else None
+        # the reference only needs cluster_size when statistic_code_usage registered it (:236-238,257-261)
+        want_counts = (not self.training) and self.statistic_code_usage
+        counts = torch.empty(k, dtype=torch.float32, device=dev) if want_counts else None
+        ws = self._ws.get(n, d, k, 1, dev) if want_counts else None
+        _lib.check(_lib.lib().mtvq_lookup(_lib.ptr(z_rows), _lib.ptr(weight), _lib.ptr(flat), n, d, k, _lib.ptr(z_q),
+                                          _lib.ptr(sse), _lib.ptr(counts), _lib.ptr(ws), 0 if ws is None else ws.numel(),
+                                          _lib.stream_ptr(dev)), "mtvq_lookup")
+        if want_counts:
+            self.all_reduce_fn(counts)                                   # reference :259
+            self.cluster_size.data.copy_(counts)                         # ema_inplace with decay 0 (:260)
+        if z_rows is not None:
+            loss = (sse * (float(self.beta) / float(max(n * d, 1)))).float().reshape(())
+        else:
+            loss = torch.zeros((), dtype=torch.float32, device=dev)      # :266
+        return z_q, loss
+
+    def forward(self, bhw, encoding_indices, z=None):
+        b, h, w = int(bhw[0]), int(bhw[1]), int(bhw[2])
+        z_rows = None
+        if z is not None:
+            _lib.require_cuda(z, "z")
+            z_rows = _rows_f32(z.permute(0, 2, 3, 1)).reshape(-1, z.shape[1])      # :263 'b c h w -> b h w c'
+        # the codebook parameter has requires_grad=False and the loss detaches z (:264): no output carries a gradient
+        z_q, loss = self._run(encoding_indices, z_rows)
+        z_q = z_q.view(b, h, w, -1).permute(0, 3, 1, 2)                             # :267
+        return z_q, loss, encoding_indices

@@ -144,6 +144,9 @@ class VectorQuantizer(nn.Module):
         if self.show_usage:
             self.register_buffer("codebook_used", torch.zeros(300000))
         self._ws = _lib.Workspace()
+        self._usage_next = None
+        self._usage_scratch = None
+        self._usage_last = 0.0
 
     # -- quantisation core ----------------------------------------------------------------------
     def _quantize(self, x, lo, hi):
@@ -192,20 +195,36 @@ class VectorQuantizer(nn.Module):
         return z_q, (vq, commit, F.normalize(original_embedding, p=2, dim=-1), z_q), usage
 
     def codebook_usage(self, min_encoding_indices, types='shared'):
-        """reference :219-236: sliding float32 window, len(unique)/n_e (quirks kept: the zero padding is
-        counted and slice-relative indices are divided by the full table size)."""
+        """reference :219-236: sliding float32 window of the last 300000 code ids, len(unique)/n_e (quirks kept: the
+        zero padding is counted and slice-relative indices are divided by the full table size).  The shift and
+        the distinct count are one pass of mtvq_codebook_usage (bitmap + popcount instead of clone + sort +
+        unique); like the reference the result is a Python float, i.e. one device->host read of 4 bytes."""
         if not self.show_usage:
             return 0.0
+        _lib.require_cuda(self.codebook_used, "codebook_used")
         with torch.no_grad():
-            flat = min_encoding_indices.reshape(-1).to(self.codebook_used.dtype)
-            cur = flat.shape[0]
-            cap = self.codebook_used.shape[0]
-            if cur >= cap:
-                self.codebook_used.copy_(flat[-cap:])
-            else:
-                self.codebook_used[:-cur] = self.codebook_used[cur:].clone()
-                self.codebook_used[-cur:] = flat
-            return len(torch.unique(self.codebook_used)) / self.n_e
+            flat = min_encoding_indices.detach().reshape(-1)
+            if flat.dtype != torch.int64 or not flat.is_contiguous():
+                flat = flat.to(torch.int64).contiguous()
+            if flat.numel() == 0:
+                return self._usage_last
+            window = self.codebook_used
+            dev = window.device
+            cap = window.shape[0]
+            if self._usage_next is None or self._usage_next.shape != window.shape or self._usage_next.device != dev:
+                self._usage_next = torch.empty_like(window)
+            words = (self.n_e + 31) // 32 + 1
+            if self._usage_scratch is None or self._usage_scratch.numel() < words + 1 or self._usage_scratch.device != dev:
+                self._usage_scratch = torch.empty(words + 1, dtype=torch.int32, device=dev)
+            distinct = self._usage_scratch[words:]
+            _lib.check(_lib.lib().mtvq_codebook_usage(_lib.ptr(window), _lib.ptr(flat), flat.numel(), cap, self.n_e,
+                                                      _lib.ptr(self._usage_next), _lib.ptr(self._usage_scratch),
+                                                      4 * words, _lib.ptr(distinct), _lib.stream_ptr(dev)),
+                       "mtvq_codebook_usage")
+            # swap the two window buffers; `codebook_used` stays the registered buffer (same state_dict key)
+            self._usage_next, self.codebook_used = window, self._usage_next
+            self._usage_last = int(distinct.item()) / self.n_e
+            return self._usage_last
 
     def forward(self, z, text_features, graph_node_features, text_attention_mask, batch, z_aug=None):
         """reference :238-271"""

@@ -214,6 +214,50 @@ def gen_kmeans(hard):
 
 
 # ------------------------------------------------------------------------------------------
+def gen_lookup(hard):
+    """lookup-only VectorQuantizer (norm_ema_quantizer.py:222-268): eval (counts -> cluster_size) and train,
+    with and without z, h*w > 1 included."""
+    g = torch.Generator().manual_seed(31)
+    for name, (b, h, w, d, k), training, with_z in (("lookup_eval_b64_d64_k512", (64, 1, 1, 64, 512), False, True),
+                                                    ("lookup_train_b6_hw12_d32_k300", (6, 3, 4, 32, 300), True, True),
+                                                    ("lookup_eval_noz_b5_hw4_d128_k64", (5, 2, 2, 128, 64), False, False)):
+        q = hard.VectorQuantizer(n_embed=k, embedding_dim=d, beta=0.25)
+        q.train(training)
+        q.cluster_size.fill_(3.0)                                   # must be overwritten (decay is forced to 0)
+        idx = torch.randint(0, k, (b * h * w,), generator=g)
+        idx[: max(1, idx.numel() // 8)] = idx[0]                    # a crowded code
+        z = torch.randn(b, d, h, w, generator=g) if with_z else None
+        with torch.no_grad():
+            z_q, loss, out_idx = q((b, h, w), idx, z)
+        rec = {"weight": _np(q.embedding.weight), "idx": _np(idx), "z_q": _np(z_q), "loss": _np(loss).reshape(1),
+               "cluster_size": _np(q.cluster_size)}
+        if with_z:
+            rec["z"] = _np(z)
+        save(name, {"kind": "lookup", "bhw": [b, h, w], "beta": 0.25, "training": training, "with_z": with_z,
+                    "state_dict_keys": sorted(q.state_dict().keys())}, **rec)
+
+
+def gen_usage(soft):
+    """codebook_usage (vector_quantization_soft_one_new.py:219-236): a sequence of calls on one window."""
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        q = soft.VectorQuantizer(n_e=3000, e_dim=16, beta=0.25, entropy_loss_ratio=0.0, l2_norm=True, show_usage=True,
+                                 split=[16, 16])
+    q.register_buffer("codebook_used", torch.zeros(300000))       # plain buffer (harness accommodation i)
+    g = torch.Generator().manual_seed(17)
+    rec, usages = {}, []
+    with torch.no_grad():
+        for i, (rows, hi) in enumerate(((100, 1000), (7000, 3000), (59999, 40), (1, 3000), (60000, 2999), (33333, 1500))):
+            idx = torch.randint(0, hi, (rows, 5), generator=g)
+            usages.append(q.codebook_usage(idx, types=("shared", "text-specific", "graph-specific")[i % 3]))
+            rec[f"idx_{i}"] = _np(idx)
+    rec["window"] = _np(q.codebook_used)
+    rec["usage"] = np.asarray(usages, np.float64)
+    save("usage_window_ne3000", {"kind": "usage", "n_e": 3000, "calls": len(usages)}, **rec)
+
+
+# ------------------------------------------------------------------------------------------
 def _gloo_worker(rank, world, port, zs, w0, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -256,7 +300,7 @@ def gen_gloo(hard):
 
 def main():
     hard, soft = ref_loader.load()
-    which = set(sys.argv[1:]) or {"hard", "soft", "kmeans", "gloo"}
+    which = set(sys.argv[1:]) or {"hard", "soft", "kmeans", "gloo", "lookup", "usage"}
     if "hard" in which:
         gen_hard(hard)
     if "soft" in which:
@@ -265,6 +309,10 @@ def main():
         gen_kmeans(hard)
     if "gloo" in which:
         gen_gloo(hard)
+    if "lookup" in which:
+        gen_lookup(hard)
+    if "usage" in which:
+        gen_usage(soft)
 
 
 if __name__ == "__main__":

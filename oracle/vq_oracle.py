@@ -248,6 +248,25 @@ def usage_window(window, new_idx, n_e):
     return w, len(np.unique(w)) / n_e
 
 
+def lookup_forward(bhw, idx, weight, beta, z=None, training=False):
+    """Lookup-only VectorQuantizer.forward, norm_ema_quantizer.py:250-268: z_q = weight[idx] viewed b h w c and
+    returned b c h w (:253,267); eval: cluster_size <- bincount (EMA with decay forced to 0, :230,257-261);
+    loss = beta * mean((z_q - z)^2) against z rearranged b h w c (:262-264), 0 without z (:266).
+    Returns (z_q[b,c,h,w], loss, counts or None)."""
+    b, h, w = bhw
+    weight = _f32(weight)
+    idx = np.asarray(idx, np.int64).reshape(-1)
+    rows = weight[idx]                                          # F.embedding
+    counts = None if training else np.bincount(idx, minlength=weight.shape[0]).astype(np.float32)
+    if z is not None:
+        zr = np.transpose(_f32(z), (0, 2, 3, 1)).reshape(-1, weight.shape[1])
+        diff = rows - zr
+        loss = float(beta) * float(np.mean((diff * diff).astype(np.float64)))
+    else:
+        loss = 0.0
+    return np.ascontiguousarray(np.transpose(rows.reshape(b, h, w, -1), (0, 3, 1, 2))), loss, counts
+
+
 # ------------------------------------------------------------------------------------------
 # k-means init (norm_ema_quantizer.py:24-57, cosine branch) given the initial means
 # ------------------------------------------------------------------------------------------
