@@ -99,6 +99,26 @@ __device__ __forceinline__ float canon_sumsq(Get get, int d) {
     return fin;
 }
 
+// canon_sumsq of a row held in shared memory, with the 32 independent accumulator chains (4 accumulators x 8 lanes)
+// spread over the lanes of a warp: the additions inside each chain and the order in which the chains are folded are
+// exactly those of canon_sumsq, only the chains run side by side.  d % 8 == 0; every lane returns the sum.
+__device__ __forceinline__ float warp_canon_sumsq(const float* xs, int d, int lane) {
+    const int u = lane >> 3, v = lane & 7;
+    const int nvec = d >> 3, n4 = nvec >> 2;
+    float a = 0.f;
+    for (int c = 0; c < n4; ++c) { const float e = xs[(c * 4 + u) * 8 + v]; a = __fadd_rn(a, __fmul_rn(e, e)); }
+    if (u == 0)
+        for (int i = n4 * 4; i < nvec; ++i) { const float e = xs[i * 8 + v]; a = __fadd_rn(a, __fmul_rn(e, e)); }
+    float f = __shfl_sync(0xffffffffu, a, v);                                 // acc[0][v]
+    f = __fadd_rn(f, __shfl_sync(0xffffffffu, a, 8 + v));
+    f = __fadd_rn(f, __shfl_sync(0xffffffffu, a, 16 + v));
+    f = __fadd_rn(f, __shfl_sync(0xffffffffu, a, 24 + v));
+    float fin = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) fin = __fadd_rn(fin, __shfl_sync(0xffffffffu, f, t));
+    return fin;
+}
+
 // d = fl( fl(zz + cc) - fl(2 * dot) ), dot = sequential fmaf chain (MKL sgemm, oracle: dist_row)
 __device__ __forceinline__ float canon_dist(float zz, float cc, float dot) {
     return __fsub_rn(__fadd_rn(zz, cc), __fmul_rn(2.0f, dot));

@@ -29,12 +29,258 @@ constexpr int kMaxTop = 8;
 
 }  // namespace
 
-__global__ void __launch_bounds__(256) soft_resolve_kernel(
-    const float* __restrict__ x, const float* __restrict__ denom, int64_t n, int d, int k, int topk,
+// Eight lanes per row, four rows per warp.  A row's candidate codes (a handful, listed by the tensor pass) are staged
+// into the group's shared-memory tile with coalesced 16-byte loads (8 lanes = one 128-byte line), eight candidates per
+// batch, and lane g then runs candidate g's sequential fmaf chain out of shared memory; merge, softmax and the weighted
+// sum stay inside the 8-lane group.  (One warp per row spent ~1500 issue slots per row with mostly idle lanes and was
+// issue-bound at 2.2 ms for 2^20 rows.)  Rows whose list is unusable (fewer than top-k entries or overflow) are
+// appended to `full_rows` for soft_full_scan_kernel.
+constexpr int kSoftWarps = 8;
+constexpr int kLaneList  = 3;     // candidates per lane: cand_cap (24) / 8 lanes
+
+// lexicographic (value, index) minimum across an aligned 8-lane group; NaN never wins
+__device__ __forceinline__ Pick group_argmin(Pick p) {
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, p.v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, p.i, o);
+        if (ov < p.v || (ov == p.v && oi < p.i)) { p.v = ov; p.i = oi; }
+    }
+    return p;
+}
+
+// canon_sumsq (common.cuh) of a row in shared memory by an 8-lane group: lane v runs the four accumulator chains
+// acc[0..3][v] in the reference order, folds them 1,2,3 -> 0, and the eight lane sums are added in lane order.
+__device__ __forceinline__ float group_canon_sumsq(const float* xs, int d, int g) {
+    const int nvec = d >> 3, n4 = nvec >> 2;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int c = 0; c < n4; ++c) {
+        const float e0 = xs[(c * 4 + 0) * 8 + g], e1 = xs[(c * 4 + 1) * 8 + g];
+        const float e2 = xs[(c * 4 + 2) * 8 + g], e3 = xs[(c * 4 + 3) * 8 + g];
+        a0 = __fadd_rn(a0, __fmul_rn(e0, e0)); a1 = __fadd_rn(a1, __fmul_rn(e1, e1));
+        a2 = __fadd_rn(a2, __fmul_rn(e2, e2)); a3 = __fadd_rn(a3, __fmul_rn(e3, e3));
+    }
+    for (int i = n4 * 4; i < nvec; ++i) { const float e = xs[i * 8 + g]; a0 = __fadd_rn(a0, __fmul_rn(e, e)); }
+    a0 = __fadd_rn(a0, a1); a0 = __fadd_rn(a0, a2); a0 = __fadd_rn(a0, a3);
+    float fin = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) fin = __fadd_rn(fin, __shfl_sync(0xffffffffu, a0, t, 8));
+    return fin;
+}
+
+template <int NQ, int KT>   // NQ: 16-byte units of a row per lane of the group, ceil(d / 32); KT: top-k bound (KT == 5: k is 5)
+__global__ void __launch_bounds__(kSoftWarps * 32) soft_resolve_kernel(
+    const float* __restrict__ x, const float* __restrict__ denom, int64_t n, int d, int k, int topk_rt,
     const float* __restrict__ cn, const float* __restrict__ cc, const int* __restrict__ cand,
     const int* __restrict__ cand_cnt, int cand_cap, int64_t* __restrict__ idx_out, float* __restrict__ val_out,
     float* __restrict__ wts_out, float* __restrict__ zq_out, float* __restrict__ out, double* __restrict__ sse_out,
-    int* __restrict__ counters) {
+    int* __restrict__ full_rows, int* __restrict__ counters) {
+    extern __shared__ __align__(16) float soft_smem[];
+    const int topk = (KT == 5) ? 5 : topk_rt;    // compile-time for MedTok's k = 5: the per-row loops below fully unroll
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int grp = lane >> 3, g = lane & 7;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int nv = d >> 2;                       // float4 per row (<= 64)
+    const int ds = d + 4;                        // tile row stride: 16-byte aligned, conflict free for 8 lanes x float4
+    float* xs = soft_smem + (size_t)(wib * 4 + grp) * (d + 8 * ds);   // per group: normalised row | 8-candidate tile
+    float* tile = xs + d;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const float4* cn4 = reinterpret_cast<const float4*>(cn);
+    double sse = 0.0;
+
+    // A warp takes 32 consecutive rows at a time (candidate counts and norms: one coalesced load per lane), four rows
+    // per step; while a step is being scored the raw rows and candidate lists of the next step are already in flight,
+    // so no HBM round trip sits on the critical path (L2 gather of the candidates -> fmaf chain -> merge -> gather of
+    // the top-k rows, which the staging has just pulled into L1).
+    const int64_t nblk = (n + 31) >> 5;
+    for (int64_t blk = warp; blk < nblk; blk += nwarps) {
+      const int64_t base = blk << 5;
+      int cnt_l = 0;
+      float den_l = 1.0f;
+      if (base + lane < n) { cnt_l = cand_cnt[base + lane]; den_l = denom[base + lane]; }
+      float4 nx[NQ];
+      int ncl[kLaneList];
+      auto fetch = [&](int step) {
+          const int64_t row = base + 4 * step + grp;
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) {
+              const int f = g + 8 * q;
+              nx[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (row < n && f < nv) nx[q] = __ldcs(x4 + row * nv + f);
+          }
+#pragma unroll
+          for (int b = 0; b < kLaneList; ++b)
+              ncl[b] = (row < n && g + 8 * b < cand_cap) ? __ldcs(cand + row * cand_cap + g + 8 * b) : -1;
+      };
+      fetch(0);
+      for (int step = 0; step < 8 && base + 4 * step < n; ++step) {
+        const int64_t row = base + 4 * step + grp;
+        const int cnt = __shfl_sync(0xffffffffu, cnt_l, 4 * step + grp);
+        const float den = __shfl_sync(0xffffffffu, den_l, 4 * step + grp);
+        float4 xr[NQ];
+        int cl[kLaneList];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) xr[q] = nx[q];
+#pragma unroll
+        for (int b = 0; b < kLaneList; ++b) cl[b] = ncl[b];
+        __syncwarp();                                         // the previous step is done with xs / tile
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const int f = g + 8 * q;
+            if (f < nv)
+                *reinterpret_cast<float4*>(xs + 4 * f) = make_float4(__fdiv_rn(xr[q].x, den), __fdiv_rn(xr[q].y, den),
+                                                                     __fdiv_rn(xr[q].z, den), __fdiv_rn(xr[q].w, den));
+        }
+        if (step + 1 < 8 && base + 4 * (step + 1) < n) fetch(step + 1);
+        const bool active = row < n && cnt >= topk && cnt <= cand_cap;
+        if (row < n && !active && g == 0) full_rows[atomicAdd(&counters[CNT_FULL], 1)] = (int)row;
+        __syncwarp();
+        const float xx = group_canon_sumsq(xs, d, g);        // ||xn||^2 in the reference's cascade order
+
+        // each lane keeps an ascending (value, index) list of the candidates it scored
+        float lv[kLaneList];
+        int li[kLaneList];
+#pragma unroll
+        for (int t = 0; t < kLaneList; ++t) { lv[t] = INFINITY; li[t] = 0x7fffffff; }
+        const int nbat = __reduce_max_sync(0xffffffffu, active ? (cnt + 7) >> 3 : 0);
+#pragma unroll
+        for (int b = 0; b < kLaneList; ++b) {
+            if (b >= nbat) break;                             // warp-uniform
+            const int nb = active ? min(8, max(0, cnt - 8 * b)) : 0;
+            const int mine = g < nb ? cl[b] : -1;
+            const int maxnb = __reduce_max_sync(0xffffffffu, nb);
+            __syncwarp();                                     // the previous batch's chains are done with the tile
+            for (int j0 = 0; j0 < maxnb; j0 += 2) {           // two candidates = 2 NQ independent 16-byte loads per lane
+                float4 v[2][NQ];
+                bool ok[2];
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int col = __shfl_sync(0xffffffffu, mine, j0 + jj, 8);
+                    ok[jj] = col >= 0 && col < k;
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) {
+                        const int f = g + 8 * q;
+                        if (ok[jj] && f < nv) v[jj][q] = __ldg(cn4 + (size_t)col * nv + f);
+                    }
+                }
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) {
+                        const int f = g + 8 * q;
+                        if (ok[jj] && f < nv) *reinterpret_cast<float4*>(tile + (j0 + jj) * ds + 4 * f) = v[jj][q];
+                    }
+            }
+            __syncwarp();
+            if (mine >= 0 && mine < k) {
+                const float4* tr = reinterpret_cast<const float4*>(tile + g * ds);
+                float dot = 0.0f;
+#pragma unroll 8
+                for (int i = 0; i < nv; ++i) {                // sequential fmaf chain over d (reference order)
+                    const float4 xv = *reinterpret_cast<const float4*>(xs + 4 * i);
+                    const float4 cv = tr[i];
+                    dot = __fmaf_rn(xv.x, cv.x, dot);
+                    dot = __fmaf_rn(xv.y, cv.y, dot);
+                    dot = __fmaf_rn(xv.z, cv.z, dot);
+                    dot = __fmaf_rn(xv.w, cv.w, dot);
+                }
+                float v = canon_dist(xx, __ldg(cc + mine), dot);
+                int ci = mine;
+#pragma unroll
+                for (int t = 0; t < kLaneList; ++t) {
+                    if (v < lv[t] || (v == lv[t] && ci < li[t])) {
+                        const float tv = lv[t]; const int ti = li[t];
+                        lv[t] = v; li[t] = ci; v = tv; ci = ti;
+                    }
+                }
+            }
+        }
+
+        // merge: topk rounds of a group-wide argmin over the list heads
+        float sv[KT];
+        int si[KT], sl[KT];                                   // value, code, tile slot (= owner lane of the group)
+#pragma unroll
+        for (int t = 0; t < KT; ++t) {
+            sl[t] = 0;
+            if (t < topk) {
+                Pick best = group_argmin(Pick{lv[0], li[0]});
+                sv[t] = best.v; si[t] = best.i;
+                const bool owner = li[0] == best.i && lv[0] == best.v;
+                sl[t] = __ffs((__ballot_sync(0xffffffffu, owner) >> (8 * grp)) & 0xffu) - 1;
+                if (owner) {                                  // owner pops its head
+#pragma unroll
+                    for (int u = 0; u + 1 < kLaneList; ++u) { lv[u] = lv[u + 1]; li[u] = li[u + 1]; }
+                    lv[kLaneList - 1] = INFINITY; li[kLaneList - 1] = 0x7fffffff;
+                }
+            } else { sv[t] = INFINITY; si[t] = 0; }
+        }
+        if (!active) continue;                                // (no warp-level primitive below this point)
+        // softmax(-vals): exp(x - max) / sum with max = -vals[0]
+        float wgt[KT];
+        float s = 0.0f;
+#pragma unroll
+        for (int t = 0; t < KT; ++t) {
+            wgt[t] = 0.0f;
+            if (t < topk) { wgt[t] = expf(__fsub_rn(sv[0], sv[t])); s = __fadd_rn(s, wgt[t]); }
+        }
+#pragma unroll
+        for (int t = 0; t < KT; ++t) if (t < topk) wgt[t] = __fdiv_rn(wgt[t], s);
+        if (g < topk) {
+            float v = 0.f, wv = 0.f; int ii = 0;
+#pragma unroll
+            for (int t = 0; t < KT; ++t) if (t == g) { v = sv[t]; wv = wgt[t]; ii = si[t]; }
+            idx_out[row * topk + g] = ii;
+            val_out[row * topk + g] = v;
+            wts_out[row * topk + g] = wv;
+        }
+        // zq = sum_j w_j * cn[idx_j] (products, then a sequential sum over j); out = x + (zq - x).  With a single batch
+        // (<= 8 candidates, the normal case) the top-k rows are still in the group's tile.
+        const bool in_tile = cnt <= 8;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const int f = g + 8 * q;
+            if (f < nv) {
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int t = 0; t < KT; ++t)
+                    if (t < topk) {
+                        const float4 c = in_tile ? *reinterpret_cast<const float4*>(tile + max(sl[t], 0) * ds + 4 * f)
+                                                 : __ldg(cn4 + (size_t)min(si[t], k - 1) * nv + f);
+                        a.x = __fadd_rn(a.x, __fmul_rn(wgt[t], c.x)); a.y = __fadd_rn(a.y, __fmul_rn(wgt[t], c.y));
+                        a.z = __fadd_rn(a.z, __fmul_rn(wgt[t], c.z)); a.w = __fadd_rn(a.w, __fmul_rn(wgt[t], c.w));
+                    }
+                const float4 xv = xr[q];
+                const float4 df = make_float4(__fsub_rn(a.x, xv.x), __fsub_rn(a.y, xv.y), __fsub_rn(a.z, xv.z),
+                                              __fsub_rn(a.w, xv.w));
+                __stcs(reinterpret_cast<float4*>(zq_out) + row * nv + f, a);
+                __stcs(reinterpret_cast<float4*>(out) + row * nv + f,
+                       make_float4(__fadd_rn(xv.x, df.x), __fadd_rn(xv.y, df.y), __fadd_rn(xv.z, df.z),
+                                   __fadd_rn(xv.w, df.w)));
+                sse += (double)__fmul_rn(df.x, df.x) + (double)__fmul_rn(df.y, df.y) + (double)__fmul_rn(df.z, df.z) +
+                       (double)__fmul_rn(df.w, df.w);
+            }
+        }
+      }
+    }
+    sse = warp_sum(sse);
+    __shared__ double part[kSoftWarps];
+    if (lane == 0) part[wib] = sse;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += part[i];
+        if (t != 0.0) atomicAdd(sse_out, t);
+    }
+}
+
+// Fallback for the rows listed in full_rows: every code is scored (one warp per row, lanes split the codes).
+__global__ void __launch_bounds__(256) soft_full_scan_kernel(
+    const float* __restrict__ x, const float* __restrict__ denom, int64_t n, int d, int k, int topk,
+    const float* __restrict__ cn, const float* __restrict__ cc, const int* __restrict__ full_rows,
+    int64_t* __restrict__ idx_out, float* __restrict__ val_out, float* __restrict__ wts_out, float* __restrict__ zq_out,
+    float* __restrict__ out, double* __restrict__ sse_out, const int* __restrict__ counters) {
     __shared__ __align__(16) float xn_s[8][kMaxDim];          // one normalised row per warp
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -43,7 +289,9 @@ __global__ void __launch_bounds__(256) soft_resolve_kernel(
     float* xs = xn_s[wib];
     double sse = 0.0;
 
-    for (int64_t row = warp; row < n; row += nwarps) {
+    const int nfull = counters[CNT_FULL];
+    for (int64_t p = warp; p < nfull; p += nwarps) {
+        const int64_t row = full_rows[p];
         const float* xr = x + row * d;
         const float den = denom[row];
         __syncwarp();
@@ -51,18 +299,13 @@ __global__ void __launch_bounds__(256) soft_resolve_kernel(
         __syncwarp();
         // ||xn||^2 in the reference's cascade order (every lane the same value; shared-memory broadcasts)
         const float xx = canon_sumsq([&](int i) { return xs[i]; }, d);
-        const int cnt = cand_cnt[row];
-        const bool full = (cnt < topk) || (cnt > cand_cap);
 
         // each lane keeps an ascending list of its own best `topk` (value, index) pairs
         float lv[kMaxTop];
         int li[kMaxTop];
 #pragma unroll
         for (int t = 0; t < kMaxTop; ++t) { lv[t] = INFINITY; li[t] = 0x7fffffff; }
-        const int total = full ? k : cnt;
-        for (int j = lane; j < total; j += 32) {
-            const int col = full ? j : cand[row * cand_cap + j];
-            if (col >= k) continue;
+        for (int col = lane; col < k; col += 32) {
             const float4* cr = reinterpret_cast<const float4*>(cn + (size_t)col * d);
             float dot = 0.0f;
             for (int i = 0; i < d; i += 4) {                       // sequential fmaf chain over d (reference order)
@@ -84,7 +327,6 @@ __global__ void __launch_bounds__(256) soft_resolve_kernel(
                 }
             }
         }
-        if (full && lane == 0) atomicAdd(&counters[CNT_FULL], 1);
 
         // merge: topk rounds of a warp-wide argmin over the list heads
         float sv[kMaxTop];
@@ -124,7 +366,7 @@ __global__ void __launch_bounds__(256) soft_resolve_kernel(
             float a = 0.0f;
 #pragma unroll
             for (int t = 0; t < kMaxTop; ++t)
-                if (t < topk) a = __fadd_rn(a, __fmul_rn(wgt[t], __ldg(cn + (size_t)si[t] * d + c)));
+                if (t < topk) a = __fadd_rn(a, __fmul_rn(wgt[t], __ldg(cn + (size_t)min(si[t], k - 1) * d + c)));
             const float xv = __ldg(xr + c);
             const float diff = __fsub_rn(a, xv);
             zq_out[row * d + c] = a;
@@ -241,10 +483,43 @@ __global__ void __launch_bounds__(256) soft_backward_kernel(const float* __restr
 cudaError_t launch_soft_resolve(const float* x, int64_t n, int d, int k, int topk, const Workspace& ws, int64_t* idx,
                                 float* vals, float* wts, float* zq, float* out, double* sse, int num_sms,
                                 cudaStream_t stream) {
-    int64_t blocks = (n + 7) / 8;
-    if (blocks > (int64_t)num_sms * 16) blocks = (int64_t)num_sms * 16;
-    soft_resolve_kernel<<<(int)blocks, 256, 0, stream>>>(x, ws.denom, n, d, k, topk, ws.codes_n, ws.cc, ws.cand, ws.cand_cnt,
-                                                         cand_capacity(topk), idx, vals, wts, zq, out, sse, ws.counters);
+    const int cap = cand_capacity(topk);
+    if (cap > 8 * kLaneList) return cudaErrorInvalidValue;
+    // shared memory: per 8-lane group the normalised row and an 8-candidate tile; d > 128 runs 4 warps per CTA
+    const int warps = d <= 128 ? kSoftWarps : kSoftWarps / 2;
+    const size_t smem = sizeof(float) * warps * 4 * ((size_t)d + 8 * (size_t)(d + 4));
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaSuccess;
+#define MTVQ_SOFT_ATTR(NQ_, KT_)                                                                                   \
+        if (e == cudaSuccess)                                                                                      \
+            e = cudaFuncSetAttribute(soft_resolve_kernel<NQ_, KT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        MTVQ_SOFT_ATTR(2, 5) MTVQ_SOFT_ATTR(4, 5) MTVQ_SOFT_ATTR(8, 5) MTVQ_SOFT_ATTR(2, 8) MTVQ_SOFT_ATTR(4, 8) MTVQ_SOFT_ATTR(8, 8)
+#undef MTVQ_SOFT_ATTR
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int per_sm = (int)((220 * 1024) / (smem + 1024)) < 1 ? 1 : (int)((220 * 1024) / (smem + 1024));
+    int64_t blocks = (n + 32 * warps - 1) / (32 * warps);
+    if (blocks > (int64_t)num_sms * per_sm) blocks = (int64_t)num_sms * per_sm;   // all resident; warps stride over 32-row blocks
+#define MTVQ_SOFT_ARGS x, ws.denom, n, d, k, topk, ws.codes_n, ws.cc, ws.cand, ws.cand_cnt, cap, idx, vals, wts, zq, out, sse, \
+                       ws.full_rows, ws.counters
+#define MTVQ_SOFT_LAUNCH(NQ_)                                                                                      \
+    do {                                                                                                           \
+        if (topk == 5) soft_resolve_kernel<NQ_, 5><<<(int)blocks, warps * 32, smem, stream>>>(MTVQ_SOFT_ARGS);     \
+        else           soft_resolve_kernel<NQ_, 8><<<(int)blocks, warps * 32, smem, stream>>>(MTVQ_SOFT_ARGS);     \
+    } while (0)
+    if (d <= 64)       MTVQ_SOFT_LAUNCH(2);
+    else if (d <= 128) MTVQ_SOFT_LAUNCH(4);
+    else               MTVQ_SOFT_LAUNCH(8);
+#undef MTVQ_SOFT_LAUNCH
+#undef MTVQ_SOFT_ARGS
+    ++g_kernel_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    // rows without a usable candidate list (device-side count, normally zero): every code is scored
+    soft_full_scan_kernel<<<num_sms * 2, 256, 0, stream>>>(x, ws.denom, n, d, k, topk, ws.codes_n, ws.cc, ws.full_rows, idx,
+                                                          vals, wts, zq, out, sse, ws.counters);
     ++g_kernel_launches;
     return cudaGetLastError();
 }

@@ -275,3 +275,36 @@ if what == "stats":
         t = getattr(e, "device_time_total", 0)
         if t > 0:
             print(f"{e.key[:70]:70s} {t / 5.0:9.1f} us/call x{e.count / 5.0:.1f}")
+
+if what == "softkernels":
+    # per-kernel device times of one soft-one quantisation at the C3 shape (CUPTI via torch.profiler)
+    from torch.profiler import profile, ProfilerActivity
+    from medtok_b200.vector_quantization_soft_one_new import _SoftQuantizeFn
+    n, d, k, kk = int(os.environ.get("PROBE_N", str(1 << 20))), int(os.environ.get("PROBE_D", "128")), int(os.environ.get("PROBE_K", "16384")), 5
+    torch.manual_seed(0)
+    x = torch.randn(n, d, device=dev)
+    table = torch.randn(k, d, device=dev)
+    wsx = _lib.Workspace()
+    with torch.no_grad():
+        for i in range(2):
+            _SoftQuantizeFn.apply(x, table, 0, k, kk, 0.25, True, wsx)
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for i in range(5):
+                _SoftQuantizeFn.apply(x, table, 0, k, kk, 0.25, True, wsx)
+            torch.cuda.synchronize()
+    rows = []
+    for e in prof.key_averages():
+        t = getattr(e, "device_time_total", None)
+        if t is None:
+            t = e.cuda_time_total
+        if t > 0:
+            rows.append((e.key[:70], t / 5.0, e.count / 5.0))
+    rows.sort(key=lambda r: -r[1])
+    for name, us, cnt in rows:
+        print(f"{name:70s} {us:9.1f} us/call  x{cnt:.1f}")
+    cnt = _lib.debug_counters(wsx.buf, n, d, k, kk)
+    print("counters", cnt)
+    out["soft_kernels"] = [{"name": r[0], "us_per_call": r[1], "launches_per_call": r[2]} for r in rows]
+    out["soft_counters"] = cnt
+    json.dump(out, open("gpurun_out/probe_softkernels.json", "w"), indent=1)
