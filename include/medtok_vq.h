@@ -181,6 +181,11 @@ MTVQ_API int mtvq_debug_set_events(void *event_before, void *event_after);
  * +4 tile reduced. */
 MTVQ_API int mtvq_debug_set_trace(void *trace_dev);
 
+/* route of mtvq_soft_forward on this host thread: 0 = production (one tensor pass + two-pass fallback for overflow
+ * rows), 1 = two tensor passes for every row (k-th score bound, then collect), 2 = no tensor pass, every row scored
+ * against every code by the exact CUDA-core scan (cross-check; slow).  All three give bit-identical results. */
+MTVQ_API int mtvq_debug_set_soft_route(int route);
+
 /* micro-benchmarks used to size the epilogue (DESIGN.md "measured machine limits"):
  * which = 0: tcgen05.ld throughput, 1: FMNMX3 tree throughput; result_host[0] = device ms,
  * result_host[1] = bytes or ops processed. */

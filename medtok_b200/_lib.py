@@ -48,6 +48,7 @@ _SIGNATURES = {
                                         _vp, _sz, _vp]),
     "mtvq_debug_set_events": (_int, [_vp, _vp]),
     "mtvq_debug_set_trace": (_int, [_vp]),
+    "mtvq_debug_set_soft_route": (_int, [_int]),
     "mtvq_microbench": (_int, [_int, _int, _int, ctypes.POINTER(_dbl), _vp]),
 }
 

@@ -22,6 +22,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 thread_local long long* g_trace = nullptr;
+thread_local int g_soft_route = 0;   // mtvq_debug_set_soft_route
 thread_local cudaEvent_t g_ev_before = nullptr, g_ev_after = nullptr;
 
 int fail(int code, const char* fmt, const char* a = "", long b = 0, long c = 0) {
@@ -87,6 +88,7 @@ void fill_coarse(CoarseParams& p, const float* z, int64_t n, int d, int norm_mod
     p.denom = denom; p.idx_out = idx_out; p.bins = ws.bins_i32; p.best_val = ws.best_val;
     p.flag_rows = ws.flag_rows; p.over_rows = ws.full_rows; p.counters = ws.counters;
     p.cand = ws.cand; p.cand_cnt = ws.cand_cnt; p.cand_cap = cand_capacity(topk); p.topk = topk;
+    p.topk_scratch = ws.topk_scratch;
     p.trace = g_trace;
     p.lbo_bytes = desc_swap() ? 128 : 2048;
     p.sbo_bytes = desc_swap() ? 2048 : 128;
@@ -300,10 +302,28 @@ int mtvq_soft_forward(const float* x, int64_t n, int d, const float* codes, int 
     CoarseParams p;
     fill_coarse(p, x, n, d, MTVQ_NORM_CONTIGUOUS, k, ws, ws.denom, topk);
     const int rt = coarse_row_tiles(d, n, di.num_sms);
-    MTVQ_CUDA(launch_coarse(p, MODE_THRESH, rt, di.num_sms, st), "coarse thresh");
-    CoarseParams c = p;
-    c.denom = nullptr;
-    MTVQ_CUDA(launch_coarse(c, MODE_COLLECT, rt, di.num_sms, st), "coarse collect");
+    // ONE tensor pass: every thread tracks its best granules (scores kept as fp16 records in an L2-resident scratch)
+    // and the row block's end turns them into the per-row candidate lists.  Rows whose tracking overflowed (more than
+    // eight qualifying granules in one thread's share, or more than cand_cap candidates) are listed in flag_rows and
+    // go through the two-pass route (k-th score bound, then collect) -- the row count is only known on the device.
+    if (g_soft_route == 2) {
+        // cross-check route: no tensor pass, every row is scored against every code by the exact CUDA-core scan
+        MTVQ_CUDA(launch_norms(x, n, d, ws.denom, di.num_sms, st), "norms");
+    } else if (g_soft_route == 1) {
+        MTVQ_CUDA(launch_coarse(p, MODE_THRESH, rt, di.num_sms, st), "coarse thresh");
+        CoarseParams c = p;
+        c.denom = nullptr;
+        MTVQ_CUDA(launch_coarse(c, MODE_COLLECT, rt, di.num_sms, st), "coarse collect");
+    } else {
+        p.over_rows = ws.flag_rows;
+        MTVQ_CUDA(launch_coarse(p, MODE_TOPK, rt, di.num_sms, st), "coarse topk");
+        CoarseParams c = p;
+        c.row_list = ws.flag_rows;
+        c.n_rows_dev = ws.counters + CNT_OVER;
+        c.denom = nullptr;
+        MTVQ_CUDA(launch_coarse(c, MODE_THRESH, 1, di.num_sms, st), "coarse thresh(overflow)");
+        MTVQ_CUDA(launch_coarse(c, MODE_COLLECT, 1, di.num_sms, st), "coarse collect(overflow)");
+    }
     MTVQ_CUDA(launch_soft_resolve(x, n, d, k, topk, ws, idx, vals, wts, zq, out, sse, di.num_sms, st), "soft_resolve");
     return 0;
 }
@@ -361,6 +381,12 @@ int mtvq_debug_coarse_scores(const float* z, int64_t n, int d, int norm_mode, co
     if (rt != 1 && rt != 2 && rt != 4) rt = 1;
     if (rt * d > 256) rt = 256 / d;
     MTVQ_CUDA(launch_coarse(p, MODE_DUMP, rt, di.num_sms, st), "coarse dump");
+    return 0;
+}
+
+int mtvq_debug_set_soft_route(int route) {
+    if (route < 0 || route > 2) return fail(MTVQ_ERR_BAD_ARG, "route must be 0, 1 or 2%s", "");
+    g_soft_route = route;
     return 0;
 }
 

@@ -142,6 +142,30 @@ __device__ __forceinline__ void record_store(unsigned char* slots, int rec, cons
     }
 }
 
+// MODE_TOPK keeps records in a per-CTA global scratch (L2 resident): uint4 index ((slot * 4 + c) * kRecords + rec)
+__device__ __forceinline__ void record_store_g(uint4* dst, const float (&v)[32]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        __half2 h0 = __floats2half2_rn(v[8 * c + 0], v[8 * c + 1]);
+        __half2 h1 = __floats2half2_rn(v[8 * c + 2], v[8 * c + 3]);
+        __half2 h2 = __floats2half2_rn(v[8 * c + 4], v[8 * c + 5]);
+        __half2 h3 = __floats2half2_rn(v[8 * c + 6], v[8 * c + 7]);
+        uint4 q;
+        q.x = *reinterpret_cast<uint32_t*>(&h0); q.y = *reinterpret_cast<uint32_t*>(&h1);
+        q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
+        __stcg(dst + c * kRecords, q);
+    }
+}
+
+constexpr int kTopSlots = 8;    // granules tracked per thread in MODE_TOPK (slot id rides in the low 3 mantissa bits)
+
+__device__ __forceinline__ float select_kth(const float (&t)[kTopSlots], int kidx) {
+    float r = t[0];
+#pragma unroll
+    for (int i = 1; i < kTopSlots; ++i) r = (i <= kidx) ? t[i] : r;
+    return r;
+}
+
 // per-row running state of one row tile
 template <int NTOP>
 struct RowState {
@@ -221,6 +245,50 @@ __device__ __forceinline__ void consume_argmax64(const float (&va)[32], const fl
             }
         }
     }
+}
+
+// TOPK (single-pass soft top-k): a thread keeps its kTopSlots best granules of the row block -- the granule maximum
+// (sorted list `top`, slot id packed into the low 3 mantissa bits: relative error 2^-20, covered by the margin), the
+// granule id (shared memory) and the 32 scores as an fp16 record (global scratch).  A granule can only matter if its
+// maximum is within the margin of the row's final k-th largest granule maximum, and that is at least the thread's own
+// k-th best so far: the trigger `cmax >= thr`, thr = top[k-1] - margin, fires ~k/i of the time at the i-th granule.
+__device__ __forceinline__ void consume_topk(const float (&v)[32], int gran, float (&top)[kTopSlots], float& thr, int kidx,
+                                             float margin, uint4* rec_base, uint16_t* gid) {
+    const float cmax = max32(v);
+    const bool trig = cmax >= thr;
+    if (__any_sync(0xffffffffu, trig)) {
+        if (trig) {
+            const int slot = __float_as_int(top[kTopSlots - 1]) & 7;          // the entry that would fall off
+            const float x = __int_as_float((__float_as_int(cmax) & ~7) | slot);
+            // x <= top[7]: eight tracked granules are already at least as good; the row is then reported as an
+            // overflow at the block end (top[7] within the margin), if it matters at all
+            if (x > top[kTopSlots - 1]) {
+                record_store_g(rec_base + slot * (4 * kRecords), v);
+                gid[slot * kRecords] = (uint16_t)gran;
+                topn_insert<kTopSlots>(top, x);
+                thr = select_kth(top, kidx) - margin;
+            }
+        }
+    }
+}
+
+// scan_record on the global scratch (read through L2: other threads of the CTA wrote it)
+__device__ __forceinline__ int scan_record_g(const uint4* src, float ts, int col0, int* dst, int n0, int cap) {
+    uint4 q[4];
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) q[cc] = __ldcg(src + cc * kRecords);
+    int n = 0;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        const uint32_t wds[4] = {q[cc].x, q[cc].y, q[cc].z, q[cc].w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&wds[t]));
+            if (f.x >= ts) { if (n0 + n < cap) dst[n0 + n] = col0 + cc * 8 + 2 * t;     ++n; }
+            if (f.y >= ts) { if (n0 + n < cap) dst[n0 + n] = col0 + cc * 8 + 2 * t + 1; ++n; }
+        }
+    }
+    return n;
 }
 
 // scan one fp16 record for columns >= ts; optionally write them to dst[n...] (capacity cap)
@@ -365,6 +433,12 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
         asm volatile("" : "+r"(full_addr[0]), "+r"(full_addr[1]), "+r"(empty_addr[0]), "+r"(empty_addr[1]),
                           "+r"(tld[0]), "+r"(tld[1]), "+r"(is_lane0));
 
+        // TOPK: margin widened by the slot-id packing error (2^-20 relative on a score bounded by |w| + |w|^2 / 2)
+        const float nwmax = p.meta[META_MAXNORM];
+        const float margin_k = margin + 4.0e-6f * (1.0f + nwmax + 0.5f * nwmax * nwmax);
+        const int kidx = min(max(p.topk, 1), kTopSlots) - 1;
+        uint4* topk_rec = static_cast<uint4*>(p.topk_scratch) + (size_t)blockIdx.x * (kTopkScratchPerCta / 16) + rec0;
+        uint16_t* topk_gid = reinterpret_cast<uint16_t*>(smem + kOffSlots) + rec0;    // [slot][1024 records]
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
             const int blk = (MODE == MODE_COLLECT) ? item / ksplit : item;
             const int cbeg = (MODE == MODE_COLLECT) ? (item - blk * ksplit) * cps : 0;
@@ -385,7 +459,8 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                 st[ss].m1 = st[ss].m2 = st[ss].m3 = st[ss].thr = -INFINITY;
                 st[ss].best_chunk = st[ss].chunk2 = 0;
 #pragma unroll
-                for (int i = 0; i < NTOP; ++i) st[ss].top[i] = -INFINITY;
+                for (int i = 0; i < NTOP; ++i)   // TOPK: finite sentinels carrying the slot ids 0..7 in their low bits
+                    st[ss].top[i] = (MODE == MODE_TOPK) ? __int_as_float((int)((0xFF61B1E0u & ~7u) | (unsigned)i)) : -INFINITY;
                 st[ss].T = INFINITY;
                 if (MODE == MODE_COLLECT && st[ss].valid) st[ss].T = p.best_val[st[ss].row] - margin;
             }
@@ -413,6 +488,13 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                     if (DBG && (p.debug_flags & 1)) continue;    // timing experiment: no epilogue work
                     if (MODE == MODE_ARGMAX) {
                         consume_argmax64<NTOP>(va, vb, c * 4 + half2, st[ss], margin, slots, ss * 512 + rec0);
+                    } else if (MODE == MODE_TOPK) {
+                        if constexpr (NTOP == kTopSlots) {
+                            consume_topk(va, c * 4 + half2, st[ss].top, st[ss].thr, kidx, margin_k,
+                                         topk_rec + ss * 512, topk_gid + ss * 512);
+                            consume_topk(vb, c * 4 + half2 + 1, st[ss].top, st[ss].thr, kidx, margin_k,
+                                         topk_rec + ss * 512, topk_gid + ss * 512);
+                        }
                     } else {
                         consume<MODE, NTOP>(va, c * 4 + half2, st[ss], margin, p, slots, ss * 512 + rec0);
                         consume<MODE, NTOP>(vb, c * 4 + half2 + 1, st[ss], margin, p, slots, ss * 512 + rec0);
@@ -513,6 +595,75 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                     }
                 }
                 named_bar_sync(bar_id, bar_n);
+            } else if (MODE == MODE_TOPK) {
+                if constexpr (NTOP == kTopSlots) {
+                float* tl = reinterpret_cast<float*>(smem + kOffSlots + 2 * kTopSlots * kRecords);   // [record][8], after the ids
+#pragma unroll
+                for (int ss = 0; ss < NS; ++ss) {
+                    float4* t4 = reinterpret_cast<float4*>(tl + (ss * 512 + rec0) * 8);
+                    t4[0] = make_float4(st[ss].top[0], st[ss].top[1], st[ss].top[2], st[ss].top[3]);
+                    t4[1] = make_float4(st[ss].top[4], st[ss].top[5], st[ss].top[6], st[ss].top[7]);
+                }
+                named_bar_sync(bar_id, bar_n);
+                if (leader) {
+                    const uint4* rec_cta = static_cast<const uint4*>(p.topk_scratch) + (size_t)blockIdx.x * (kTopkScratchPerCta / 16);
+                    const uint16_t* gid_all = reinterpret_cast<const uint16_t*>(smem + kOffSlots);
+#pragma unroll
+                    for (int ss = 0; ss < NS; ++ss) {
+                        // k-th largest granule maximum over the threads that shared the row
+#pragma unroll
+                        for (int pp = 0; pp < NP; ++pp)
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh) {
+                                const int w2 = quarter + 4 * hh + 8 * ((RT == 1) ? pp : pair);
+                                if (w2 == warp) continue;
+                                const float4* o4 = reinterpret_cast<const float4*>(tl + (ss * 512 + w2 * 32 + lane) * 8);
+                                const float4 oa = o4[0], ob = o4[1];
+                                topn_insert<NTOP>(st[ss].top, oa.x); topn_insert<NTOP>(st[ss].top, oa.y);
+                                topn_insert<NTOP>(st[ss].top, oa.z); topn_insert<NTOP>(st[ss].top, oa.w);
+                                topn_insert<NTOP>(st[ss].top, ob.x); topn_insert<NTOP>(st[ss].top, ob.y);
+                                topn_insert<NTOP>(st[ss].top, ob.z); topn_insert<NTOP>(st[ss].top, ob.w);
+                            }
+                        const float kth = select_kth(st[ss].top, kidx);
+                        const float thrG = kth - margin_k;
+                        // records are fp16: accept anything that could be >= thrG before rounding
+                        const float thrS = thrG - (fmaxf(fabsf(kth), fabsf(thrG)) * 4.8829e-4f + 1e-7f);
+                        bool over = !(kth > -1.0e37f);           // fewer than k granules seen, or NaN scores
+                        int nw = 0;
+                        int* dst = p.cand + st[ss].row * p.cand_cap;
+                        if (st[ss].valid) {
+#pragma unroll
+                            for (int pp = 0; pp < NP; ++pp)
+#pragma unroll
+                                for (int hh = 0; hh < 2; ++hh) {
+                                    const int w2 = quarter + 4 * hh + 8 * ((RT == 1) ? pp : pair);
+                                    const int rec = ss * 512 + w2 * 32 + lane;
+                                    for (int i = 0; i < kTopSlots; ++i) {
+                                        const float e = tl[rec * 8 + i];
+                                        if (!(e >= thrG)) break;
+                                        if (i == kTopSlots - 1) over = true;     // an untracked granule may qualify too
+                                        const int slot = __float_as_int(e) & 7;
+                                        const int gran = gid_all[slot * kRecords + rec];
+                                        nw += scan_record_g(rec_cta + (slot * 4) * kRecords + rec, thrS, gran * kChunk, dst, nw,
+                                                            p.cand_cap);
+                                    }
+                                }
+                            if (nw > p.cand_cap || nw < p.topk) over = true;
+                            if (!over) p.cand_cnt[st[ss].row] = nw;
+                        }
+                        // overflow rows (rare) get their list from a THRESH + COLLECT pass over `over_rows`
+                        const bool ov = st[ss].valid && over;
+                        const unsigned oall = __ballot_sync(0xffffffffu, ov);
+                        if (oall) {
+                            int base = 0;
+                            if (lane == 0) base = atomicAdd(&p.counters[CNT_OVER], __popc(oall));
+                            base = __shfl_sync(0xffffffffu, base, 0);
+                            if (ov) p.over_rows[base + __popc(oall & ((1u << lane) - 1))] = (int)st[ss].row;
+                        }
+                    }
+                }
+                named_bar_sync(bar_id, bar_n);
+                }
             } else if (MODE == MODE_THRESH) {
                 float* tl = reinterpret_cast<float*>(smem + kOffSlots);   // [record][8]
 #pragma unroll
@@ -769,7 +920,8 @@ int coarse_row_tiles(int d, int64_t nrows, int num_sms) {
 
 cudaError_t launch_coarse(const CoarseParams& p, int mode, int row_tiles, int num_sms, cudaStream_t stream) {
     // NTOP only matters in THRESH mode (size of the per-row top list): 5 covers MedTok's k = 5
-    const int ntop = (mode == MODE_THRESH && p.topk > 5) ? 8 : 5;
+    const int ntop = ((mode == MODE_THRESH && p.topk > 5) || mode == MODE_TOPK) ? 8 : 5;
+    if (mode == MODE_TOPK && (num_sms > kTopkMaxCtas || p.topk_scratch == nullptr)) return cudaErrorInvalidValue;
     // timing knobs / pipeline trace live in a separate instantiation so that the production kernels carry none of it
     const bool dbg = (mode == MODE_ARGMAX) && (p.trace != nullptr || p.debug_flags != 0);
 #define MTVQ_CASE(RT_, MODE_, NTOP_)                                                                   \
@@ -782,7 +934,8 @@ cudaError_t launch_coarse(const CoarseParams& p, int mode, int row_tiles, int nu
     MTVQ_CASE(RT_, MODE_COLLECT, 5) \
     MTVQ_CASE(RT_, MODE_DUMP, 5)    \
     MTVQ_CASE(RT_, MODE_THRESH, 5)  \
-    MTVQ_CASE(RT_, MODE_THRESH, 8)
+    MTVQ_CASE(RT_, MODE_THRESH, 8)  \
+    MTVQ_CASE(RT_, MODE_TOPK, 8)
     MTVQ_MODES(1)
     MTVQ_MODES(2)
     MTVQ_MODES(4)

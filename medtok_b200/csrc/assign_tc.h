@@ -7,7 +7,12 @@
 
 namespace mtvq {
 
-enum CoarseMode { MODE_ARGMAX = 0, MODE_THRESH = 1, MODE_COLLECT = 2, MODE_DUMP = 3 };
+enum CoarseMode { MODE_ARGMAX = 0, MODE_THRESH = 1, MODE_COLLECT = 2, MODE_DUMP = 3, MODE_TOPK = 4 };
+
+// MODE_TOPK keeps the fp16 scores of every thread's best granules in an L2-resident scratch: per CTA 8 slots x 4 x
+// 1024 records x 16 B
+constexpr size_t kTopkScratchPerCta = 8 * 4 * 1024 * 16;
+constexpr int    kTopkMaxCtas       = 160;
 
 struct CoarseParams {
     // rows
@@ -35,6 +40,7 @@ struct CoarseParams {
     int*         cand_cnt;   // [rows]
     int          cand_cap;
     int          topk;
+    void*        topk_scratch; // TOPK: kTopkScratchPerCta bytes per CTA
     float*       dump;       // DUMP: [dump_rows, kpad]
     int64_t      dump_rows;
     // shared-memory descriptor strides (kept as parameters so tests can probe the encoding)

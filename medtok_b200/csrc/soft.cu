@@ -480,6 +480,21 @@ __global__ void __launch_bounds__(256) soft_backward_kernel(const float* __restr
     }
 }
 
+// canonical row norms alone (cross-check route of the soft forward: no tensor pass has written `denom`)
+__global__ void norms_kernel(const float* __restrict__ x, int64_t n, int d, float* __restrict__ denom) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    const float* xr = x + row * d;
+    denom[row] = canon_denom([&](int i) { return __ldg(xr + i); }, d, 0);
+}
+
+cudaError_t launch_norms(const float* x, int64_t n, int d, float* denom, int num_sms, cudaStream_t stream) {
+    (void)num_sms;
+    norms_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(x, n, d, denom);
+    ++g_kernel_launches;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_soft_resolve(const float* x, int64_t n, int d, int k, int topk, const Workspace& ws, int64_t* idx,
                                 float* vals, float* wts, float* zq, float* out, double* sse, int num_sms,
                                 cudaStream_t stream) {

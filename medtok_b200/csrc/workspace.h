@@ -31,6 +31,7 @@ struct Workspace {
     int*     cand_cnt;     // [n]
     int*     full_rows;    // [n]
     int*     counters;     // [CNT_COUNT]
+    void*    topk_scratch; // soft path: per-CTA record scratch of the single-pass top-k kernel (L2 resident)
     // statistics side
     int*     bins_i32;     // [k]
     int*     offsets;      // [k+1]
@@ -67,6 +68,7 @@ inline Workspace carve(void* base, int64_t n, int d, int k, int topk) {
     w.cand_cnt  = (int*)take(sizeof(int) * n);
     w.full_rows = (int*)take(sizeof(int) * n);
     w.counters  = (int*)take(sizeof(int) * CNT_COUNT);
+    w.topk_scratch = take(topk > 1 ? (size_t)160 * (8 * 4 * 1024 * 16) : 0);   // kTopkMaxCtas x kTopkScratchPerCta
     w.bins_i32  = (int*)take(sizeof(int) * k);
     w.offsets   = (int*)take(sizeof(int) * (k + 1));
     w.cursor    = (int*)take(sizeof(int) * k);

@@ -115,3 +115,33 @@ def test_full_forward_matches_reference(mode, dev):
         assert isinstance(out[key], float) and out[key] == float(a["out::" + key][0])
     for key in ("shared_embed_loss", "text_specific_loss", "graph_specific_loss"):
         assert float(out[key][0]) == 0.0 and float(out[key][1]) == 0.0
+
+
+@pytest.mark.parametrize("n,d,k,kk", [(60000, 128, 16384, 5), (50000, 64, 8192, 5), (20000, 256, 4096, 8),
+                                      (30000, 32, 1000, 3), (40000, 64, 21000, 5)])
+def test_single_pass_equals_two_pass_and_exact_scan(dev, n, d, k, kk):
+    """The production route (one tensor pass, records in the L2 scratch) must give bit-identical top-k indices,
+    distances, weights and outputs to the two-pass route and to the exact CUDA-core scan of every code."""
+    from medtok_b200 import _lib
+    from medtok_b200.vector_quantization_soft_one_new import _SoftQuantizeFn
+    g = torch.Generator().manual_seed(n + d)
+    x = (torch.randn(n, d, generator=g) * 0.7).to(dev)
+    table = torch.randn(k, d, generator=g).to(dev)
+    table[5] = table[4]                                          # duplicated codes: exact ties, lower index first
+    res = []
+    try:
+        for route in (0, 1, 2):
+            _lib.check(_lib.lib().mtvq_debug_set_soft_route(route), "route")
+            ws = _lib.Workspace()
+            with torch.no_grad():
+                out, vq, commit, idx, wts = _SoftQuantizeFn.apply(x, table, 0, k, kk, 0.25, True, ws)
+            cnt = _lib.debug_counters(ws.buf, n, d, k, kk)
+            res.append((out, vq, idx, wts, cnt))
+    finally:
+        _lib.lib().mtvq_debug_set_soft_route(0)
+    for r in res[1:]:
+        assert torch.equal(res[0][2], r[2]), "top-k indices differ between routes"
+        assert torch.equal(res[0][3], r[3]) and torch.equal(res[0][0], r[0])
+        assert abs(float(res[0][1]) - float(r[1])) <= 1e-6 * float(r[1])
+    assert res[0][4]["full_scan_rows"] <= 0.01 * n, res[0][4]
+    assert res[2][4]["full_scan_rows"] == n
