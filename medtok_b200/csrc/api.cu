@@ -304,8 +304,9 @@ int mtvq_soft_forward(const float* x, int64_t n, int d, const float* codes, int 
     const int rt = coarse_row_tiles(d, n, di.num_sms);
     // ONE tensor pass: every thread tracks its best granules (scores kept as fp16 records in an L2-resident scratch)
     // and the row block's end turns them into the per-row candidate lists.  Rows whose tracking overflowed (more than
-    // eight qualifying granules in one thread's share, or more than cand_cap candidates) are listed in flag_rows and
-    // go through the two-pass route (k-th score bound, then collect) -- the row count is only known on the device.
+    // eight qualifying granules in one thread's share, or more than cand_cap candidates) are listed in flag_rows with
+    // their k-th score bound in best_val and get their list from a COLLECT pass -- the row count is only known on the
+    // device, the kernel splits the codebook over CTAs to fill the SMs.
     if (g_soft_route == 2) {
         // cross-check route: no tensor pass, every row is scored against every code by the exact CUDA-core scan
         MTVQ_CUDA(launch_norms(x, n, d, ws.denom, di.num_sms, st), "norms");
@@ -321,7 +322,6 @@ int mtvq_soft_forward(const float* x, int64_t n, int d, const float* codes, int 
         c.row_list = ws.flag_rows;
         c.n_rows_dev = ws.counters + CNT_OVER;
         c.denom = nullptr;
-        MTVQ_CUDA(launch_coarse(c, MODE_THRESH, 1, di.num_sms, st), "coarse thresh(overflow)");
         MTVQ_CUDA(launch_coarse(c, MODE_COLLECT, 1, di.num_sms, st), "coarse collect(overflow)");
     }
     MTVQ_CUDA(launch_soft_resolve(x, n, d, k, topk, ws, idx, vals, wts, zq, out, sse, di.num_sms, st), "soft_resolve");

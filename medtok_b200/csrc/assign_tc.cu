@@ -167,19 +167,19 @@ __device__ __forceinline__ float select_kth(const float (&t)[kTopSlots], int kid
 }
 
 // per-row running state of one row tile
-template <int NTOP>
+template <int NLIST>
 struct RowState {
     float m1, m2, m3, thr;  // ARGMAX: best granule max (its scores are in the record), second-best granule max,
                             //         max over every other granule seen, m1 - margin
     int   best_chunk, chunk2;   //     granule ids of m1 and m2
-    float top[NTOP];        // THRESH: largest granule maxima, descending
+    float top[NLIST];       // THRESH / TOPK: largest granule maxima, descending
     float T;                // COLLECT: threshold
     int64_t pos, row;
     bool  valid;
 };
 
-template <int MODE, int NTOP>
-__device__ __forceinline__ void consume(const float (&v)[32], int chunk, RowState<NTOP>& st, float margin,
+template <int MODE, int NTOP, int NLIST>
+__device__ __forceinline__ void consume(const float (&v)[32], int chunk, RowState<NLIST>& st, float margin,
                                         const CoarseParams& p, unsigned char* slots, int rec) {
     if (MODE == MODE_DUMP) {
         if (st.valid && st.pos < p.dump_rows) {
@@ -191,7 +191,7 @@ __device__ __forceinline__ void consume(const float (&v)[32], int chunk, RowStat
     }
     const float cmax = max32(v);
     if (MODE == MODE_THRESH) {
-        topn_insert<NTOP>(st.top, cmax);
+        if constexpr (NLIST == NTOP) topn_insert<NTOP>(st.top, cmax);
     } else if (MODE == MODE_COLLECT) {
         const bool trig = cmax >= st.T;
         if (__any_sync(0xffffffffu, trig)) {
@@ -252,22 +252,33 @@ __device__ __forceinline__ void consume_argmax64(const float (&va)[32], const fl
 // granule id (shared memory) and the 32 scores as an fp16 record (global scratch).  A granule can only matter if its
 // maximum is within the margin of the row's final k-th largest granule maximum, and that is at least the thread's own
 // k-th best so far: the trigger `cmax >= thr`, thr = top[k-1] - margin, fires ~k/i of the time at the i-th granule.
+template <int KSTATIC>
 __device__ __forceinline__ void consume_topk(const float (&v)[32], int gran, float (&top)[kTopSlots], float& thr, int kidx,
-                                             float margin, uint4* rec_base, uint16_t* gid) {
+                                             float margin, uint4* rec_base, uint16_t* gid, float4* pub, const float4* partner) {
     const float cmax = max32(v);
     const bool trig = cmax >= thr;
     if (__any_sync(0xffffffffu, trig)) {
         if (trig) {
-            const int slot = __float_as_int(top[kTopSlots - 1]) & 7;          // the entry that would fall off
+            // thr >= top[7] always, so the new entry never falls off itself: it evicts top[7] and takes over its slot
+            // (an evicted granule that still matters shows up as top[7] within the margin at the block end: overflow)
+            const int slot = __float_as_int(top[kTopSlots - 1]) & 7;
             const float x = __int_as_float((__float_as_int(cmax) & ~7) | slot);
-            // x <= top[7]: eight tracked granules are already at least as good; the row is then reported as an
-            // overflow at the block end (top[7] within the margin), if it matters at all
-            if (x > top[kTopSlots - 1]) {
-                record_store_g(rec_base + slot * (4 * kRecords), v);
-                gid[slot * kRecords] = (uint16_t)gran;
-                topn_insert<kTopSlots>(top, x);
-                thr = select_kth(top, kidx) - margin;
+            record_store_g(rec_base + slot * (4 * kRecords), v);
+            gid[slot * kRecords] = (uint16_t)gran;
+            topn_insert<kTopSlots>(top, x);
+            // Lower bound on the ROW's k-th largest granule maximum: the thread's own k-th, or what the thread that
+            // owns the other column half has published (its values only grow, so a stale read is still a bound);
+            // for k = 5 also the 3 + 2 splits.  Halves the trigger rate of the second half of a row block.
+            float kth;
+            const float4 o = *partner;
+            if (KSTATIC == 5) {
+                kth = fmaxf(fmaxf(top[4], o.z), fmaxf(fminf(top[2], o.x), fminf(top[1], o.y)));
+                *pub = make_float4(top[1], top[2], top[4], 0.f);
+            } else {
+                kth = fmaxf(select_kth(top, kidx), o.z);
+                *pub = make_float4(0.f, 0.f, select_kth(top, kidx), 0.f);
             }
+            thr = fmaxf(kth - margin, top[kTopSlots - 1]);
         }
     }
 }
@@ -410,6 +421,7 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
     if (warp < kEpiWarps) {
         // ---------------------------------- EPILOGUE --------------------------------------------
         constexpr int NS = (RT == 4) ? 2 : 1;       // row tiles (state sets) per thread
+        constexpr int NLIST = (MODE == MODE_TOPK) ? kTopSlots : NTOP;   // TOPK: NTOP is the static k (5) or 8 = runtime k
         const int quarter = warp & 3;               // TMEM lane quarter
         const int half    = (warp >> 2) & 1;        // columns [64*half, 64*half + 64) of every tile
         const int pair    = warp >> 3;              // serves accumulator slots pair and pair + 2
@@ -439,11 +451,16 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
         const int kidx = min(max(p.topk, 1), kTopSlots) - 1;
         uint4* topk_rec = static_cast<uint4*>(p.topk_scratch) + (size_t)blockIdx.x * (kTopkScratchPerCta / 16) + rec0;
         uint16_t* topk_gid = reinterpret_cast<uint16_t*>(smem + kOffSlots) + rec0;    // [slot][1024 records]
+        if (MODE == MODE_TOPK) {      // published bounds (kOffState): nothing known yet
+#pragma unroll
+            for (int ss = 0; ss < NS; ++ss) state[ss * 512 + rec0] = make_float4(-3.0e38f, -3.0e38f, -3.0e38f, 0.f);
+            named_bar_sync((RT == 1) ? 1 : 1 + pair, (RT == 1) ? 512 : 256);
+        }
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
             const int blk = (MODE == MODE_COLLECT) ? item / ksplit : item;
             const int cbeg = (MODE == MODE_COLLECT) ? (item - blk * ksplit) * cps : 0;
             const int cend = min(nchunks, cbeg + cps);
-            RowState<NTOP> st[NS];
+            RowState<NLIST> st[NS];
             // which row a state set belongs to: needed inside the chunk loop only by COLLECT / DUMP; ARGMAX / THRESH
             // work it out after the loop so that it does not hold registers through it
             auto locate = [&](int ss) {
@@ -459,7 +476,7 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                 st[ss].m1 = st[ss].m2 = st[ss].m3 = st[ss].thr = -INFINITY;
                 st[ss].best_chunk = st[ss].chunk2 = 0;
 #pragma unroll
-                for (int i = 0; i < NTOP; ++i)   // TOPK: finite sentinels carrying the slot ids 0..7 in their low bits
+                for (int i = 0; i < NLIST; ++i)  // TOPK: finite sentinels carrying the slot ids 0..7 in their low bits
                     st[ss].top[i] = (MODE == MODE_TOPK) ? __int_as_float((int)((0xFF61B1E0u & ~7u) | (unsigned)i)) : -INFINITY;
                 st[ss].T = INFINITY;
                 if (MODE == MODE_COLLECT && st[ss].valid) st[ss].T = p.best_val[st[ss].row] - margin;
@@ -483,21 +500,24 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                     // both granules are in registers: hand the accumulator back before reducing them
                     tc_fence_before();
                     __syncwarp();
-                    if (is_lane0) mbar_arrive_addr(empty_addr[si]);
+                    if (is_lane0) mbar_arrive_relaxed_addr(empty_addr[si]);
                     if (DBG && tracing && si == 0 && uses[0] <= 512) p.trace[(uses[0] - 1) * 8 + 3] = clock64();
                     if (DBG && (p.debug_flags & 1)) continue;    // timing experiment: no epilogue work
                     if (MODE == MODE_ARGMAX) {
-                        consume_argmax64<NTOP>(va, vb, c * 4 + half2, st[ss], margin, slots, ss * 512 + rec0);
+                        consume_argmax64<NLIST>(va, vb, c * 4 + half2, st[ss], margin, slots, ss * 512 + rec0);
                     } else if (MODE == MODE_TOPK) {
-                        if constexpr (NTOP == kTopSlots) {
-                            consume_topk(va, c * 4 + half2, st[ss].top, st[ss].thr, kidx, margin_k,
-                                         topk_rec + ss * 512, topk_gid + ss * 512);
-                            consume_topk(vb, c * 4 + half2 + 1, st[ss].top, st[ss].thr, kidx, margin_k,
-                                         topk_rec + ss * 512, topk_gid + ss * 512);
+                        if constexpr (NLIST == kTopSlots) {
+                            constexpr int KS = (NTOP == 5) ? 5 : 0;
+                            consume_topk<KS>(va, c * 4 + half2, st[ss].top, st[ss].thr, kidx, margin_k,
+                                             topk_rec + ss * 512, topk_gid + ss * 512, state + ss * 512 + rec0,
+                                             state + ss * 512 + (rec0 ^ 128));
+                            consume_topk<KS>(vb, c * 4 + half2 + 1, st[ss].top, st[ss].thr, kidx, margin_k,
+                                             topk_rec + ss * 512, topk_gid + ss * 512, state + ss * 512 + rec0,
+                                             state + ss * 512 + (rec0 ^ 128));
                         }
                     } else {
-                        consume<MODE, NTOP>(va, c * 4 + half2, st[ss], margin, p, slots, ss * 512 + rec0);
-                        consume<MODE, NTOP>(vb, c * 4 + half2 + 1, st[ss], margin, p, slots, ss * 512 + rec0);
+                        consume<MODE, NTOP, NLIST>(va, c * 4 + half2, st[ss], margin, p, slots, ss * 512 + rec0);
+                        consume<MODE, NTOP, NLIST>(vb, c * 4 + half2 + 1, st[ss], margin, p, slots, ss * 512 + rec0);
                     }
                     if (DBG && tracing && si == 0 && uses[0] <= 512) p.trace[(uses[0] - 1) * 8 + 4] = clock64();
                 }
@@ -596,7 +616,7 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                 }
                 named_bar_sync(bar_id, bar_n);
             } else if (MODE == MODE_TOPK) {
-                if constexpr (NTOP == kTopSlots) {
+                if constexpr (NLIST == kTopSlots) {
                 float* tl = reinterpret_cast<float*>(smem + kOffSlots + 2 * kTopSlots * kRecords);   // [record][8], after the ids
 #pragma unroll
                 for (int ss = 0; ss < NS; ++ss) {
@@ -619,10 +639,10 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                                 if (w2 == warp) continue;
                                 const float4* o4 = reinterpret_cast<const float4*>(tl + (ss * 512 + w2 * 32 + lane) * 8);
                                 const float4 oa = o4[0], ob = o4[1];
-                                topn_insert<NTOP>(st[ss].top, oa.x); topn_insert<NTOP>(st[ss].top, oa.y);
-                                topn_insert<NTOP>(st[ss].top, oa.z); topn_insert<NTOP>(st[ss].top, oa.w);
-                                topn_insert<NTOP>(st[ss].top, ob.x); topn_insert<NTOP>(st[ss].top, ob.y);
-                                topn_insert<NTOP>(st[ss].top, ob.z); topn_insert<NTOP>(st[ss].top, ob.w);
+                                topn_insert<NLIST>(st[ss].top, oa.x); topn_insert<NLIST>(st[ss].top, oa.y);
+                                topn_insert<NLIST>(st[ss].top, oa.z); topn_insert<NLIST>(st[ss].top, oa.w);
+                                topn_insert<NLIST>(st[ss].top, ob.x); topn_insert<NLIST>(st[ss].top, ob.y);
+                                topn_insert<NLIST>(st[ss].top, ob.z); topn_insert<NLIST>(st[ss].top, ob.w);
                             }
                         const float kth = select_kth(st[ss].top, kidx);
                         const float thrG = kth - margin_k;
@@ -650,8 +670,10 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                                 }
                             if (nw > p.cand_cap || nw < p.topk) over = true;
                             if (!over) p.cand_cnt[st[ss].row] = nw;
+                            // overflow rows (rare) get their list from a COLLECT pass over `over_rows`: the k-th largest
+                            // TRACKED granule maximum is still a lower bound on the row's k-th largest score
+                            else p.best_val[st[ss].row] = (kth > -1.0e37f) ? kth - (margin_k - margin) : -INFINITY;
                         }
-                        // overflow rows (rare) get their list from a THRESH + COLLECT pass over `over_rows`
                         const bool ov = st[ss].valid && over;
                         const unsigned oall = __ballot_sync(0xffffffffu, ov);
                         if (oall) {
@@ -662,6 +684,10 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                         }
                     }
                 }
+                // the next row block starts with no published bounds (reset before the barrier: the thread of the other
+                // column half must not see this block's values)
+#pragma unroll
+                for (int ss = 0; ss < NS; ++ss) state[ss * 512 + rec0] = make_float4(-3.0e38f, -3.0e38f, -3.0e38f, 0.f);
                 named_bar_sync(bar_id, bar_n);
                 }
             } else if (MODE == MODE_THRESH) {
@@ -682,7 +708,7 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                                 if (w2 == warp) continue;
 #pragma unroll
                                 for (int i = 0; i < NTOP; ++i)
-                                    topn_insert<NTOP>(st[ss].top, tl[(ss * 512 + w2 * 32 + lane) * 8 + i]);
+                                    topn_insert<NLIST>(st[ss].top, tl[(ss * 512 + w2 * 32 + lane) * 8 + i]);
                             }
                         if (st[ss].valid) {
                             float kth = st[ss].top[0];
@@ -920,7 +946,8 @@ int coarse_row_tiles(int d, int64_t nrows, int num_sms) {
 
 cudaError_t launch_coarse(const CoarseParams& p, int mode, int row_tiles, int num_sms, cudaStream_t stream) {
     // NTOP only matters in THRESH mode (size of the per-row top list): 5 covers MedTok's k = 5
-    const int ntop = ((mode == MODE_THRESH && p.topk > 5) || mode == MODE_TOPK) ? 8 : 5;
+    // THRESH: size of the per-row top list (5 covers MedTok's k = 5).  TOPK: 5 = k is exactly 5 (static), 8 = runtime k.
+    const int ntop = mode == MODE_TOPK ? (p.topk == 5 ? 5 : 8) : ((mode == MODE_THRESH && p.topk > 5) ? 8 : 5);
     if (mode == MODE_TOPK && (num_sms > kTopkMaxCtas || p.topk_scratch == nullptr)) return cudaErrorInvalidValue;
     // timing knobs / pipeline trace live in a separate instantiation so that the production kernels carry none of it
     const bool dbg = (mode == MODE_ARGMAX) && (p.trace != nullptr || p.debug_flags != 0);
@@ -935,6 +962,7 @@ cudaError_t launch_coarse(const CoarseParams& p, int mode, int row_tiles, int nu
     MTVQ_CASE(RT_, MODE_DUMP, 5)    \
     MTVQ_CASE(RT_, MODE_THRESH, 5)  \
     MTVQ_CASE(RT_, MODE_THRESH, 8)  \
+    MTVQ_CASE(RT_, MODE_TOPK, 5)    \
     MTVQ_CASE(RT_, MODE_TOPK, 8)
     MTVQ_MODES(1)
     MTVQ_MODES(2)

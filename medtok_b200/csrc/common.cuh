@@ -224,6 +224,12 @@ __device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity, u
 __device__ __forceinline__ void mbar_arrive_addr(uint32_t addr) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
 }
+// Arrive without release semantics: for barriers that only hand a tensor-memory slot back (the tcgen05 fences order
+// the TMEM accesses).  A releasing arrive first waits for the thread's outstanding global stores to be performed --
+// an L2 round trip on the slot loop's critical path whenever the epilogue has just written records to global memory.
+__device__ __forceinline__ void mbar_arrive_relaxed_addr(uint32_t addr) {
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
 
 // 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {

@@ -216,6 +216,8 @@ __global__ void __launch_bounds__(kSoftWarps * 32) soft_resolve_kernel(
                 }
             } else { sv[t] = INFINITY; si[t] = 0; }
         }
+        // single batch everywhere in the warp (the normal case): the top-k rows are still in the groups' tiles
+        const bool all_in_tile = __all_sync(0xffffffffu, !active || cnt <= 8);
         if (!active) continue;                                // (no warp-level primitive below this point)
         // softmax(-vals): exp(x - max) / sum with max = -vals[0]
         float wgt[KT];
@@ -235,22 +237,29 @@ __global__ void __launch_bounds__(kSoftWarps * 32) soft_resolve_kernel(
             val_out[row * topk + g] = v;
             wts_out[row * topk + g] = wv;
         }
-        // zq = sum_j w_j * cn[idx_j] (products, then a sequential sum over j); out = x + (zq - x).  With a single batch
-        // (<= 8 candidates, the normal case) the top-k rows are still in the group's tile.
-        const bool in_tile = cnt <= 8;
+        // zq = sum_j w_j * cn[idx_j] (products, then a sequential sum over j); out = x + (zq - x)
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
             const int f = g + 8 * q;
             if (f < nv) {
                 float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (all_in_tile) {                            // warp-uniform
 #pragma unroll
-                for (int t = 0; t < KT; ++t)
-                    if (t < topk) {
-                        const float4 c = in_tile ? *reinterpret_cast<const float4*>(tile + max(sl[t], 0) * ds + 4 * f)
-                                                 : __ldg(cn4 + (size_t)min(si[t], k - 1) * nv + f);
-                        a.x = __fadd_rn(a.x, __fmul_rn(wgt[t], c.x)); a.y = __fadd_rn(a.y, __fmul_rn(wgt[t], c.y));
-                        a.z = __fadd_rn(a.z, __fmul_rn(wgt[t], c.z)); a.w = __fadd_rn(a.w, __fmul_rn(wgt[t], c.w));
-                    }
+                    for (int t = 0; t < KT; ++t)
+                        if (t < topk) {
+                            const float4 c = *reinterpret_cast<const float4*>(tile + sl[t] * ds + 4 * f);
+                            a.x = __fadd_rn(a.x, __fmul_rn(wgt[t], c.x)); a.y = __fadd_rn(a.y, __fmul_rn(wgt[t], c.y));
+                            a.z = __fadd_rn(a.z, __fmul_rn(wgt[t], c.z)); a.w = __fadd_rn(a.w, __fmul_rn(wgt[t], c.w));
+                        }
+                } else {
+#pragma unroll
+                    for (int t = 0; t < KT; ++t)
+                        if (t < topk) {
+                            const float4 c = __ldg(cn4 + (size_t)min(si[t], k - 1) * nv + f);
+                            a.x = __fadd_rn(a.x, __fmul_rn(wgt[t], c.x)); a.y = __fadd_rn(a.y, __fmul_rn(wgt[t], c.y));
+                            a.z = __fadd_rn(a.z, __fmul_rn(wgt[t], c.z)); a.w = __fadd_rn(a.w, __fmul_rn(wgt[t], c.w));
+                        }
+                }
                 const float4 xv = xr[q];
                 const float4 df = make_float4(__fsub_rn(a.x, xv.x), __fsub_rn(a.y, xv.y), __fsub_rn(a.z, xv.z),
                                               __fsub_rn(a.w, xv.w));
