@@ -317,7 +317,10 @@ int mtvq_soft_forward(const float* x, int64_t n, int d, const float* codes, int 
         MTVQ_CUDA(launch_coarse(c, MODE_COLLECT, rt, di.num_sms, st), "coarse collect");
     } else {
         p.over_rows = ws.flag_rows;
+        if (g_ev_before) cudaEventRecord(g_ev_before, st);
         MTVQ_CUDA(launch_coarse(p, MODE_TOPK, rt, di.num_sms, st), "coarse topk");
+        if (g_ev_after) cudaEventRecord(g_ev_after, st);
+        g_ev_before = g_ev_after = nullptr;
         CoarseParams c = p;
         c.row_list = ws.flag_rows;
         c.n_rows_dev = ws.counters + CNT_OVER;

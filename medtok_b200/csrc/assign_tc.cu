@@ -338,6 +338,7 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
     const int tile_b    = (nplanes + 2) * kPlaneBytes;   // one codebook tile in the global image
     const int nchunks   = p.kpad / kTileCodes;
     const int64_t nrows = p.n_rows_dev ? (int64_t)(*p.n_rows_dev) : p.n;
+    if (nrows <= 0) return;                               // (whole grid: a device-side row list is usually empty)
     const int rows_blk  = RT * kTileRows;
     const int nblocks   = (int)((nrows + rows_blk - 1) / rows_blk);
     // the 64 KB A area holds nreg = 4, 2 or 1 row tiles (D <= 64, <= 128, <= 256); they form a ring over
