@@ -94,6 +94,19 @@ MTVQ_API int mtvq_ema_finalize(float *weight, float *cluster_size, const double 
                       double beta, double decay, int update_cluster_size, int update_weight,
                       float *loss, void *stream);
 
+/* mtvq_ema_finalize fused with the cross-GPU exchange of the statistics (replaces the all-reduces of
+ * norm_ema_quantizer.py:188,195,203 AND the update :197-210 with ONE kernel per rank).  peer_stats / peer_flags are
+ * DEVICE arrays of `world` pointers: peer_stats[r] = rank r's packed statistics of this step (mtvq_hard_forward with
+ * MTVQ_F_SKIP_FINALIZE), peer_flags[r] = rank r's flag array (>= world uint32, zero before the first step), both mapped
+ * into this process (CUDA IPC / symmetric memory over NVLink).  `epoch` must grow by one per call and be the same on
+ * every rank; the caller alternates between two statistics buffers (epoch parity) so that a rank running ahead never
+ * overwrites what a peer still reads.  The kernel signals "rank's statistics complete" with one releasing system-scope
+ * store per peer, waits for all peers, and sums the partial statistics in rank order in fp64, so every rank ends up
+ * with bit-identical weight / cluster_size.  loss (may be NULL) receives beta * sum(sse) / (sum(rows) * d). */
+MTVQ_API int mtvq_ema_finalize_peers(float *weight, float *cluster_size, const void *const *peer_stats,
+                            void *const *peer_flags, int world, int rank, unsigned epoch, int k, int d, double beta,
+                            double decay, int update_cluster_size, int update_weight, float *loss, void *stream);
+
 /* Pieces of the forward, exposed for tests, k-means and the lookup-only VectorQuantizer
  * (norm_ema_quantizer.py:222-268). */
 

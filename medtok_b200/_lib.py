@@ -35,6 +35,8 @@ _SIGNATURES = {
     "mtvq_hard_forward": (_int, [_vp, _i64, _int, _int, _vp, _int, _vp, _dbl, _dbl, ctypes.c_uint,
                                  _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mtvq_ema_finalize": (_int, [_vp, _vp, _vp, _int, _int, _dbl, _dbl, _int, _int, _vp, _vp]),
+    "mtvq_ema_finalize_peers": (_int, [_vp, _vp, _vp, _vp, _int, _int, ctypes.c_uint, _int, _int, _dbl, _dbl, _int, _int,
+                                       _vp, _vp]),
     "mtvq_hard_assign": (_int, [_vp, _i64, _int, _int, _vp, _int, _vp, _vp, _vp, _sz, _vp]),
     "mtvq_hard_assign_exact": (_int, [_vp, _i64, _int, _int, _vp, _int, _vp, _vp, _vp, _sz, _vp]),
     "mtvq_gather_ste": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _vp, _vp, _vp]),

@@ -209,6 +209,21 @@ int mtvq_ema_finalize(float* weight, float* cluster_size, const double* stats, i
     return 0;
 }
 
+int mtvq_ema_finalize_peers(float* weight, float* cluster_size, const void* const* peer_stats, void* const* peer_flags,
+                            int world, int rank, unsigned epoch, int k, int d, double beta, double decay,
+                            int update_cluster_size, int update_weight, float* loss, void* stream) {
+    if (int r = check_dims(0, d, k)) return r;
+    if (!peer_stats || !peer_flags || (update_weight && !weight) || (update_cluster_size && !cluster_size))
+        return fail(MTVQ_ERR_BAD_ARG, "null pointer%s", "");
+    if (world < 1 || world > 64 || rank < 0 || rank >= world) return fail(MTVQ_ERR_BAD_ARG, "bad world / rank%s", "");
+    DeviceInfo di;
+    if (int r = device_info(&di)) return r;
+    MTVQ_CUDA(launch_ema_finalize_peers(weight, cluster_size, peer_stats, peer_flags, world, rank, epoch, k, d, beta, decay,
+                                        update_cluster_size, update_weight, loss, static_cast<cudaStream_t>(stream)),
+              "ema_finalize_peers");
+    return 0;
+}
+
 int mtvq_hard_forward(const float* z, int64_t n, int d, int norm_mode, float* weight, int k, float* cluster_size,
                       double beta, double decay, unsigned flags, float* z_q, int64_t* idx, float* loss, double* stats,
                       void* workspace, size_t workspace_bytes, void* stream) {

@@ -388,25 +388,70 @@ __global__ void __launch_bounds__(256) sorted_rows_kernel(const float* __restric
 // ------------------------------------------------------------------------------------------------
 constexpr int kEmaCodes = 32;   // codes per CTA
 
+// Cross-GPU exchange fused into the finalize (multi-GPU data parallel, norm_ema_quantizer.py:188,195,203): every
+// rank's packed statistics live in peer-mapped memory; a rank announces "my statistics of step `epoch` are complete" by
+// writing the epoch into its slot of every peer's flag array (one releasing system-scope store per peer over NVLink),
+// waits until all its own slots carry the epoch, and then reads the W partial statistics straight out of the peers'
+// memory, adding them in RANK ORDER in fp64 -- so every rank computes bit-identical sums and the replicas stay
+// identical without a broadcast.  One kernel instead of all-reduce + finalize; the statistics buffers alternate between
+// two copies (epoch parity) so that a rank that runs ahead cannot overwrite what a slower peer is still reading.
+struct PeerTable {
+    const double* const* stats;   // [world] peer-mapped statistics buffers of this epoch's parity
+    unsigned* const*     flags;   // [world] peer-mapped flag arrays, flags[r][q] = last epoch rank q announced to rank r
+    int world, rank;
+    unsigned epoch;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <bool PEERS>
 __global__ void __launch_bounds__(128) ema_finalize_kernel(float* __restrict__ weight, float* __restrict__ cluster_size,
-                                                            const double* __restrict__ stats, int k, int d, float beta,
-                                                            float decay, float alpha, int update_cs, int update_w,
-                                                            float* __restrict__ loss) {
+                                                            const double* __restrict__ stats, PeerTable pt, int k, int d,
+                                                            float beta, float decay, float alpha, int update_cs,
+                                                            int update_w, float* __restrict__ loss) {
     // tile[c][i] (row stride d + 1: conflict-free when 32 threads walk 32 different rows) holds, per code,
     // first the per-code mean e = fl(fl32(sum) / bins) (or the old row of a dead code), then the updated row
     extern __shared__ float tile[];
     float* wold = tile + kEmaCodes * (d + 1);
+    __shared__ double bins_s[kEmaCodes];
     const int code0 = blockIdx.x * kEmaCodes;
+    if (PEERS) {
+        if (threadIdx.x < pt.world) {
+            if (blockIdx.x == 0) {
+                __threadfence_system();
+                st_release_sys(pt.flags[threadIdx.x] + pt.rank, pt.epoch);
+            }
+            const unsigned* mine = pt.flags[pt.rank] + threadIdx.x;
+            while ((int)(ld_acquire_sys(mine) - pt.epoch) < 0) __nanosleep(200);
+        }
+        __syncthreads();
+    }
+    // one statistic, summed over the ranks in rank order (PEERS) or read from the local / all-reduced buffer
+    auto stat = [&](size_t i) -> double {
+        if (!PEERS) return stats[i];
+        double s = 0.0;
+        for (int r = 0; r < pt.world; ++r) s += __ldcv(pt.stats[r] + i);
+        return s;
+    };
     if (blockIdx.x == 0 && threadIdx.x == 0 && loss) {
-        const double sse = stats[(size_t)k + (size_t)k * d], rows = stats[(size_t)k + (size_t)k * d + 1];
+        const double sse = stat((size_t)k + (size_t)k * d), rows = stat((size_t)k + (size_t)k * d + 1);
         const float mse = (float)(sse / (rows * (double)d));
         *loss = __fmul_rn(beta, mse);
     }
+    if (threadIdx.x < kEmaCodes) bins_s[threadIdx.x] = code0 + threadIdx.x < k ? stat(code0 + threadIdx.x) : 0.0;
+    __syncthreads();
     if (update_cs) {   // ema_inplace: fl(cs*decay) then fma(new, alpha, .)
         const int code = code0 + threadIdx.x;
         if (threadIdx.x < kEmaCodes && code < k) {
             const float t = __fmul_rn(cluster_size[code], decay);
-            cluster_size[code] = __fmaf_rn((float)stats[code], alpha, t);
+            cluster_size[code] = __fmaf_rn((float)bins_s[threadIdx.x], alpha, t);
         }
     }
     if (!update_w) return;
@@ -418,15 +463,15 @@ __global__ void __launch_bounds__(128) ema_finalize_kernel(float* __restrict__ w
     for (int e = threadIdx.x; e < ncodes * d; e += blockDim.x) {
         const int c = e / d, i = e - c * d;
         const float wv = weight[(size_t)(code0 + c) * d + i];
-        const double bins = stats[code0 + c];
+        const double bins = bins_s[c];
         wold[c * (d + 1) + i] = wv;
         // per-code mean; a dead code keeps its row (still re-normalised below, like the reference)
-        tile[c * (d + 1) + i] = (bins == 0.0) ? wv : __fdiv_rn((float)stats[(size_t)k + (size_t)(code0 + c) * d + i], (float)bins);
+        tile[c * (d + 1) + i] = (bins == 0.0) ? wv : __fdiv_rn((float)stat((size_t)k + (size_t)(code0 + c) * d + i), (float)bins);
     }
     __syncthreads();
     if (threadIdx.x < ncodes) {
         float den = 1.0f;
-        if (stats[code0 + threadIdx.x] != 0.0) {
+        if (bins_s[threadIdx.x] != 0.0) {
             const float* e = tile + threadIdx.x * (d + 1);
             den = canon_norm_seq([&](int i) { return e[i]; }, d);   // strided (.t()) view in the reference
             den = den < kNormEps ? kNormEps : den;
@@ -437,7 +482,7 @@ __global__ void __launch_bounds__(128) ema_finalize_kernel(float* __restrict__ w
     for (int e = threadIdx.x; e < ncodes * d; e += blockDim.x) {
         const int c = e / d, i = e - c * d;
         float v = tile[c * (d + 1) + i];
-        if (stats[code0 + c] != 0.0) v = __fdiv_rn(v, den_s[c]);
+        if (bins_s[c] != 0.0) v = __fdiv_rn(v, den_s[c]);
         tile[c * (d + 1) + i] = __fmaf_rn(v, alpha, __fmul_rn(wold[c * (d + 1) + i], decay));
     }
     __syncthreads();
@@ -539,19 +584,41 @@ cudaError_t launch_sorted_rows(const float* z, const float* denom, const float* 
     return cudaGetLastError();
 }
 
+static cudaError_t ema_finalize_configure() {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(ema_finalize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(ema_finalize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    return cudaSuccess;
+}
+
 cudaError_t launch_ema_finalize(float* weight, float* cluster_size, const double* stats, int k, int d, double beta,
                                 double decay, int update_cs, int update_w, float* loss, cudaStream_t s) {
     // python: mul_(decay).add_(new, alpha=1-decay): both scalars are doubles cast to fp32
     const size_t smem = sizeof(float) * 2 * kEmaCodes * (d + 1);   // <= 65.8 KB at d = 256
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(ema_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    ema_finalize_kernel<<<(k + kEmaCodes - 1) / kEmaCodes, 128, smem, s>>>(weight, cluster_size, stats, k, d, (float)beta,
-                                                                            (float)decay, (float)(1.0 - decay), update_cs,
-                                                                            update_w, loss);
+    if (cudaError_t e = ema_finalize_configure()) return e;
+    ema_finalize_kernel<false><<<(k + kEmaCodes - 1) / kEmaCodes, 128, smem, s>>>(
+        weight, cluster_size, stats, PeerTable{}, k, d, (float)beta, (float)decay, (float)(1.0 - decay), update_cs, update_w,
+        loss);
+    ++g_kernel_launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ema_finalize_peers(float* weight, float* cluster_size, const void* const* peer_stats,
+                                      void* const* peer_flags, int world, int rank, unsigned epoch, int k, int d,
+                                      double beta, double decay, int update_cs, int update_w, float* loss, cudaStream_t s) {
+    const size_t smem = sizeof(float) * 2 * kEmaCodes * (d + 1);
+    if (cudaError_t e = ema_finalize_configure()) return e;
+    PeerTable pt;
+    pt.stats = reinterpret_cast<const double* const*>(peer_stats);
+    pt.flags = reinterpret_cast<unsigned* const*>(peer_flags);
+    pt.world = world; pt.rank = rank; pt.epoch = epoch;
+    ema_finalize_kernel<true><<<(k + kEmaCodes - 1) / kEmaCodes, 128, smem, s>>>(
+        weight, cluster_size, nullptr, pt, k, d, (float)beta, (float)decay, (float)(1.0 - decay), update_cs, update_w, loss);
     ++g_kernel_launches;
     return cudaGetLastError();
 }

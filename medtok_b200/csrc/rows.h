@@ -23,6 +23,10 @@ cudaError_t launch_sorted_rows(const float* z, const float* denom, const float* 
                                int k, float* z_q, double* stats, const Workspace& ws, int num_sms, cudaStream_t s);
 cudaError_t launch_ema_finalize(float* weight, float* cluster_size, const double* stats, int k, int d, double beta,
                                 double decay, int update_cs, int update_w, float* loss, cudaStream_t s);
+// finalize fused with the cross-GPU exchange: peer_stats / peer_flags are DEVICE arrays of `world` peer-mapped pointers
+cudaError_t launch_ema_finalize_peers(float* weight, float* cluster_size, const void* const* peer_stats,
+                                      void* const* peer_flags, int world, int rank, unsigned epoch, int k, int d,
+                                      double beta, double decay, int update_cs, int update_w, float* loss, cudaStream_t s);
 cudaError_t launch_loss(const double* stats, int k, int d, double beta, float* loss, cudaStream_t s);
 
 }  // namespace mtvq

@@ -46,3 +46,54 @@ def all_reduce_stats(stats: torch.Tensor, all_reduce_fn) -> torch.Tensor:
         raise ValueError("packed statistics must be a contiguous float64 tensor")
     all_reduce_fn(stats)
     return stats
+
+
+class PeerExchange:
+    """Peer-mapped buffers for the exchange fused into the finalize kernel (mtvq_ema_finalize_peers): two packed
+    statistics buffers per rank (alternating by step) and one flag array, allocated as torch symmetric memory so that
+    every rank holds device pointers into every peer's copy (NVLink P2P).  PyTorch only provides the mapping; the
+    signalling, the waiting and the rank-ordered fp64 sum all happen inside the one kernel.
+
+    Construction is collective (every rank of `group` must call it with the same `numel`).  Raises if symmetric
+    memory cannot be set up -- the caller then keeps the all-reduce + finalize route."""
+
+    def __init__(self, numel: int, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.numel = numel
+        try:
+            symm_mem.enable_symm_mem_for_group(group.group_name)
+        except Exception:
+            pass                                                   # newer torch enables groups lazily
+        self.stats = [symm_mem.empty(numel, dtype=torch.float64, device=device) for _ in range(2)]
+        self.flags = symm_mem.empty(64, dtype=torch.int32, device=device)
+        self._handles = [symm_mem.rendezvous(t, group) for t in (*self.stats, self.flags)]
+        tables = []
+        for t, h in zip((*self.stats, self.flags), self._handles):
+            off = int(getattr(h, "offset", 0) or 0)
+            ptrs = [int(p) + off for p in h.buffer_ptrs]
+            if len(ptrs) != self.world or ptrs[self.rank] != t.data_ptr():
+                raise RuntimeError("symmetric-memory handle does not describe the tensor it was made from")
+            tables.append(ptrs)
+        # device tables of peer pointers: [stats parity 0 | stats parity 1 | flags], `world` int64 each
+        self.table = torch.tensor(tables, dtype=torch.int64, device=device)
+        self.flags.zero_()
+        for t in self.stats:
+            t.zero_()
+        self.epoch = 0
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                                        # nobody signals before every flag array is zero
+
+    def next_buffer(self) -> torch.Tensor:
+        """Statistics buffer of the coming step (call once per step, before mtvq_hard_forward)."""
+        self.epoch += 1
+        return self.stats[self.epoch & 1]
+
+    def peer_stats_ptr(self) -> int:
+        return self.table[self.epoch & 1].data_ptr()
+
+    def peer_flags_ptr(self) -> int:
+        return self.table[2].data_ptr()

@@ -9,6 +9,8 @@ There is no CPU / PyTorch fallback: CPU tensors raise.
 """
 from __future__ import annotations
 
+import ctypes
+import os
 import sys
 
 import torch
@@ -17,7 +19,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
-from .distributed import all_reduce_stats
+from .distributed import PeerExchange, all_reduce_stats
 
 
 def l2norm(t):
@@ -232,11 +234,38 @@ class NormEMAVectorQuantizer(nn.Module):
         self.global_loss = False          # True: loss = beta * sum_ranks(sse) / (sum_ranks(rows) * D)
         self._ws = _lib.Workspace()
         self.last_stats = None            # packed fp64 statistics of the last forward (diagnostics)
+        # exchange fused into the finalize kernel over NVLink peer memory (set up at the first multi-GPU forward);
+        # False = unavailable / disabled -> one packed all-reduce + finalize
+        self.fused_exchange = os.environ.get("MEDTOK_FUSED_EXCHANGE", "1") != "0"
+        self._peers = None
 
     def reset_cluster_size(self, device):
         if self.statistic_code_usage:
             self.register_buffer('cluster_size', torch.zeros(self.num_tokens))
             self.cluster_size = self.cluster_size.to(device)
+
+    def _peer_exchange(self, dev, d, k):
+        """PeerExchange for the fused finalize, or None (-> all-reduce route).  Only for the stock binding
+        (`all_reduce_fn is torch.distributed.all_reduce` on an NCCL group); set up once, collectively."""
+        if self._peers is not None or not self.fused_exchange:
+            return self._peers or None
+        self.fused_exchange = False
+        if self.all_reduce_fn is not distributed.all_reduce or distributed.get_backend() != "nccl":
+            return None
+        ok = torch.ones(1, device=dev)
+        try:
+            peers = PeerExchange(_lib.stats_len(d, k), dev)
+        except Exception as e:                       # no P2P / symmetric memory: every rank must take the same route
+            print(f"medtok_b200: fused NVLink exchange unavailable ({type(e).__name__}: {e}); using all_reduce",
+                  file=sys.stderr)
+            peers = None
+            ok.zero_()
+        distributed.all_reduce(ok, op=distributed.ReduceOp.MIN)
+        if float(ok) == 0.0:
+            return None
+        self._peers = peers
+        self.fused_exchange = True
+        return peers
 
     # -- one forward on rows [N, D] -------------------------------------------------------------
     def _run(self, z_rows_in: torch.Tensor, norm_mode: int):
@@ -258,15 +287,24 @@ class NormEMAVectorQuantizer(nn.Module):
         z_q = torch.empty_like(z_rows)
         idx = torch.empty(n, dtype=torch.int64, device=dev)
         loss = torch.empty(1, dtype=torch.float32, device=dev)
-        stats = torch.empty(_lib.stats_len(d, k), dtype=torch.float64, device=dev)
+        upd_w = self.training and self.embedding.update
+        upd_cs = has_cs and ((not self.training) or self.embedding.update)
+        peers = self._peer_exchange(dev, d, k) if (distributed_on and (upd_w or upd_cs)) else None
+        stats = peers.next_buffer() if peers is not None else \
+            torch.empty(_lib.stats_len(d, k), dtype=torch.float64, device=dev)
         cs = self.cluster_size if has_cs else None
         _lib.check(L.mtvq_hard_forward(_lib.ptr(z_rows), n, d, norm_mode, _lib.ptr(weight), k, _lib.ptr(cs),
                                        float(self.beta), float(self.decay), flags, _lib.ptr(z_q), _lib.ptr(idx),
                                        _lib.ptr(loss), _lib.ptr(stats), _lib.ptr(ws), ws.numel(),
                                        _lib.stream_ptr(dev)), "mtvq_hard_forward")
-        if flags & _lib.F_SKIP_FINALIZE:
-            upd_w = self.training and self.embedding.update
-            upd_cs = has_cs and ((not self.training) or self.embedding.update)
+        if peers is not None:
+            # ONE kernel: signal / wait over NVLink, rank-ordered fp64 sum of the peers' statistics, EMA update
+            _lib.check(L.mtvq_ema_finalize_peers(_lib.ptr(weight), _lib.ptr(cs), ctypes.c_void_p(peers.peer_stats_ptr()),
+                                                 ctypes.c_void_p(peers.peer_flags_ptr()), peers.world, peers.rank,
+                                                 peers.epoch, k, d, float(self.beta), float(self.decay), int(upd_cs),
+                                                 int(upd_w), _lib.ptr(loss) if self.global_loss else None,
+                                                 _lib.stream_ptr(dev)), "mtvq_ema_finalize_peers")
+        elif flags & _lib.F_SKIP_FINALIZE:
             if distributed_on and (upd_w or upd_cs):
                 all_reduce_stats(stats, self.all_reduce_fn)   # ONE packed all-reduce (reference: :188 / :195 + :203)
             if upd_w or upd_cs:
