@@ -78,3 +78,52 @@ def test_shard_rows_covers_everything():
             spans = [shard_rows(n, w, r) for r in range(w)]
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+
+
+def _sweep_worker(rank, world, port, tmp, q):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from medtok_b200.tokenize_sweep import TokenSweep, compose_eval_outputs
+    n, d, k = 1003, 8, 5
+    g = torch.Generator().manual_seed(3)
+    perm = torch.randperm(n, generator=g)                      # the loader's (shuffled) order of the vocabulary
+    full = {name: torch.randn(n, d, generator=g) for name in
+            ("specific_embedding_text", "specific_embedding_graph", "shared_text_embedding", "shared_graph_embedding")}
+    for name in ("text", "graph", "shared_text", "shared_graph"):
+        full[name + "_tokens"] = torch.randint(0, 999, (n, k), generator=g)
+        full[name + "_tokens_weights"] = torch.rand(n, k, generator=g)
+    sweep = TokenSweep(n, 4 * d, k, pin=False)
+    mine = perm[rank::world]                                    # DistributedSampler-style interleaving
+    for lo in range(0, mine.numel(), 97):                       # ragged last batch
+        ci = mine[lo:lo + 97]
+        e, t, w = compose_eval_outputs({key: v[ci] for key, v in full.items()})
+        sweep.add(ci, e, t, w)
+    done = sweep.finish()
+    if done:
+        sweep.save(tmp)
+        e_all, t_all, w_all = compose_eval_outputs(full)
+        ok = (np.array_equal(np.load(os.path.join(tmp, "embeddings_all.npy")), e_all.numpy())
+              and np.array_equal(np.load(os.path.join(tmp, "tokens_all.npy")), t_all.numpy())
+              and np.array_equal(np.load(os.path.join(tmp, "weights_all.npy")), w_all.numpy()))
+        q.put(("rank0", ok, tuple(np.load(os.path.join(tmp, "tokens_all.npy")).shape)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_token_sweep_two_ranks_gloo(tmp_path):
+    """Tokenization sweep writer (inference.py:97-134): two ranks own interleaved code indices, rank 0 writes the three
+    files once, rows in vocabulary order (the reference orders by the last batch's indices only)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sweep_worker, args=(r, 2, 29747, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    tag, ok, shape = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+    assert tag == "rank0" and ok and shape == (1003, 4, 5)
