@@ -160,6 +160,16 @@ MTVQ_API int mtvq_soft_backward(const float *x, int64_t n, int d, const float *c
                        float *grad_x, float *grad_codes, void *workspace, size_t workspace_bytes,
                        void *stream);
 
+/* The whole backward of one soft quantisation in one pass (what autograd does for :196-214 in the reference): g_out =
+ * dL/d(returned z_q) [n,d] (may be NULL), g_vq / g_commit = DEVICE scalars dL/d(vq_loss), dL/d(commit_loss) (may be NULL);
+ * writes grad_x [n,d] = g_out - g_commit*beta*diff + (soft path through the weights and normalize), diff = (zq - x)*2/(n d),
+ * and ACCUMULATES the raw codebook rows' gradient into grad_codes [k,d].  zq is recomputed from idx / wts.  With
+ * training == 0 the losses are constants (:211-212): grad_x = g_out.  workspace: 4*(k*d + pad128(k)) bytes. */
+MTVQ_API int mtvq_soft_backward_fused(const float *x, int64_t n, int d, const float *codes, int k, int topk,
+                             const int64_t *idx, const float *wts, const float *g_out, const float *g_vq,
+                             const float *g_commit, double beta, int training, float *grad_x, float *grad_codes,
+                             void *workspace, size_t workspace_bytes, void *stream);
+
 /* VectorQuantizer.codebook_usage (vector_quantization_soft_one_new.py:219-236): next[cap] = the last `cap`
  * entries of concat(window[cap], float(idx[count])) and *distinct (device int) = number of distinct values in it
  * (the reference's len(torch.unique(window)); usage = distinct / n_e on the host).  window and next must not

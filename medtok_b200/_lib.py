@@ -45,6 +45,8 @@ _SIGNATURES = {
     "mtvq_codebook_usage": (_int, [_vp, _vp, _i64, _int, _int, _vp, _vp, _sz, _vp, _vp]),
     "mtvq_soft_forward": (_int, [_vp, _i64, _int, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mtvq_soft_backward": (_int, [_vp, _i64, _int, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mtvq_soft_backward_fused": (_int, [_vp, _i64, _int, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _dbl, _int, _vp, _vp,
+                                        _vp, _sz, _vp]),
     "mtvq_debug_counters": (_int, [_vp, _i64, _int, _int, _int, ctypes.POINTER(_i64), _vp]),
     "mtvq_debug_coarse_scores": (_int, [_vp, _i64, _int, _int, _vp, _int, _vp, _i64, ctypes.POINTER(_int),
                                         _vp, _sz, _vp]),

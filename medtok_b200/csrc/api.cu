@@ -361,6 +361,29 @@ int mtvq_soft_backward(const float* x, int64_t n, int d, const float* codes, int
     return 0;
 }
 
+int mtvq_soft_backward_fused(const float* x, int64_t n, int d, const float* codes, int k, int topk, const int64_t* idx,
+                             const float* wts, const float* g_out, const float* g_vq, const float* g_commit, double beta,
+                             int training, float* grad_x, float* grad_codes, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+    if (int r = check_dims(n, d, k)) return r;
+    if (topk < 1 || topk > 8) return fail(MTVQ_ERR_UNSUPPORTED, "top-k must be in [1, 8]%s", "");
+    if (!x || !codes || !idx || !wts || !grad_x || !grad_codes || !workspace) return fail(MTVQ_ERR_BAD_ARG, "null pointer%s", "");
+    if (!aligned16(x) || !aligned16(codes) || !aligned16(grad_x) || !aligned16(grad_codes) || !aligned16(workspace) ||
+        (g_out && !aligned16(g_out)))
+        return fail(MTVQ_ERR_BAD_ARG, "16-byte alignment%s", "");
+    const size_t need = sizeof(float) * ((size_t)k * d + (size_t)pad_codes(k));
+    if (workspace_bytes < need) return fail(MTVQ_ERR_WORKSPACE, "workspace too small%s: need %ld", "", (long)need);
+    DeviceInfo di;
+    if (int r = device_info(&di)) return r;
+    float* codes_n = static_cast<float*>(workspace);
+    float* norms = codes_n + (size_t)k * d;
+    if (n > 0)
+        MTVQ_CUDA(launch_soft_backward_fused(x, n, d, codes, k, topk, idx, wts, g_out, g_vq, g_commit, (float)beta, training,
+                                             grad_x, grad_codes, codes_n, norms, di.num_sms,
+                                             static_cast<cudaStream_t>(stream)), "soft_backward_fused");
+    return 0;
+}
+
 int mtvq_debug_counters(const void* workspace, int64_t n, int d, int k, int topk, int64_t* out_host, void* stream) {
     if (!workspace || !out_host) return fail(MTVQ_ERR_BAD_ARG, "null pointer%s", "");
     Workspace ws = carve(const_cast<void*>(workspace), n, d, k, topk < 1 ? 1 : topk);

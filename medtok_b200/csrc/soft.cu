@@ -548,6 +548,204 @@ cudaError_t launch_soft_resolve(const float* x, int64_t n, int d, int k, int top
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// fused backward of one soft quantisation (training step of the quantisation core): everything the autograd node owes
+//   x      <- dL/dout (straight-through)  - g_commit * beta * diff  + (I - xn xn^T)/||x|| dL/dxn
+//   W_r    <- (I - c c^T)/||W_r|| dL/dc        (atomic float4 adds into the raw codebook's gradient)
+// with diff = (zq - x) * 2/(n d), dL/dzq = g_vq * diff, zq = sum_j w_j c_j recomputed from the gathered rows (nothing of
+// the forward but idx / weights is re-read).  Eight lanes per row, four rows per warp, fp32 group reductions.
+// ------------------------------------------------------------------------------------------------
+__global__ void soft_backward_prep_kernel(const float* __restrict__ codes, int k, int d, float* __restrict__ codes_n,
+                                          float* __restrict__ norms) {
+    // one warp per code: ||W_r|| (clamped like F.normalize) and the normalised row
+    const int lane = threadIdx.x & 31;
+    const int code = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (code >= k) return;
+    float s = 0.f;
+    for (int i = lane; i < d; i += 32) { const float v = codes[(size_t)code * d + i]; s = fmaf(v, v, s); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float nrm = fmaxf(sqrtf(s), kNormEps);
+    if (lane == 0) norms[code] = nrm;
+    for (int i = lane; i < d; i += 32) codes_n[(size_t)code * d + i] = codes[(size_t)code * d + i] / nrm;
+}
+
+__device__ __forceinline__ float group_sum8(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+
+template <int NQ, int KT>
+__global__ void __launch_bounds__(256) soft_backward_fused_kernel(
+    const float* __restrict__ x, int64_t n, int d, const float* __restrict__ codes_n, const float* __restrict__ norms,
+    int k, int topk_rt, const int64_t* __restrict__ idx, const float* __restrict__ wts, const float* __restrict__ g_out,
+    const float* __restrict__ g_vq_p, const float* __restrict__ g_commit_p, float beta, int training,
+    float* __restrict__ grad_x, float* __restrict__ grad_codes) {
+    const int topk = (KT == 5) ? 5 : topk_rt;
+    const int lane = threadIdx.x & 31, grp = lane >> 3, g = lane & 7;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int nv = d >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const float4* go4 = reinterpret_cast<const float4*>(g_out);
+    const float4* cn4 = reinterpret_cast<const float4*>(codes_n);
+    const float scale = 2.0f / ((float)n * (float)d);
+    const float gvq = (training && g_vq_p) ? __ldg(g_vq_p) : 0.0f;
+    const float gcm = (training && g_commit_p) ? __ldg(g_commit_p) * beta : 0.0f;
+    const int64_t nsteps = (n + 3) >> 2;
+    for (int64_t step = warp; step < nsteps; step += nwarps) {
+        const int64_t row = step * 4 + grp;
+        const bool valid = row < n;
+        float4 xr[NQ], gx[NQ];
+        float nx2 = 0.f;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const int f = g + 8 * q;
+            const bool ok = valid && f < nv;
+            xr[q] = ok ? __ldcs(x4 + row * nv + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+            gx[q] = (ok && g_out) ? __ldcs(go4 + row * nv + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+            nx2 += dot4(xr[q], xr[q]);
+        }
+        // top-k ids / weights of the row: lane t of the group loads entry t, the group shares them
+        int my_r = 0;
+        float my_w = 0.f;
+        if (valid && g < topk) { my_r = (int)idx[row * topk + g]; my_w = wts[row * topk + g]; }
+        nx2 = group_sum8(nx2);
+        const float nx = fmaxf(sqrtf(nx2), kNormEps);
+        const float rnx = 1.0f / nx;
+        int rj[KT];
+        float wj[KT];
+        // the gathered normalised rows stay in registers (D <= 128) or are re-read from L1 / L2 in each phase (D = 256)
+        constexpr bool kKeep = NQ <= 4;
+        float4 creg[kKeep ? KT : 1][kKeep ? NQ : 1];
+#pragma unroll
+        for (int t = 0; t < KT; ++t) {
+            rj[t] = __shfl_sync(0xffffffffu, my_r, t, 8);
+            wj[t] = __shfl_sync(0xffffffffu, my_w, t, 8);
+            if (t >= topk) wj[t] = 0.f;
+            rj[t] = min(max(rj[t], 0), k - 1);
+        }
+        auto ldc = [&](int t, int q) -> float4 {
+            const int f = g + 8 * q;
+            return (valid && t < topk && f < nv) ? __ldg(cn4 + (size_t)rj[t] * nv + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        if constexpr (kKeep) {
+#pragma unroll
+            for (int t = 0; t < KT; ++t)
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) creg[t][q] = ldc(t, q);
+        }
+#define MTVQ_C(t, q) (kKeep ? creg[kKeep ? (t) : 0][kKeep ? (q) : 0] : ldc((t), (q)))
+        // zq, diff, dL/dzq; a_j = dL/dzq . c_j
+        float4 gz[NQ];
+        float a[KT];
+#pragma unroll
+        for (int t = 0; t < KT; ++t) a[t] = 0.f;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            float4 zq = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int t = 0; t < KT; ++t) {
+                const float4 cq = MTVQ_C(t, q);
+                zq.x += wj[t] * cq.x; zq.y += wj[t] * cq.y; zq.z += wj[t] * cq.z; zq.w += wj[t] * cq.w;
+            }
+            const float4 df = make_float4((zq.x - xr[q].x) * scale, (zq.y - xr[q].y) * scale, (zq.z - xr[q].z) * scale,
+                                          (zq.w - xr[q].w) * scale);
+            gz[q] = make_float4(gvq * df.x, gvq * df.y, gvq * df.z, gvq * df.w);
+            gx[q].x -= gcm * df.x; gx[q].y -= gcm * df.y; gx[q].z -= gcm * df.z; gx[q].w -= gcm * df.w;
+#pragma unroll
+            for (int t = 0; t < KT; ++t) a[t] += dot4(gz[q], MTVQ_C(t, q));
+        }
+        float sdot = 0.f;
+#pragma unroll
+        for (int t = 0; t < KT; ++t) { a[t] = group_sum8(a[t]); sdot += wj[t] * a[t]; }
+        float h[KT];
+#pragma unroll
+        for (int t = 0; t < KT; ++t) h[t] = -wj[t] * (a[t] - sdot);
+        // dL/dxn and the codebook rows' gradients
+        float px = 0.f;
+        float4 gxn[NQ];
+        float proj[KT];
+#pragma unroll
+        for (int t = 0; t < KT; ++t) proj[t] = 0.f;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const float4 xn = make_float4(xr[q].x * rnx, xr[q].y * rnx, xr[q].z * rnx, xr[q].w * rnx);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int t = 0; t < KT; ++t) {
+                const float4 cq = MTVQ_C(t, q);
+                acc.x += h[t] * (2.f * xn.x - 2.f * cq.x); acc.y += h[t] * (2.f * xn.y - 2.f * cq.y);
+                acc.z += h[t] * (2.f * xn.z - 2.f * cq.z); acc.w += h[t] * (2.f * xn.w - 2.f * cq.w);
+                // dL/dc_j (kept in place of c_j . dL/dc_j accumulation first)
+                const float4 gc = make_float4(wj[t] * gz[q].x + h[t] * (2.f * cq.x - 2.f * xn.x),
+                                              wj[t] * gz[q].y + h[t] * (2.f * cq.y - 2.f * xn.y),
+                                              wj[t] * gz[q].z + h[t] * (2.f * cq.z - 2.f * xn.z),
+                                              wj[t] * gz[q].w + h[t] * (2.f * cq.w - 2.f * xn.w));
+                proj[t] += dot4(gc, cq);
+            }
+            gxn[q] = acc;
+            px += dot4(acc, xn);
+        }
+        px = group_sum8(px);
+#pragma unroll
+        for (int t = 0; t < KT; ++t) proj[t] = group_sum8(proj[t]);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const int f = g + 8 * q;
+            const bool live = valid && f < nv;
+            const float4 xn = make_float4(xr[q].x * rnx, xr[q].y * rnx, xr[q].z * rnx, xr[q].w * rnx);
+            if (live) __stcs(reinterpret_cast<float4*>(grad_x) + row * nv + f,
+                   make_float4(gx[q].x + (gxn[q].x - xn.x * px) * rnx, gx[q].y + (gxn[q].y - xn.y * px) * rnx,
+                               gx[q].z + (gxn[q].z - xn.z * px) * rnx, gx[q].w + (gxn[q].w - xn.w * px) * rnx));
+            if (training && live) {
+#pragma unroll
+                for (int t = 0; t < KT; ++t) {
+                    if (t < topk) {
+                    const float4 cq = MTVQ_C(t, q);
+                    const float rn = 1.0f / __ldg(norms + rj[t]);
+                    const float4 gc = make_float4(wj[t] * gz[q].x + h[t] * (2.f * cq.x - 2.f * xn.x),
+                                                  wj[t] * gz[q].y + h[t] * (2.f * cq.y - 2.f * xn.y),
+                                                  wj[t] * gz[q].z + h[t] * (2.f * cq.z - 2.f * xn.z),
+                                                  wj[t] * gz[q].w + h[t] * (2.f * cq.w - 2.f * xn.w));
+                    atomicAdd(reinterpret_cast<float4*>(grad_codes) + (size_t)rj[t] * nv + f,
+                              make_float4((gc.x - cq.x * proj[t]) * rn, (gc.y - cq.y * proj[t]) * rn,
+                                          (gc.z - cq.z * proj[t]) * rn, (gc.w - cq.w * proj[t]) * rn));
+                    }
+                }
+            }
+        }
+    }
+#undef MTVQ_C
+}
+
+cudaError_t launch_soft_backward_fused(const float* x, int64_t n, int d, const float* codes, int k, int topk,
+                                       const int64_t* idx, const float* wts, const float* g_out, const float* g_vq,
+                                       const float* g_commit, float beta, int training, float* grad_x, float* grad_codes,
+                                       float* codes_n, float* norms, int num_sms, cudaStream_t stream) {
+    soft_backward_prep_kernel<<<(k * 32 + 255) / 256, 256, 0, stream>>>(codes, k, d, codes_n, norms);
+    ++g_kernel_launches;
+    int64_t blocks = ((n + 3) / 4 + 7) / 8;
+    if (blocks > (int64_t)num_sms * 8) blocks = (int64_t)num_sms * 8;
+    if (blocks < 1) blocks = 1;
+#define MTVQ_BWD_ARGS x, n, d, codes_n, norms, k, topk, idx, wts, g_out, g_vq, g_commit, beta, training, grad_x, grad_codes
+#define MTVQ_BWD_LAUNCH(NQ_)                                                                                  \
+    do {                                                                                                      \
+        if (topk == 5) soft_backward_fused_kernel<NQ_, 5><<<(int)blocks, 256, 0, stream>>>(MTVQ_BWD_ARGS);    \
+        else           soft_backward_fused_kernel<NQ_, 8><<<(int)blocks, 256, 0, stream>>>(MTVQ_BWD_ARGS);    \
+    } while (0)
+    if (d <= 64)       MTVQ_BWD_LAUNCH(2);
+    else if (d <= 128) MTVQ_BWD_LAUNCH(4);
+    else               MTVQ_BWD_LAUNCH(8);
+#undef MTVQ_BWD_LAUNCH
+#undef MTVQ_BWD_ARGS
+    ++g_kernel_launches;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_soft_backward(const float* x, int64_t n, int d, const float* codes, int k, int topk,
                                  const int64_t* idx, const float* wts, const float* g_zq, float* grad_x,
                                  float* grad_codes, int num_sms, cudaStream_t stream) {

@@ -91,26 +91,28 @@ class _SoftQuantizeFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_out, g_vq, g_commit, _gi, _gw):
+        """One fused kernel (mtvq_soft_backward_fused): straight-through + commitment term + the path through the
+        softmax weights and F.normalize for x, and the gathered rows' gradient for the raw table (atomic adds)."""
         x32, codes, idx, wts, zq = ctx.saved_tensors
         lo, hi, topk, beta, training, tshape, tdtype, xdtype = ctx.meta
         n, d = x32.shape
         k = codes.shape[0]
         dev = x32.device
-        grad_x = torch.zeros_like(x32) if g_out is None else g_out.float().clone()      # straight-through
+        grad_x = torch.empty_like(x32)
         grad_table = torch.zeros(tshape, dtype=torch.float32, device=dev)
-        if training:
-            diff = (zq - x32) * (2.0 / float(n * d))
-            if g_commit is not None:
-                grad_x -= (g_commit * beta) * diff                                        # d commit / d x
-            if g_vq is not None:
-                g_zq = (g_vq * diff).contiguous()                                         # d vq / d zq
-                gx_soft = torch.empty_like(x32)
-                gslice = grad_table[lo:hi]
-                _lib.check(_lib.lib().mtvq_soft_backward(_lib.ptr(x32), n, d, _lib.ptr(codes), k, topk,
-                                                         _lib.ptr(idx), _lib.ptr(wts), _lib.ptr(g_zq),
-                                                         _lib.ptr(gx_soft), _lib.ptr(gslice), None, 0,
-                                                         _lib.stream_ptr(dev)), "mtvq_soft_backward")
-                grad_x += gx_soft
+        gslice = grad_table[lo:hi]
+
+        def dev_scalar(g):
+            return None if g is None else g.detach().float().reshape(1).contiguous()
+
+        go = None if g_out is None else g_out.detach().float().contiguous()
+        gv, gc = dev_scalar(g_vq), dev_scalar(g_commit)
+        scratch = torch.empty(k * d + ((k + 127) // 128) * 128, dtype=torch.float32, device=dev)
+        _lib.check(_lib.lib().mtvq_soft_backward_fused(_lib.ptr(x32), n, d, _lib.ptr(codes), k, topk, _lib.ptr(idx),
+                                                       _lib.ptr(wts), _lib.ptr(go), _lib.ptr(gv), _lib.ptr(gc), float(beta),
+                                                       int(bool(training)), _lib.ptr(grad_x), _lib.ptr(gslice),
+                                                       _lib.ptr(scratch), scratch.numel() * 4, _lib.stream_ptr(dev)),
+                   "mtvq_soft_backward_fused")
         return grad_x.to(xdtype), grad_table.to(tdtype), None, None, None, None, None, None
 
 

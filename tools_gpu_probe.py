@@ -308,3 +308,33 @@ if what == "softkernels":
     out["soft_kernels"] = [{"name": r[0], "us_per_call": r[1], "launches_per_call": r[2]} for r in rows]
     out["soft_counters"] = cnt
     json.dump(out, open("gpurun_out/probe_softkernels.json", "w"), indent=1)
+
+if what == "softbwd":
+    # soft-one forward + backward (training step of the quantisation core) at the C3 shape
+    from torch.profiler import profile, ProfilerActivity
+    from medtok_b200.vector_quantization_soft_one_new import _SoftQuantizeFn
+    n, d, k, kk = int(os.environ.get("PROBE_N", str(1 << 20))), int(os.environ.get("PROBE_D", "128")), int(os.environ.get("PROBE_K", "16384")), 5
+    torch.manual_seed(0)
+    x = torch.randn(n, d, device=dev, requires_grad=True)
+    table = torch.randn(k, d, device=dev, requires_grad=True)
+    wsx = _lib.Workspace()
+    def step():
+        out, vq, commit, idx, wts = _SoftQuantizeFn.apply(x, table, 0, k, kk, 0.25, True, wsx)
+        (out.sum() * 1e-3 + vq + commit).backward()
+        x.grad = None; table.grad = None
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+    rows = []
+    for e in prof.key_averages():
+        t = getattr(e, "device_time_total", None) or 0
+        if t > 0:
+            rows.append((e.key[:80], t / 3.0, e.count / 3.0))
+    rows.sort(key=lambda r: -r[1])
+    for name, us, cnt in rows[:14]:
+        print(f"{name:80s} {us:9.1f} us/step  x{cnt:.1f}")
+    print("total", sum(r[1] for r in rows))
