@@ -301,7 +301,7 @@ int mtvq_soft_forward(const float* x, int64_t n, int d, const float* codes, int 
                       void* stream) {
     if (int r = check_dims(n, d, k)) return r;
     if (topk < 1 || topk > 8 || topk > k) return fail(MTVQ_ERR_UNSUPPORTED, "top-k must be in [1, min(8, k)]%s", "");
-    if (!x || !codes || !idx || !vals || !wts || !zq || !out || !sse || !workspace)
+    if (!codes || !sse || !workspace || (n > 0 && (!x || !idx || !vals || !wts || !zq || !out)))
         return fail(MTVQ_ERR_BAD_ARG, "null pointer%s", "");
     if (!aligned16(x) || !aligned16(codes) || !aligned16(zq) || !aligned16(out) || !aligned16(workspace))
         return fail(MTVQ_ERR_BAD_ARG, "16-byte alignment%s", "");
@@ -367,7 +367,8 @@ int mtvq_soft_backward_fused(const float* x, int64_t n, int d, const float* code
                              void* stream) {
     if (int r = check_dims(n, d, k)) return r;
     if (topk < 1 || topk > 8) return fail(MTVQ_ERR_UNSUPPORTED, "top-k must be in [1, 8]%s", "");
-    if (!x || !codes || !idx || !wts || !grad_x || !grad_codes || !workspace) return fail(MTVQ_ERR_BAD_ARG, "null pointer%s", "");
+    if (!codes || !grad_codes || !workspace || (n > 0 && (!x || !idx || !wts || !grad_x)))
+        return fail(MTVQ_ERR_BAD_ARG, "null pointer%s", "");
     if (!aligned16(x) || !aligned16(codes) || !aligned16(grad_x) || !aligned16(grad_codes) || !aligned16(workspace) ||
         (g_out && !aligned16(g_out)))
         return fail(MTVQ_ERR_BAD_ARG, "16-byte alignment%s", "");
