@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(256) segsum_kernel(const float* __restrict__ z
 // (:181,212-214) AND the per-code sums (:202), so z is read once instead of twice.  Same work split as
 // segsum_kernel; a row's d/4 threads write the 4*d-byte z_q row as whole 128-byte lines.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) sorted_rows_kernel(const float* __restrict__ z, const float* __restrict__ denom,
+__global__ void __launch_bounds__(256, 3) sorted_rows_kernel(const float* __restrict__ z, const float* __restrict__ denom,
                                                            const float* __restrict__ w, const int64_t* __restrict__ idx,
                                                            const int* __restrict__ perm, const int* __restrict__ bins,
                                                            int64_t n, int d, int k,
@@ -338,27 +338,39 @@ __global__ void __launch_bounds__(256) sorted_rows_kernel(const float* __restric
             }
             a0 = a1 = a2 = a3 = 0.0;
         };
-        for (int j0 = 0; j0 < cnt; j0 += 4) {
-            int rows[4], codes[4];
-            float dens[4];
-            float4 x[4], c[4];
+        // software pipeline: the (row, code, norm) triples of the NEXT four sorted positions are fetched (two dependent
+        // round trips: perm -> idx / denom) while the rows and codebook rows of the current four are in flight
+        int rows[4], codes[4];
+        float dens[4];
+        auto fetch_meta = [&](int j) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) rows[u] = (j0 + u < cnt) ? perm[p0 + j0 + u] : 0;
+            for (int u = 0; u < 4; ++u) rows[u] = (j + u < cnt) ? perm[p0 + j + u] : 0;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const bool ok = j0 + u < cnt;
+                const bool ok = j + u < cnt;
                 codes[u] = ok ? (int)__ldg(idx + rows[u]) : 0;
                 dens[u] = ok ? __ldg(denom + rows[u]) : 1.0f;
-                x[u] = ok ? __ldcs(reinterpret_cast<const float4*>(z + (size_t)rows[u] * d) + c4) : make_float4(0, 0, 0, 0);
             }
+        };
+        fetch_meta(0);
+        for (int j0 = 0; j0 < cnt; j0 += 4) {
+            float4 x[4], c[4];
+            int crow[4], ccode[4];
+            float cden[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) c[u] = __ldg(reinterpret_cast<const float4*>(w + (size_t)codes[u] * d) + c4);
+            for (int u = 0; u < 4; ++u) {
+                crow[u] = rows[u]; ccode[u] = codes[u]; cden[u] = dens[u];
+                const bool ok = j0 + u < cnt;
+                x[u] = ok ? __ldcs(reinterpret_cast<const float4*>(z + (size_t)crow[u] * d) + c4) : make_float4(0, 0, 0, 0);
+                c[u] = __ldg(reinterpret_cast<const float4*>(w + (size_t)ccode[u] * d) + c4);
+            }
+            if (j0 + 4 < cnt) fetch_meta(j0 + 4);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 if (j0 + u < cnt) {
-                    if (codes[u] != cur) { flush(); cur = codes[u]; }
-                    const float zf0 = __fdiv_rn(x[u].x, dens[u]), zf1 = __fdiv_rn(x[u].y, dens[u]),
-                                zf2 = __fdiv_rn(x[u].z, dens[u]), zf3 = __fdiv_rn(x[u].w, dens[u]);
+                    if (ccode[u] != cur) { flush(); cur = ccode[u]; }
+                    const float zf0 = __fdiv_rn(x[u].x, cden[u]), zf1 = __fdiv_rn(x[u].y, cden[u]),
+                                zf2 = __fdiv_rn(x[u].z, cden[u]), zf3 = __fdiv_rn(x[u].w, cden[u]);
                     a0 += (double)zf0; a1 += (double)zf1; a2 += (double)zf2; a3 += (double)zf3;
                     const float d0 = __fsub_rn(c[u].x, zf0), d1 = __fsub_rn(c[u].y, zf1), d2 = __fsub_rn(c[u].z, zf2),
                                 d3 = __fsub_rn(c[u].w, zf3);
@@ -366,7 +378,7 @@ __global__ void __launch_bounds__(256) sorted_rows_kernel(const float* __restric
                            (double)__fmul_rn(d3, d3);
                     float4 o;
                     o.x = __fadd_rn(zf0, d0); o.y = __fadd_rn(zf1, d1); o.z = __fadd_rn(zf2, d2); o.w = __fadd_rn(zf3, d3);
-                    __stcs(reinterpret_cast<float4*>(z_q + (size_t)rows[u] * d) + c4, o);
+                    __stcs(reinterpret_cast<float4*>(z_q + (size_t)crow[u] * d) + c4, o);
                 }
             }
         }
