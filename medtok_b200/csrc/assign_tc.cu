@@ -142,18 +142,21 @@ __device__ __forceinline__ void record_store(unsigned char* slots, int rec, cons
     }
 }
 
-// MODE_TOPK keeps records in a per-CTA global scratch (L2 resident): uint4 index ((slot * 4 + c) * kRecords + rec)
+// MODE_TOPK keeps records in a per-CTA global scratch (L2 resident): 32-byte unit ((slot * 2 + c2) * kRecords + rec),
+// written with two 256-bit stores (STG.256 exists on sm_100a; each store instruction in the slot loop costs ~0.1 ms of a
+// 4 ms pass, see profiles/r01_soft_path.md)
 __device__ __forceinline__ void record_store_g(uint4* dst, const float (&v)[32]) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        __half2 h0 = __floats2half2_rn(v[8 * c + 0], v[8 * c + 1]);
-        __half2 h1 = __floats2half2_rn(v[8 * c + 2], v[8 * c + 3]);
-        __half2 h2 = __floats2half2_rn(v[8 * c + 4], v[8 * c + 5]);
-        __half2 h3 = __floats2half2_rn(v[8 * c + 6], v[8 * c + 7]);
-        uint4 q;
-        q.x = *reinterpret_cast<uint32_t*>(&h0); q.y = *reinterpret_cast<uint32_t*>(&h1);
-        q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
-        __stcg(dst + c * kRecords, q);
+    for (int c2 = 0; c2 < 2; ++c2) {
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            __half2 h = __floats2half2_rn(v[16 * c2 + 2 * i], v[16 * c2 + 2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        asm volatile("st.global.cg.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 2 * c2 * kRecords), "r"(w[0]),
+                     "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                     : "memory");
     }
 }
 
@@ -285,9 +288,9 @@ __device__ __forceinline__ void consume_topk(const float (&v)[32], int gran, flo
 
 // scan_record on the global scratch (read through L2: other threads of the CTA wrote it)
 __device__ __forceinline__ int scan_record_g(const uint4* src, float ts, int col0, int* dst, int n0, int cap) {
-    uint4 q[4];
+    uint4 q[4];     // 16-byte unit cc of the record: 32-byte unit cc / 2, half cc % 2
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) q[cc] = __ldcg(src + cc * kRecords);
+    for (int cc = 0; cc < 4; ++cc) q[cc] = __ldcg(src + 2 * (cc >> 1) * kRecords + (cc & 1));
     int n = 0;
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) {
@@ -450,7 +453,7 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
         const float nwmax = p.meta[META_MAXNORM];
         const float margin_k = margin + 4.0e-6f * (1.0f + nwmax + 0.5f * nwmax * nwmax);
         const int kidx = min(max(p.topk, 1), kTopSlots) - 1;
-        uint4* topk_rec = static_cast<uint4*>(p.topk_scratch) + (size_t)blockIdx.x * (kTopkScratchPerCta / 16) + rec0;
+        uint4* topk_rec = static_cast<uint4*>(p.topk_scratch) + (size_t)blockIdx.x * (kTopkScratchPerCta / 16) + 2 * rec0;
         uint16_t* topk_gid = reinterpret_cast<uint16_t*>(smem + kOffSlots) + rec0;    // [slot][1024 records]
         if (MODE == MODE_TOPK) {      // published bounds (kOffState): nothing known yet
 #pragma unroll
@@ -510,10 +513,10 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                         if constexpr (NLIST == kTopSlots) {
                             constexpr int KS = (NTOP == 5) ? 5 : 0;
                             consume_topk<KS>(va, c * 4 + half2, st[ss].top, st[ss].thr, kidx, margin_k,
-                                             topk_rec + ss * 512, topk_gid + ss * 512, state + ss * 512 + rec0,
+                                             topk_rec + ss * 1024, topk_gid + ss * 512, state + ss * 512 + rec0,
                                              state + ss * 512 + (rec0 ^ 128));
                             consume_topk<KS>(vb, c * 4 + half2 + 1, st[ss].top, st[ss].thr, kidx, margin_k,
-                                             topk_rec + ss * 512, topk_gid + ss * 512, state + ss * 512 + rec0,
+                                             topk_rec + ss * 1024, topk_gid + ss * 512, state + ss * 512 + rec0,
                                              state + ss * 512 + (rec0 ^ 128));
                         }
                     } else {
@@ -665,7 +668,7 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                                         if (i == kTopSlots - 1) over = true;     // an untracked granule may qualify too
                                         const int slot = __float_as_int(e) & 7;
                                         const int gran = gid_all[slot * kRecords + rec];
-                                        nw += scan_record_g(rec_cta + (slot * 4) * kRecords + rec, thrS, gran * kChunk, dst, nw,
+                                        nw += scan_record_g(rec_cta + (slot * 4) * kRecords + 2 * rec, thrS, gran * kChunk, dst, nw,
                                                             p.cand_cap);
                                     }
                                 }
