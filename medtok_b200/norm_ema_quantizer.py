@@ -411,3 +411,96 @@ class VectorQuantizer(nn.Module):
         z_q, loss = self._run(encoding_indices, z_rows)
         z_q = z_q.view(b, h, w, -1).permute(0, 3, 1, 2)                             # :267
         return z_q, loss, encoding_indices
+
+
+# ------------------------------------------------------------------------------------------------
+class FeaturePool():
+    """reference :405-460: buffer of previously seen features for the 'random' anchor (host-side bookkeeping)."""
+
+    def __init__(self, pool_size, dim=64):
+        self.pool_size = pool_size
+        if self.pool_size > 0:
+            self.nums_features = 0
+            self.features = (torch.rand((pool_size, dim)) * 2 - 1) / pool_size
+
+    def query(self, features):
+        self.features = self.features.to(features.device)
+        if self.nums_features < self.pool_size:
+            if features.size(0) > self.pool_size:
+                random_feat_id = torch.randint(0, features.size(0), (int(self.pool_size),))
+                self.features = features[random_feat_id]
+                self.nums_features = self.pool_size
+            else:
+                num = self.nums_features + features.size(0)
+                self.features[self.nums_features:num] = features
+                self.nums_features = num
+        else:
+            if features.size(0) > int(self.pool_size):
+                random_feat_id = torch.randint(0, features.size(0), (int(self.pool_size),))
+                self.features = features[random_feat_id]
+            else:
+                random_id = torch.randperm(self.pool_size)
+                self.features[random_id[:features.size(0)]] = features
+        return self.features
+
+
+class CVectorQuantiser(NormEMAVectorQuantizer):
+    """Drop-in for reference :272-403 (norm-EMA quantizer + online re-initialisation of dead codes).
+
+    The assignment, statistics, EMA and loss are exactly the NormEMAVectorQuantizer forward (the reference's
+    `d = -|z|^2 - |e|^2 + 2 z.e`, argmax, is the exact negation of :175-179, ties included), run by the same kernels.  On
+    top, in training mode: `embed_prob` tracks the LOCAL usage frequencies (:375-377) and every code is pulled towards an
+    anchor sample with weight exp(-(embed_prob * K * 10) / (1 - decay) - 1e-3) (:379-393).  For anchor='closest' the anchor
+    is the sample nearest to the code under the PRE-update codebook, found with the same tensor-core assignment kernel
+    with the roles swapped (codes as rows, normalised samples as the codebook) and gathered with mtvq_lookup; the
+    K x D blend itself is plain elementwise PyTorch (not on the hot path).  anchor='probrandom' (a K x N softmax +
+    multinomial) and contras_loss=True (a NameError in the reference, :396-402) are not implemented."""
+
+    def __init__(self, n_embed, embedding_dim, beta, decay=0.99, eps=1e-5,
+                 statistic_code_usage=True, kmeans_init=True, codebook_init_path='',
+                 distance='l2', anchor='closest', first_batch=False, contras_loss=False):
+        super().__init__(n_embed, embedding_dim, beta, decay, eps, statistic_code_usage, kmeans_init, codebook_init_path)
+        if distance != 'l2':
+            raise NotImplementedError("only distance='l2' (on l2-normalised rows 'cos' selects the same codes)")
+        if contras_loss:
+            raise NotImplementedError("contras_loss=True raises NameError in the reference (:396-402)")
+        if anchor == 'probrandom':
+            raise NotImplementedError("anchor='probrandom' materialises a K x N softmax; use 'closest' or 'random'")
+        self.num_embed = n_embed
+        self.n_e = n_embed
+        self.embed_dim = embedding_dim
+        self.distance = distance
+        self.anchor = anchor
+        self.first_batch = first_batch
+        self.contras_loss = contras_loss
+        self.init = False
+        self.pool = FeaturePool(self.num_embed, self.embed_dim)
+        self.register_buffer("embed_prob", torch.zeros(self.num_embed))
+        self._ws_anchor = _lib.Workspace()
+
+    def forward(self, z, temp=None, rescale_logits=False, return_logits=False):
+        reinit = self.training and self.anchor in ('closest', 'random') and not self.init
+        w_old = self.embedding.weight.data.clone() if (reinit and self.anchor == 'closest') else None
+        z_q, loss, idx = super().forward(z)
+        if self.training:
+            with torch.no_grad():
+                k, d = self.num_tokens, self.codebook_dim
+                n = idx.numel()
+                local_bins = torch.bincount(idx, minlength=k).to(torch.float32)          # :375 mean of the LOCAL one-hot
+                self.embed_prob.mul_(self.decay).add_(local_bins / float(max(n, 1)), alpha=1 - self.decay)
+                if reinit:
+                    rows = z.permute(0, 2, 3, 1).reshape(-1, d)
+                    zf = l2norm(_rows_f32(rows))                                         # z_flattened (:313-315)
+                    if self.anchor == 'closest':
+                        # sample with the largest d[:, k] per code (:381-383) == nearest sample to the code
+                        near, _ = hard_assign(w_old, zf, workspace=self._ws_anchor)
+                        feat = torch.empty(k, d, dtype=torch.float32, device=zf.device)
+                        _lib.check(_lib.lib().mtvq_lookup(None, _lib.ptr(zf), _lib.ptr(near), k, d, n, _lib.ptr(feat), None,
+                                                          None, None, 0, _lib.stream_ptr(zf.device)), "mtvq_lookup")
+                    else:
+                        feat = self.pool.query(zf)
+                    dec = torch.exp(-(self.embed_prob * self.num_embed * 10) / (1 - self.decay) - 1e-3).unsqueeze(1)
+                    self.embedding.weight.data = self.embedding.weight.data * (1 - dec) + feat * dec
+                    if self.first_batch:
+                        self.init = True
+        return z_q, loss, idx

@@ -237,6 +237,26 @@ def gen_lookup(hard):
                     "state_dict_keys": sorted(q.state_dict().keys())}, **rec)
 
 
+def gen_cvq(hard):
+    """CVectorQuantiser (norm_ema_quantizer.py:272-403), anchor='closest': two training steps and one eval step."""
+    g = torch.Generator().manual_seed(61)
+    n, d, k = 600, 32, 96
+    w0 = hard.l2norm(torch.randn(k, d, generator=g))
+    zs = [torch.randn(n, d, 1, 1, generator=g) for _ in range(3)]
+    q = hard.CVectorQuantiser(n_embed=k, embedding_dim=d, beta=0.25, kmeans_init=False, anchor='closest')
+    q.embedding.weight.data.copy_(w0)
+    rec = {"weight0": _np(w0)}
+    with torch.no_grad():
+        for s, mode in enumerate(("train", "train", "eval")):
+            q.train(mode == "train")
+            z_q, loss, idx = q(zs[s])
+            rec.update({f"z_{s}": _np(zs[s]), f"z_q_{s}": _np(z_q), f"loss_{s}": _np(loss).reshape(1), f"idx_{s}": _np(idx),
+                        f"cluster_size_{s}": _np(q.cluster_size), f"weight_{s}": _np(q.embedding.weight),
+                        f"embed_prob_{s}": _np(q.embed_prob)})
+    save("cvq_closest_n600_d32_k96", {"kind": "cvq", "beta": 0.25, "decay": 0.99, "modes": ["train", "train", "eval"],
+                                      "state_dict_keys": sorted(q.state_dict().keys())}, **rec)
+
+
 def gen_usage(soft):
     """codebook_usage (vector_quantization_soft_one_new.py:219-236): a sequence of calls on one window."""
     import contextlib
@@ -300,7 +320,7 @@ def gen_gloo(hard):
 
 def main():
     hard, soft = ref_loader.load()
-    which = set(sys.argv[1:]) or {"hard", "soft", "kmeans", "gloo", "lookup", "usage"}
+    which = set(sys.argv[1:]) or {"hard", "soft", "kmeans", "gloo", "lookup", "usage", "cvq"}
     if "hard" in which:
         gen_hard(hard)
     if "soft" in which:
@@ -313,6 +333,8 @@ def main():
         gen_lookup(hard)
     if "usage" in which:
         gen_usage(soft)
+    if "cvq" in which:
+        gen_cvq(hard)
 
 
 if __name__ == "__main__":

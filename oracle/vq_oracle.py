@@ -199,6 +199,31 @@ def hard_forward(z, weight, cluster_size, beta, decay=0.99, training=True, updat
     return HardResult(zq, loss, idx, new_cs, new_w, zf, bins, esum, sse)
 
 
+def cvq_forward(z, weight, cluster_size, embed_prob, beta, decay=0.99, training=True, init_done=False):
+    """CVectorQuantiser.forward, norm_ema_quantizer.py:313-403, anchor='closest', distance='l2': the norm-EMA forward
+    (d of :320-324 is the exact negation of :175-177, so argmax d == argmin with the same ties; :336-364 == :183-210),
+    then in training mode embed_prob <- decay*embed_prob + (1-decay)*mean(one_hot) (:375-377) and, unless `init_done`,
+    every code is blended with the sample that has the largest d in its column under the PRE-update codebook
+    (:381-383,391-392).  Returns (HardResult, embed_prob, weight_after_reinit)."""
+    z = _f32(z)
+    weight = _f32(weight)
+    r = hard_forward(z, weight, cluster_size, beta, decay, training=training, update=True)
+    ep = _f32(embed_prob).copy()
+    w_out = r.weight
+    if training:
+        n = z.shape[0]
+        avg = (np.bincount(r.idx, minlength=weight.shape[0]).astype(np.float32) / np.float32(n)).astype(np.float32)
+        ep = (ep * np.float32(decay) + avg * np.float32(1 - decay)).astype(np.float32)          # :377
+        if not init_done:
+            dm = -C().dist_matrix(r.zf, weight)                                                 # :320-324 (negated :175-177)
+            near = dm.shape[0] - 1 - np.argmax(dm[::-1], axis=0)                                # last row among equal maxima
+            feat = r.zf[near]
+            dec = np.exp(-(ep * np.float32(weight.shape[0]) * np.float32(10)) / np.float32(1 - decay)
+                         - np.float32(1e-3)).astype(np.float32)[:, None]
+            w_out = (r.weight * (np.float32(1) - dec) + feat * dec).astype(np.float32)          # :392
+    return r, ep, w_out
+
+
 # ------------------------------------------------------------------------------------------
 # Soft path: VectorQuantizer.specific_embedding / shared core
 # (vector_quantization_soft_one_new.py:147-185, 187-217)

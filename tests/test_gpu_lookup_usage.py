@@ -121,3 +121,28 @@ def test_accumulated_batches_equal_one_pass(dev):
     assert torch.equal(stats[:k], q.last_stats[:k])
     assert (w1 - w2).abs().max().item() <= 1.2e-7
     assert abs(float(loss) - float(loss1)) <= 1e-6 * float(loss1)
+
+
+def test_cvector_quantiser_matches_reference_golden(dev):
+    """CVectorQuantiser (norm_ema_quantizer.py:272-403, anchor='closest'): indices / counts / z_q bit-exact, embed_prob and
+    the re-initialised codebook within tolerance, over two training steps and one eval step."""
+    from medtok_b200.norm_ema_quantizer import CVectorQuantiser
+    meta, a = load_golden("cvq_closest_n600_d32_k96")
+    k, d = a["weight0"].shape
+    q = CVectorQuantiser(n_embed=k, embedding_dim=d, beta=meta["beta"], kmeans_init=False, anchor='closest').to(dev)
+    assert sorted(q.state_dict().keys()) == meta["state_dict_keys"]
+    q.embedding.weight.data.copy_(torch.from_numpy(a["weight0"]).to(dev))
+    for s, mode in enumerate(meta["modes"]):
+        q.train(mode == "train")
+        with torch.no_grad():
+            z_q, loss, idx = q(torch.from_numpy(a[f"z_{s}"]).to(dev))
+        assert np.array_equal(idx.cpu().numpy(), a[f"idx_{s}"]), f"step {s}"
+        assert np.array_equal(q.cluster_size.cpu().numpy(), a[f"cluster_size_{s}"])
+        assert np.array_equal(z_q.cpu().numpy(), a[f"z_q_{s}"])
+        ref = float(a[f"loss_{s}"][0])
+        assert abs(float(loss) - ref) <= 1e-5 * ref
+        assert np.max(np.abs(q.embed_prob.cpu().numpy() - a[f"embed_prob_{s}"])) <= 1e-8
+        assert np.max(np.abs(q.embedding.weight.cpu().numpy() - a[f"weight_{s}"])) <= 2e-6
+        # continue from the reference's own state so that every step is checked on its own
+        q.embedding.weight.data.copy_(torch.from_numpy(a[f"weight_{s}"]).to(dev))
+        q.embed_prob.copy_(torch.from_numpy(a[f"embed_prob_{s}"]).to(dev))
