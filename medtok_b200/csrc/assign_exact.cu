@@ -16,7 +16,19 @@ namespace mtvq {
 __global__ void codebook_prep_kernel(const float* __restrict__ w, int k, int kpad, int d, int normalize,
                                      unsigned char* __restrict__ image, float* __restrict__ cc,
                                      float* __restrict__ codes_n, float* __restrict__ meta) {
+    // the block's 32 rows are staged into shared memory with coalesced loads, all in flight at once (one thread per
+    // code reading its own row from global memory was bound by dependent-load latency: ~2 warps per SM)
+    __shared__ float rows_s[32 * (kMaxDim + 1)];
     const int code = blockIdx.x * blockDim.x + threadIdx.x;
+    {
+        const int code0 = blockIdx.x * blockDim.x;
+        const int nrows = min(32, k - code0);
+        for (int e = threadIdx.x; e < nrows * d; e += 32) {
+            const int r = e / d, c = e - r * d;
+            rows_s[r * (d + 1) + c] = __ldg(w + (size_t)code0 * d + e);
+        }
+        __syncwarp();
+    }
     if (code >= kpad) return;
     const int nplanes = d >> 3;
     const int tile = code >> 7, r = code & 127;
@@ -31,10 +43,10 @@ __global__ void codebook_prep_kernel(const float* __restrict__ w, int k, int kpa
         cc[code] = 3.0e38f;
         return;
     }
-    const float* wr = w + (size_t)code * d;
+    const float* wr = rows_s + threadIdx.x * (d + 1);     // this thread's row, staged below
     float den = 1.0f;
-    if (normalize) den = canon_denom([&](int i) { return __ldg(wr + i); }, d, 0);
-    auto elem = [&](int i) { return normalize ? __fdiv_rn(__ldg(wr + i), den) : __ldg(wr + i); };
+    if (normalize) den = canon_denom([&](int i) { return wr[i]; }, d, 0);
+    auto elem = [&](int i) { return normalize ? __fdiv_rn(wr[i], den) : wr[i]; };
     const float c2 = canon_sumsq(elem, d);
     cc[code] = c2;
     {   // spread of the squared norms around code 0's: if it is negligible the kernels drop the bias K-step

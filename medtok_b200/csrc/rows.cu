@@ -424,7 +424,7 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
 }
 
 template <bool PEERS>
-__global__ void __launch_bounds__(128) ema_finalize_kernel(float* __restrict__ weight, float* __restrict__ cluster_size,
+__global__ void __launch_bounds__(256) ema_finalize_kernel(float* __restrict__ weight, float* __restrict__ cluster_size,
                                                             const double* __restrict__ stats, PeerTable pt, int k, int d,
                                                             float beta, float decay, float alpha, int update_cs,
                                                             int update_w, float* __restrict__ loss) {
@@ -471,7 +471,8 @@ __global__ void __launch_bounds__(128) ema_finalize_kernel(float* __restrict__ w
     // the contract (oracle: vqo_ema_*), run one thread per code
     __shared__ float den_s[kEmaCodes];
     const int ncodes = min(kEmaCodes, k - code0);
-#pragma unroll 4
+    // (latency-bound: 256 threads and 8 independent element loads per thread keep the whole tile's loads in flight)
+#pragma unroll 8
     for (int e = threadIdx.x; e < ncodes * d; e += blockDim.x) {
         const int c = e / d, i = e - c * d;
         const float wv = weight[(size_t)(code0 + c) * d + i];
@@ -613,7 +614,7 @@ cudaError_t launch_ema_finalize(float* weight, float* cluster_size, const double
     // python: mul_(decay).add_(new, alpha=1-decay): both scalars are doubles cast to fp32
     const size_t smem = sizeof(float) * 2 * kEmaCodes * (d + 1);   // <= 65.8 KB at d = 256
     if (cudaError_t e = ema_finalize_configure()) return e;
-    ema_finalize_kernel<false><<<(k + kEmaCodes - 1) / kEmaCodes, 128, smem, s>>>(
+    ema_finalize_kernel<false><<<(k + kEmaCodes - 1) / kEmaCodes, 256, smem, s>>>(
         weight, cluster_size, stats, PeerTable{}, k, d, (float)beta, (float)decay, (float)(1.0 - decay), update_cs, update_w,
         loss);
     ++g_kernel_launches;
@@ -629,7 +630,7 @@ cudaError_t launch_ema_finalize_peers(float* weight, float* cluster_size, const 
     pt.stats = reinterpret_cast<const double* const*>(peer_stats);
     pt.flags = reinterpret_cast<unsigned* const*>(peer_flags);
     pt.world = world; pt.rank = rank; pt.epoch = epoch;
-    ema_finalize_kernel<true><<<(k + kEmaCodes - 1) / kEmaCodes, 128, smem, s>>>(
+    ema_finalize_kernel<true><<<(k + kEmaCodes - 1) / kEmaCodes, 256, smem, s>>>(
         weight, cluster_size, nullptr, pt, k, d, (float)beta, (float)decay, (float)(1.0 - decay), update_cs, update_w, loss);
     ++g_kernel_launches;
     return cudaGetLastError();
