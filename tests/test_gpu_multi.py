@@ -16,8 +16,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_two_rank_forward_matches_single_process(fused):
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs two CUDA devices")
+    import socket
     env = dict(os.environ, MEDTOK_FUSED_EXCHANGE=fused)
-    port = 29620 + int(fused)
+    with socket.socket() as sock:                      # a free rendezvous port
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools_dist_check.py")],
                        capture_output=True, text=True, env=env, timeout=600, cwd=ROOT)
