@@ -220,7 +220,8 @@ __device__ __forceinline__ void consume(const float (&v)[32], int chunk, RowStat
 // a maximum (m3; if THAT ends up within the margin the row falls back to a COLLECT pass).
 template <int NTOP>
 __device__ __forceinline__ void consume_argmax64(const float (&va)[32], const float (&vb)[32], int chunk,
-                                                 RowState<NTOP>& st, float margin, unsigned char* slots, int rec) {
+                                                 RowState<NTOP>& st, float margin, unsigned char* slots, int rec,
+                                                 float* pub, const float* partner) {
     const float ma = max32(va), mb = max32(vb);
     const float cmax = fmaxf(ma, mb);
     const bool trig = cmax >= st.thr;
@@ -228,6 +229,9 @@ __device__ __forceinline__ void consume_argmax64(const float (&va)[32], const fl
         if (trig) {
             const bool b_wins = mb > ma;
             const float lo = fminf(ma, mb);
+            // the ROW's best so far is at least what the thread owning the other column half has published (its value
+            // only grows, so a stale read is still a bound): a granule below that minus the margin cannot matter
+            const float other = *partner;
             if (cmax > st.m1) {          // new record
                 const float nthr = cmax - margin;
                 // Only granules within the margin of the CURRENT best can matter at the end (the best only grows), so
@@ -239,12 +243,14 @@ __device__ __forceinline__ void consume_argmax64(const float (&va)[32], const fl
                     else            { st.m3 = fmaxf(fmaxf(st.m3, st.m2), lo);    st.m2 = st.m1; st.chunk2 = st.best_chunk; }
                 }
                 st.m1 = cmax;
-                st.thr = nthr;
+                *pub = cmax;
+                st.thr = fmaxf(nthr, other - margin);
                 if (b_wins) { st.best_chunk = chunk + 1; record_store(slots, rec, vb); }
                 else        { st.best_chunk = chunk;     record_store(slots, rec, va); }
-            } else {                      // rare: granule(s) within the margin of the record
+            } else {                      // rare: granule(s) within the margin of the record (or of the other half's best)
                 if (cmax > st.m2) { st.m3 = fmaxf(fmaxf(st.m3, st.m2), lo); st.m2 = cmax; st.chunk2 = b_wins ? chunk + 1 : chunk; }
                 else              { st.m3 = fmaxf(st.m3, cmax); }
+                st.thr = fmaxf(st.thr, other - margin);
             }
         }
     }
@@ -455,9 +461,11 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
         const int kidx = min(max(p.topk, 1), kTopSlots) - 1;
         uint4* topk_rec = static_cast<uint4*>(p.topk_scratch) + (size_t)blockIdx.x * (kTopkScratchPerCta / 16) + 2 * rec0;
         uint16_t* topk_gid = reinterpret_cast<uint16_t*>(smem + kOffSlots) + rec0;    // [slot][1024 records]
-        if (MODE == MODE_TOPK) {      // published bounds (kOffState): nothing known yet
+        if (MODE == MODE_TOPK || MODE == MODE_ARGMAX) {      // published bounds (kOffState): nothing known yet
 #pragma unroll
-            for (int ss = 0; ss < NS; ++ss) state[ss * 512 + rec0] = make_float4(-3.0e38f, -3.0e38f, -3.0e38f, 0.f);
+            for (int ss = 0; ss < NS; ++ss)
+                state[ss * 512 + rec0] = (MODE == MODE_TOPK) ? make_float4(-3.0e38f, -3.0e38f, -3.0e38f, 0.f)
+                                                             : make_float4(-INFINITY, 0.f, 0.f, 0.f);
             named_bar_sync((RT == 1) ? 1 : 1 + pair, (RT == 1) ? 512 : 256);
         }
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
@@ -508,7 +516,8 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                     if (DBG && tracing && si == 0 && uses[0] <= 512) p.trace[(uses[0] - 1) * 8 + 3] = clock64();
                     if (DBG && (p.debug_flags & 1)) continue;    // timing experiment: no epilogue work
                     if (MODE == MODE_ARGMAX) {
-                        consume_argmax64<NLIST>(va, vb, c * 4 + half2, st[ss], margin, slots, ss * 512 + rec0);
+                        consume_argmax64<NLIST>(va, vb, c * 4 + half2, st[ss], margin, slots, ss * 512 + rec0,
+                                                &state[ss * 512 + rec0].x, &state[ss * 512 + (rec0 ^ 128)].x);
                     } else if (MODE == MODE_TOPK) {
                         if constexpr (NLIST == kTopSlots) {
                             constexpr int KS = (NTOP == 5) ? 5 : 0;
@@ -616,6 +625,14 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                             base = __shfl_sync(0xffffffffu, base, 0);
                             if (over) p.over_rows[base + __popc(oall & ((1u << lane) - 1))] = (int)st[ss].row;
                         }
+                        // the next row block starts with no published best (the leader has read every entry of the row)
+#pragma unroll
+                        for (int pp = 0; pp < NP; ++pp)
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh) {
+                                const int w2 = quarter + 4 * hh + 8 * ((RT == 1) ? pp : pair);
+                                state[ss * 512 + w2 * 32 + lane].x = -INFINITY;
+                            }
                     }
                 }
                 named_bar_sync(bar_id, bar_n);
