@@ -415,32 +415,36 @@ class VectorQuantizer(nn.Module):
 
 # ------------------------------------------------------------------------------------------------
 class FeaturePool():
-    """reference :405-460: buffer of previously seen features for the 'random' anchor (host-side bookkeeping)."""
+    """Feature history for the 'random' anchor (reference :405-460; host-side bookkeeping, behaviour kept):
+    until the pool has filled once, batches are appended (a batch larger than the pool replaces it by a random sample
+    of the batch and marks it full); afterwards a larger batch again replaces the pool by a random sample, a smaller one
+    overwrites randomly chosen slots.  `query` returns the pool."""
 
     def __init__(self, pool_size, dim=64):
         self.pool_size = pool_size
-        if self.pool_size > 0:
+        if pool_size > 0:
             self.nums_features = 0
-            self.features = (torch.rand((pool_size, dim)) * 2 - 1) / pool_size
+            self.features = (2.0 * torch.rand((pool_size, dim)) - 1.0) / pool_size
+
+    def _resample(self, batch):
+        pick = torch.randint(0, batch.size(0), (int(self.pool_size),))
+        self.features = batch[pick]
 
     def query(self, features):
         self.features = self.features.to(features.device)
-        if self.nums_features < self.pool_size:
-            if features.size(0) > self.pool_size:
-                random_feat_id = torch.randint(0, features.size(0), (int(self.pool_size),))
-                self.features = features[random_feat_id]
-                self.nums_features = self.pool_size
-            else:
-                num = self.nums_features + features.size(0)
-                self.features[self.nums_features:num] = features
-                self.nums_features = num
+        rows, cap = features.size(0), int(self.pool_size)
+        filling = self.nums_features < cap
+        if rows > cap:
+            self._resample(features)
+            if filling:
+                self.nums_features = cap
+        elif filling:
+            end = self.nums_features + rows
+            self.features[self.nums_features:end] = features
+            self.nums_features = end
         else:
-            if features.size(0) > int(self.pool_size):
-                random_feat_id = torch.randint(0, features.size(0), (int(self.pool_size),))
-                self.features = features[random_feat_id]
-            else:
-                random_id = torch.randperm(self.pool_size)
-                self.features[random_id[:features.size(0)]] = features
+            slots = torch.randperm(cap)[:rows]
+            self.features[slots] = features
         return self.features
 
 
