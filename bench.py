@@ -249,9 +249,11 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": elapsed_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (exact re-scoring) over an fp16-operand / fp32-accumulate tcgen05 candidate pass",
+            "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"BASELINE config 2: hard argmin + norm-EMA update, N={n} rows/GPU, D={d}, K={k}",
+                       "arithmetic": "results are the reference's fp32 results (exact re-scoring in reference order); the "
+                                     "tcgen05 candidate pass uses fp16 operands with fp32 accumulation",
                        "rows_per_gpu": n, "dim": d, "codes": k, "parallelism": f"rows sharded x{world}, codebook replicated",
                        "l2": "two alternating 256 MiB input batches (> 126 MB L2) between timed iterations",
                        "near_tie_rows_last_step": counters["near_tie_rows"],
@@ -341,9 +343,10 @@ def run_soft(args):
             "metric": "quantized embeddings/sec (soft top-5 forward)", "value": world * n * steps / (elapsed_ms * 1e-3),
             "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": elapsed_ms / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (exact re-scoring) over an fp16-operand / fp32-accumulate tcgen05 candidate pass",
+            "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"BASELINE config 3: soft-one top-{kk} quantisation, N={n} rows/GPU, D={d}, K'={k}",
+                       "arithmetic": "fp32 results (exact re-scoring); fp16-operand / fp32-accumulate tcgen05 candidate pass",
                        "l2": "two alternating 512 MiB input batches", "full_scan_rows_last_step": counters["full_scan_rows"]},
             "roofline": {"bound": "tensor", "achieved": flops / (kms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
                          "frac": flops / (kms * 1e-3) / 1e12 / peak, "traffic": None,
