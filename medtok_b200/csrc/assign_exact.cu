@@ -419,7 +419,8 @@ cudaError_t launch_exact_scan(const float* z, int64_t n, int d, int norm_mode, c
                               const float* cc, const int* row_list, const int* n_rows_dev, int64_t* idx, int* bins,
                               float* denom_out, int num_sms, cudaStream_t stream) {
     const size_t smem = sizeof(float) * ((size_t)d * XR + XD * (XC + 1) + XR + XR * 16) + sizeof(int) * XR * 16;
-    static bool configured = false;
+    static PerDeviceOnce once;
+    bool& configured = once.flag();
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(exact_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         if (e != cudaSuccess) return e;

@@ -942,7 +942,8 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
 template <int RT, int MODE, int NTOP, bool DBG>
 static cudaError_t launch_one(const CoarseParams& p, int grid, cudaStream_t stream) {
     auto kern = coarse_kernel<RT, MODE, NTOP, DBG>;
-    static bool configured = false;   // one per instantiation
+    static PerDeviceOnce once;         // one per instantiation and device
+    bool& configured = once.flag();
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e != cudaSuccess) return e;

@@ -598,7 +598,8 @@ cudaError_t launch_sorted_rows(const float* z, const float* denom, const float* 
 }
 
 static cudaError_t ema_finalize_configure() {
-    static bool configured = false;
+    static PerDeviceOnce once;
+    bool& configured = once.flag();
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(ema_finalize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
         if (e == cudaSuccess)

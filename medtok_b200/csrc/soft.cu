@@ -512,7 +512,8 @@ cudaError_t launch_soft_resolve(const float* x, int64_t n, int d, int k, int top
     // shared memory: per 8-lane group the normalised row and an 8-candidate tile; d > 128 runs 4 warps per CTA
     const int warps = d <= 128 ? kSoftWarps : kSoftWarps / 2;
     const size_t smem = sizeof(float) * warps * 4 * ((size_t)d + 8 * (size_t)(d + 4));
-    static bool configured = false;
+    static PerDeviceOnce once;
+    bool& configured = once.flag();
     if (!configured) {
         cudaError_t e = cudaSuccess;
 #define MTVQ_SOFT_ATTR(NQ_, KT_)                                                                                   \

@@ -1,5 +1,6 @@
 // workspace.h -- host-side carving of the caller-provided scratch blob (the library never allocates).
 #pragma once
+#include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
 
@@ -13,6 +14,17 @@ enum MetaSlot { META_MARGIN = 0, META_EPS = 1, META_MAXNORM = 2, META_SPREAD = 3
 constexpr float kBiasSkipTol = 1.0e-6f;
 // counters (ints), zeroed at the start of every assign
 enum Counter { CNT_FLAGGED = 0, CNT_FULL = 1, CNT_CANDS = 2, CNT_LAUNCHES = 3, CNT_OVER = 4, CNT_COUNT = 8 };
+
+// cudaFuncSetAttribute applies to the current device only: "configured once" flags are kept per device (a host may
+// drive several GPUs from one process, even though the module layer uses one process per GPU)
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool& flag() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        return done[dev & 63];
+    }
+};
 
 // kernels this thread has enqueued (every launcher adds its own; reported through mtvq_debug_counters)
 extern thread_local long g_kernel_launches;
