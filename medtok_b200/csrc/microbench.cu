@@ -149,7 +149,111 @@ __global__ void __launch_bounds__(256, 1) umma_multi_issuer_kernel(int iters, in
     if (sink == nullptr) sm[0] = 1;
 }
 
+// which = 7: functional probe of the two-CTA MMA (tcgen05.mma.cta_group::2, M = 256 over a CTA pair, each CTA holding
+// its 128 rows of A and its 64-code half of B): one K-step on known data, every accumulator element checked.
+// result_host[0] = number of wrong elements, result_host[1] = elements checked.
+__global__ void __launch_bounds__(128, 1) umma_2cta_probe_kernel(float* out /* [256][128] */) {
+    extern __shared__ __align__(1024) unsigned char sm[];
+    __shared__ uint32_t tmem_ptr;
+    __shared__ uint64_t bar;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // A: 128 rows x 16 fp16 (2 planes of 128 x 16 B at sm + 0); row r = 128 * rank + tid: A[r][0] = (r % 7 + 1) / 8
+    // B: 64 codes x 16 fp16 (2 planes of 64 x 16 B at sm + 8192); code n = 64 * rank + tid: B[n][0] = (n % 5 + 1) / 4
+    for (int i = threadIdx.x; i < 16384 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = 0u;
+    __syncthreads();
+    {
+        const int r = 128 * (int)rank + (int)threadIdx.x;
+        reinterpret_cast<__half*>(sm + threadIdx.x * 16)[0] = __float2half((float)(r % 7 + 1) / 8.0f);
+        if (threadIdx.x < 64) {
+            const int n = 64 * (int)rank + (int)threadIdx.x;
+            reinterpret_cast<__half*>(sm + 8192 + threadIdx.x * 16)[0] = __float2half((float)(n % 5 + 1) / 4.0f);
+        }
+    }
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    fence_proxy_async_smem();
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr)), "r"(128u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    tc_fence_after();
+    if (rank == 0 && warp == 1 && elect_one()) {
+        const uint32_t idesc = umma_idesc_f16(256, 128);
+        const uint64_t da = umma_smem_desc(smem_u32(sm), 2048, 128);
+        const uint64_t db = umma_smem_desc(smem_u32(sm + 8192), 1024, 128);
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_ptr), "l"(da), "l"(db), "r"(idesc), "r"(0u)
+            : "memory");
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                         smem_u32(&bar)),
+                     "h"((uint16_t)3)
+                     : "memory");
+    }
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+    {
+        // warp w reads TMEM lanes [32 w, 32 w + 32): row = 128 * rank + 32 * w + lane, all 128 columns
+        const uint32_t base = tmem_ptr + ((uint32_t)(warp * 32) << 16);
+        for (int c = 0; c < 128; c += 32) {
+            float v[32];
+            tmem_ld32(base + c, v);
+            tmem_ld_wait();
+            const int row = 128 * (int)rank + 32 * warp + lane;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) out[row * 128 + c + i] = v[i];
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_ptr), "r"(128u) : "memory");
+    }
+}
+
+static cudaError_t run_2cta_probe(double* result_host, cudaStream_t stream) {
+    float* out = nullptr;
+    cudaError_t e = cudaMalloc(&out, 256 * 128 * sizeof(float));
+    if (e != cudaSuccess) return e;
+    cudaMemsetAsync(out, 0xff, 256 * 128 * sizeof(float), stream);
+    cudaFuncSetAttribute(umma_2cta_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2, 1, 1);
+    cfg.blockDim = dim3(128, 1, 1);
+    cfg.dynamicSmemBytes = 32768;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, umma_2cta_probe_kernel, out);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e == cudaSuccess) {
+        static float host[256 * 128];
+        e = cudaMemcpy(host, out, sizeof(host), cudaMemcpyDeviceToHost);
+        long bad = 0;
+        for (int r = 0; r < 256 && e == cudaSuccess; ++r)
+            for (int n = 0; n < 128; ++n) {
+                const float want = ((float)(r % 7 + 1) / 8.0f) * ((float)(n % 5 + 1) / 4.0f);
+                if (!(host[r * 128 + n] == want)) ++bad;
+            }
+        result_host[0] = (double)bad;
+        result_host[1] = 256.0 * 128.0;
+    }
+    cudaFree(out);
+    return e;
+}
+
 cudaError_t run_microbench(int which, int warps, int iters, int num_sms, double* result_host, cudaStream_t stream) {
+    if (which == 7) return run_2cta_probe(result_host, stream);
     const int warps_raw = warps;
     if (warps < 4) warps = 4;
     if (warps > 32) warps = 32;
