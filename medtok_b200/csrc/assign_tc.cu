@@ -55,24 +55,32 @@ constexpr int kThreads    = 28 * 32;
 constexpr int kPlaneBytes = kTileRows * 16;          // 2048
 constexpr int kKblkBytes  = 8 * kPlaneBytes;         // 16384: 64 fp16 per row
 constexpr int kBiasBytes  = 2 * kPlaneBytes;         // 4096
-constexpr int kDataStages = 4;
 constexpr int kBiasStages = 3;
 constexpr int kMinSplitChunks = 2;                   // COLLECT: fewest 128-code chunks per (row block, range) item
 constexpr int kItemLoadCost   = 6;                   // COLLECT: an item's A-tile load + pipeline fill, in chunk-times
-constexpr int kRecords    = 1024;                    // 512 epilogue threads x up to 2 row tiles each
+constexpr int kRecords    = 1024;                    // records per CTA in the TOPK global scratch (fixed layout)
 
-// dynamic shared memory map
-constexpr int kOffA      = 0;                                    // RT tiles, <= 64 KB in total
-constexpr int kOffOnes   = 65536;
-constexpr int kOffBData  = kOffOnes + kBiasBytes;
-constexpr int kOffBBias  = kOffBData + kDataStages * kKblkBytes;
-constexpr int kOffSlots  = kOffBBias + kBiasStages * kBiasBytes;  // 4 chunks x 1024 records x 16 B (fp16 granules)
-constexpr int kOffState  = kOffSlots + 4 * kRecords * 16;         // 1024 records x 16 B
-constexpr int kOffBars   = kOffState + kRecords * 16;
-constexpr int kNumBars   = 2 * kDataStages + 2 * kBiasStages + 4 + 4 + 4 + 4;
-constexpr int kOffTmem   = kOffBars + kNumBars * 8;
-constexpr int kSmemBytes = kOffTmem + 16;
-static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
+// Dynamic shared memory map.  It depends on the row tiles per block: with RT = 4 (D <= 64) 512 epilogue threads keep two
+// state sets each (1024 records); with RT = 1 (D > 128) one -- the 40 KB that frees go to two more codebook stages.
+// The codebook ring is what hides the L2 latency of the stream: a D = 256 chunk fills four stages, so with a 4-stage
+// ring the tensor pipe waits for every reload (measured 0.60 of peak, 0.67 with six stages).
+// RT = 2 (D = 128) keeps the 4-stage map: six stages measured 2-12 % SLOWER there.
+template <int RT>
+struct SmemMap {
+    static constexpr int kStages   = (RT == 1) ? 6 : 4;                  // codebook K-block stages of 16 KB
+    static constexpr int kRec      = (RT == 1) ? 512 : 1024;             // epilogue threads x state sets
+    static constexpr int kOffA     = 0;                                  // RT tiles, <= 64 KB in total
+    static constexpr int kOffOnes  = 65536;
+    static constexpr int kOffBData = kOffOnes + kBiasBytes;
+    static constexpr int kOffBBias = kOffBData + kStages * kKblkBytes;
+    static constexpr int kOffSlots = kOffBBias + kBiasStages * kBiasBytes;   // 4 chunks x kRec records x 16 B (fp16 granules)
+    static constexpr int kOffState = kOffSlots + 4 * kRec * 16;              // kRec records x 16 B
+    static constexpr int kOffBars  = kOffState + kRec * 16;
+    static constexpr int kNumBars  = 2 * kStages + 2 * kBiasStages + 4 + 4 + 4 + 4;
+    static constexpr int kOffTmem  = kOffBars + kNumBars * 8;
+    static constexpr int kSmemBytes = kOffTmem + 16;
+    static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
+};
 
 struct Bars {
     uint64_t* bd_full;   // [kDataStages]
@@ -85,11 +93,12 @@ struct Bars {
     uint64_t* acc_empty; // [4]
 };
 
+template <int RT>
 __device__ __forceinline__ Bars carve_bars(unsigned char* smem) {
-    uint64_t* b = reinterpret_cast<uint64_t*>(smem + kOffBars);
+    uint64_t* b = reinterpret_cast<uint64_t*>(smem + SmemMap<RT>::kOffBars);
     Bars r;
-    r.bd_full = b;                 b += kDataStages;
-    r.bd_empty = b;                b += kDataStages;
+    r.bd_full = b;                 b += SmemMap<RT>::kStages;
+    r.bd_empty = b;                b += SmemMap<RT>::kStages;
     r.bb_full = b;                 b += kBiasStages;
     r.bb_empty = b;                b += kBiasStages;
     r.a_full = b;                  b += 4;
@@ -128,6 +137,7 @@ __device__ __forceinline__ void topn_insert(float (&t)[NTOP], float x) {
 
 // record = the 32 scores of a row's best granule, kept as fp16 (64 B) in chunk-major order so that a warp's
 // 16-byte stores are contiguous (conflict free).  fp16 is relative, the final scan widens its threshold.
+template <int REC>
 __device__ __forceinline__ void record_store(unsigned char* slots, int rec, const float (&v)[32]) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -138,7 +148,7 @@ __device__ __forceinline__ void record_store(unsigned char* slots, int rec, cons
         uint4 q;
         q.x = *reinterpret_cast<uint32_t*>(&h0); q.y = *reinterpret_cast<uint32_t*>(&h1);
         q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
-        *reinterpret_cast<uint4*>(slots + (c * kRecords + rec) * 16) = q;
+        *reinterpret_cast<uint4*>(slots + (c * REC + rec) * 16) = q;
     }
 }
 
@@ -218,7 +228,7 @@ __device__ __forceinline__ void consume(const float (&v)[32], int chunk, RowStat
 // `vb` granule `chunk + 1`.  Per thread the best granule is kept by value (the record), the second-best by id
 // (chunk2; listed wholesale for the exact re-scoring if it ends up within the margin) and everything else only as
 // a maximum (m3; if THAT ends up within the margin the row falls back to a COLLECT pass).
-template <int NTOP>
+template <int NTOP, int REC>
 __device__ __forceinline__ void consume_argmax64(const float (&va)[32], const float (&vb)[32], int chunk,
                                                  RowState<NTOP>& st, float margin, unsigned char* slots, int rec,
                                                  float* pub, const float* partner) {
@@ -245,8 +255,8 @@ __device__ __forceinline__ void consume_argmax64(const float (&va)[32], const fl
                 st.m1 = cmax;
                 *pub = cmax;
                 st.thr = fmaxf(nthr, other - margin);
-                if (b_wins) { st.best_chunk = chunk + 1; record_store(slots, rec, vb); }
-                else        { st.best_chunk = chunk;     record_store(slots, rec, va); }
+                if (b_wins) { st.best_chunk = chunk + 1; record_store<REC>(slots, rec, vb); }
+                else        { st.best_chunk = chunk;     record_store<REC>(slots, rec, va); }
             } else {                      // rare: granule(s) within the margin of the record (or of the other half's best)
                 if (cmax > st.m2) { st.m3 = fmaxf(fmaxf(st.m3, st.m2), lo); st.m2 = cmax; st.chunk2 = b_wins ? chunk + 1 : chunk; }
                 else              { st.m3 = fmaxf(st.m3, cmax); }
@@ -261,7 +271,7 @@ __device__ __forceinline__ void consume_argmax64(const float (&va)[32], const fl
 // granule id (shared memory) and the 32 scores as an fp16 record (global scratch).  A granule can only matter if its
 // maximum is within the margin of the row's final k-th largest granule maximum, and that is at least the thread's own
 // k-th best so far: the trigger `cmax >= thr`, thr = top[k-1] - margin, fires ~k/i of the time at the i-th granule.
-template <int KSTATIC>
+template <int KSTATIC, int REC>
 __device__ __forceinline__ void consume_topk(const float (&v)[32], int gran, float (&top)[kTopSlots], float& thr, int kidx,
                                              float margin, uint4* rec_base, uint16_t* gid, float4* pub, const float4* partner) {
     const float cmax = max32(v);
@@ -273,7 +283,7 @@ __device__ __forceinline__ void consume_topk(const float (&v)[32], int gran, flo
             const int slot = __float_as_int(top[kTopSlots - 1]) & 7;
             const float x = __int_as_float((__float_as_int(cmax) & ~7) | slot);
             record_store_g(rec_base + slot * (4 * kRecords), v);
-            gid[slot * kRecords] = (uint16_t)gran;
+            gid[slot * REC] = (uint16_t)gran;
             topn_insert<kTopSlots>(top, x);
             // Lower bound on the ROW's k-th largest granule maximum: the thread's own k-th, or what the thread that
             // owns the other column half has published (its values only grow, so a stale read is still a bound);
@@ -312,12 +322,13 @@ __device__ __forceinline__ int scan_record_g(const uint4* src, float ts, int col
 }
 
 // scan one fp16 record for columns >= ts; optionally write them to dst[n...] (capacity cap)
+template <int REC>
 __device__ __forceinline__ int scan_record(const unsigned char* slots, int rec, float ts, int col0, int* last_col,
                                            int* dst, int n0, int cap) {
     int n = 0;
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) {
-        const uint4 q = *reinterpret_cast<const uint4*>(slots + (cc * kRecords + rec) * 16);
+        const uint4 q = *reinterpret_cast<const uint4*>(slots + (cc * REC + rec) * 16);
         const uint32_t wds[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -334,6 +345,10 @@ __device__ __forceinline__ int scan_record(const unsigned char* slots, int rec, 
 template <int RT, int MODE, int NTOP, bool DBG>
 __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
+    using SM = SmemMap<RT>;
+    constexpr int kDataStages = SM::kStages;
+    constexpr int kOffA = SM::kOffA, kOffOnes = SM::kOffOnes, kOffBData = SM::kOffBData, kOffBBias = SM::kOffBBias;
+    constexpr int kOffSlots = SM::kOffSlots, kOffState = SM::kOffState, kOffTmem = SM::kOffTmem;
     // thread id through a volatile read: ptxas otherwise re-derives warp/lane (S2R + shifts) inside the hot loops
     uint32_t tid_x;
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid_x));
@@ -378,7 +393,7 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
     const bool use_bias = !(DBG && (p.debug_flags & 2)) &&
                           (MODE == MODE_DUMP || p.k != p.kpad || !(p.meta[META_SPREAD] <= kBiasSkipTol));
 
-    Bars bars = carve_bars(smem);
+    Bars bars = carve_bars<RT>(smem);
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kOffTmem);
 
     // ---- one-time setup ------------------------------------------------------------------------
@@ -516,15 +531,15 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                     if (DBG && tracing && si == 0 && uses[0] <= 512) p.trace[(uses[0] - 1) * 8 + 3] = clock64();
                     if (DBG && (p.debug_flags & 1)) continue;    // timing experiment: no epilogue work
                     if (MODE == MODE_ARGMAX) {
-                        consume_argmax64<NLIST>(va, vb, c * 4 + half2, st[ss], margin, slots, ss * 512 + rec0,
+                        consume_argmax64<NLIST, SM::kRec>(va, vb, c * 4 + half2, st[ss], margin, slots, ss * 512 + rec0,
                                                 &state[ss * 512 + rec0].x, &state[ss * 512 + (rec0 ^ 128)].x);
                     } else if (MODE == MODE_TOPK) {
                         if constexpr (NLIST == kTopSlots) {
                             constexpr int KS = (NTOP == 5) ? 5 : 0;
-                            consume_topk<KS>(va, c * 4 + half2, st[ss].top, st[ss].thr, kidx, margin_k,
+                            consume_topk<KS, SM::kRec>(va, c * 4 + half2, st[ss].top, st[ss].thr, kidx, margin_k,
                                              topk_rec + ss * 1024, topk_gid + ss * 512, state + ss * 512 + rec0,
                                              state + ss * 512 + (rec0 ^ 128));
-                            consume_topk<KS>(vb, c * 4 + half2 + 1, st[ss].top, st[ss].thr, kidx, margin_k,
+                            consume_topk<KS, SM::kRec>(vb, c * 4 + half2 + 1, st[ss].top, st[ss].thr, kidx, margin_k,
                                              topk_rec + ss * 1024, topk_gid + ss * 512, state + ss * 512 + rec0,
                                              state + ss * 512 + (rec0 ^ 128));
                         }
@@ -576,7 +591,7 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                                 const int w2 = quarter + 4 * hh + 8 * ((RT == 1) ? pp : pair);
                                 const int rec = ss * 512 + w2 * 32 + lane;
                                 const float4 sv = state[rec];
-                                if (sv.x >= thrF) cnt += scan_record(slots, rec, thrS, (__float_as_int(sv.z) & 0xffff) * kChunk, &col, nullptr, 0, 0);
+                                if (sv.x >= thrF) cnt += scan_record<SM::kRec>(slots, rec, thrS, (__float_as_int(sv.z) & 0xffff) * kChunk, &col, nullptr, 0, 0);
                                 if (sv.y >= thrF) ++nsec;
                             }
                         // near-tie row: more than one column (or an unrecorded granule) within the margin of the best
@@ -596,7 +611,7 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                                     const int rec = ss * 512 + w2 * 32 + lane;
                                     const float4 sv = state[rec];
                                     int dummy;
-                                    if (sv.x >= thrF) nw += scan_record(slots, rec, thrS, (__float_as_int(sv.z) & 0xffff) * kChunk, &dummy, dst, nw, p.cand_cap);
+                                    if (sv.x >= thrF) nw += scan_record<SM::kRec>(slots, rec, thrS, (__float_as_int(sv.z) & 0xffff) * kChunk, &dummy, dst, nw, p.cand_cap);
                                     if (sv.y >= thrF) { dst[nw] = -((__float_as_int(sv.z) >> 16) + 1); ++nw; }
                                 }
                             p.cand_cnt[st[ss].row] = nw;
@@ -638,7 +653,7 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                 named_bar_sync(bar_id, bar_n);
             } else if (MODE == MODE_TOPK) {
                 if constexpr (NLIST == kTopSlots) {
-                float* tl = reinterpret_cast<float*>(smem + kOffSlots + 2 * kTopSlots * kRecords);   // [record][8], after the ids
+                float* tl = reinterpret_cast<float*>(smem + SM::kOffSlots + 2 * kTopSlots * SM::kRec);   // [record][8], after the ids
 #pragma unroll
                 for (int ss = 0; ss < NS; ++ss) {
                     float4* t4 = reinterpret_cast<float4*>(tl + (ss * 512 + rec0) * 8);
@@ -684,7 +699,7 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                                         if (!(e >= thrG)) break;
                                         if (i == kTopSlots - 1) over = true;     // an untracked granule may qualify too
                                         const int slot = __float_as_int(e) & 7;
-                                        const int gran = gid_all[slot * kRecords + rec];
+                                        const int gran = gid_all[slot * SM::kRec + rec];
                                         nw += scan_record_g(rec_cta + (slot * 4) * kRecords + 2 * rec, thrS, gran * kChunk, dst, nw,
                                                             p.cand_cap);
                                     }
@@ -826,19 +841,20 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
         // ---------------------------------- B PRODUCER ------------------------------------------
         if (elect_one()) {
             const unsigned char* img = static_cast<const unsigned char*>(p.b_image);
-            uint32_t itD = 0, itB = 0;
+            uint32_t itB = 0;
+            uint32_t st = 0, ph = 0;      // ring position and phase, advanced per K-block (the ring need not be a power of 2)
             for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
                 const int cbeg = (MODE == MODE_COLLECT) ? (item % ksplit) * cps : 0;
                 const int cend = min(nchunks, cbeg + cps);
                 for (int c = cbeg; c < cend; ++c) {
                     const unsigned char* tile = img + (size_t)c * tile_b;
-                    for (int kb = 0; kb < nkblk; ++kb, ++itD) {
-                        const int st = itD % kDataStages;
+                    for (int kb = 0; kb < nkblk; ++kb) {
                         const uint32_t bytes = (uint32_t)min(8, nplanes - 8 * kb) * kPlaneBytes;
-                        mbar_wait(&bars.bd_empty[st], ((itD / kDataStages) & 1) ^ 1);
+                        mbar_wait(&bars.bd_empty[st], ph ^ 1);
                         mbar_arrive_expect_tx(&bars.bd_full[st], bytes);
                         bulk_g2s(smem + kOffBData + st * kKblkBytes, tile + (size_t)kb * kKblkBytes, bytes,
                                  &bars.bd_full[st]);
+                        if (++st == (uint32_t)kDataStages) { st = 0; ph ^= 1; }
                     }
                     if (use_bias) {
                         const int sb = itB % kBiasStages;
@@ -868,6 +884,7 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
             const uint64_t dBB0 = umma_smem_desc(smem_u32(smem + kOffBBias), lbo, sbo);
             const uint32_t tacc = tmem_base + (uint32_t)(j * kTileCodes);
             uint32_t uses = 0, bi = 0;
+            uint32_t dst0 = 0, dph0 = 0;             // codebook ring position / phase of the next chunk's first K-block
             uint32_t chunk0 = 0;                     // chunks issued by the CTA before this block
             const bool tracing = DBG && (p.trace != nullptr) && blockIdx.x == 0 && j == 0;
             int cbeg = 0, cend = nchunks;
@@ -882,15 +899,21 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                 for (int c = cbeg; c < cend; ++c) {
                     const bool own = (c % G) == (j / RT);
                     const uint32_t gc = chunk0 + (uint32_t)(c - cbeg);    // running chunk number
-                    const uint32_t itD = gc * nkblk;
                     const uint32_t sb = gc % kBiasStages;
+                    // this chunk's K-blocks occupy ring positions dst0, dst0 + 1, ... (wrapping, phase flips at the wrap)
+                    const uint32_t cst = dst0, cph = dph0;
+                    auto next_stage = [&](uint32_t& st_, uint32_t& ph_) { if (++st_ == (uint32_t)kDataStages) { st_ = 0; ph_ ^= 1; } };
                     // operands first, accumulator last: when the epilogue hands the slot back, every MMA of
                     // the tile is issued back to back
-                    for (int kb = 0; kb < nkblk; ++kb)
-                        mbar_wait(&bars.bd_full[(itD + kb) % kDataStages], ((itD + kb) / kDataStages) & 1);
+                    {
+                        uint32_t st_ = cst, ph_ = cph;
+                        for (int kb = 0; kb < nkblk; ++kb) { mbar_wait(&bars.bd_full[st_], ph_); next_stage(st_, ph_); }
+                        dst0 = st_; dph0 = ph_;
+                    }
                     if (use_bias) mbar_wait(&bars.bb_full[sb], (gc / kBiasStages) & 1);
                     if (!own) {
-                        for (int kb = 0; kb < nkblk; ++kb) mbar_arrive(&bars.bd_empty[(itD + kb) % kDataStages]);
+                        uint32_t st_ = cst, ph_ = cph;
+                        for (int kb = 0; kb < nkblk; ++kb) { mbar_arrive(&bars.bd_empty[st_]); next_stage(st_, ph_); }
                         if (use_bias) mbar_arrive(&bars.bb_empty[sb]);
                         continue;
                     }
@@ -899,8 +922,8 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                     if (DBG && tracing && uses < 512) p.trace[uses * 8 + 0] = clock64();
                     ++uses;
                     tc_fence_after();
+                    uint32_t st = cst, sph = cph;
                     for (int kb = 0; kb < nkblk; ++kb) {
-                        const uint32_t st = (itD + kb) % kDataStages;
                         const int nsteps = min(8, nplanes - 8 * kb) >> 1;
                         uint64_t da = dA + (uint64_t)(kb * (kKblkBytes >> 4));
                         uint64_t db = dBD0 + (uint64_t)(st * (kKblkBytes >> 4));
@@ -910,6 +933,7 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                             db += (2 * kPlaneBytes) >> 4;
                         }
                         umma_commit(&bars.bd_empty[st]);
+                        next_stage(st, sph);
                     }
                     if (use_bias) umma_f16(tacc, dOnes, dBB0 + (uint64_t)(sb * (kBiasBytes >> 4)), idesc, 1u);
                     umma_commit(&bars.acc_full[j]);
@@ -945,11 +969,11 @@ static cudaError_t launch_one(const CoarseParams& p, int grid, cudaStream_t stre
     static PerDeviceOnce once;         // one per instantiation and device
     bool& configured = once.flag();
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemMap<RT>::kSmemBytes);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    kern<<<grid, kThreads, kSmemBytes, stream>>>(p);
+    kern<<<grid, kThreads, SmemMap<RT>::kSmemBytes, stream>>>(p);
     ++g_kernel_launches;
     return cudaGetLastError();
 }
@@ -994,6 +1018,6 @@ cudaError_t launch_coarse(const CoarseParams& p, int mode, int row_tiles, int nu
     return cudaErrorInvalidValue;
 }
 
-int coarse_smem_bytes() { return kSmemBytes; }
+int coarse_smem_bytes() { return SmemMap<4>::kSmemBytes > SmemMap<1>::kSmemBytes ? SmemMap<4>::kSmemBytes : SmemMap<1>::kSmemBytes; }
 
 }  // namespace mtvq
