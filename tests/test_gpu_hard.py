@@ -228,3 +228,38 @@ def test_full_size_config2_properties(oracle, dev):
     assert abs(float(loss) - ref_loss) <= 1e-5 * ref_loss
     assert cnt["full_scan_rows"] == 0
     print("config2 near-tie rows:", cnt)
+
+
+def test_full_size_clustered_zipf_properties(dev):
+    """SURVEY 8d second distribution at config-2 size: z = l2norm(C[j] + 0.1 randn), j ~ Zipf(1.5) over K (heavily skewed
+    bins, thousands of dead codes, many near-ties around the popular codes): tensor-core path == exact CUDA-core kernel on
+    every row, histogram / dead-code / unit-norm invariants of the EMA update."""
+    from medtok_b200 import _lib
+    from medtok_b200.norm_ema_quantizer import NormEMAVectorQuantizer, hard_assign
+    n, d, k = 1 << 20, 64, 8192
+    g = torch.Generator().manual_seed(11)
+    w = torch.nn.functional.normalize(torch.randn(k, d, generator=g), dim=-1)
+    ranks = torch.arange(1, k + 1, dtype=torch.float64)
+    pz = (1.0 / ranks ** 1.5)
+    j = torch.multinomial(pz / pz.sum(), n, replacement=True, generator=g)
+    z = torch.nn.functional.normalize(w[j] + 0.1 * torch.randn(n, d, generator=g), dim=-1)
+    zd, wd = z.to(dev), w.to(dev)
+    q = NormEMAVectorQuantizer(k, d, 0.25).to(dev).train()
+    q.embedding.weight.data.copy_(wd)
+    with torch.no_grad():
+        z_q, loss, idx = q(zd.view(n, d, 1, 1))
+    cnt = _lib.debug_counters(q._ws.buf, n, d, k)
+    idx_x, _ = hard_assign(zd, wd, exact=True)
+    mism = (idx != idx_x).nonzero().flatten()
+    assert mism.numel() == 0, f"{mism.numel()} rows differ from the exact kernel, first {mism[:8].tolist()}"
+    bins = torch.bincount(idx, minlength=k).double()
+    assert torch.equal(q.last_stats[:k], bins) and int(bins.sum()) == n
+    assert (idx.cpu() == j).float().mean().item() > 0.95                     # rows land on their own cluster centre
+    dead = bins == 0
+    assert int(dead.sum()) > 100                                             # the Zipf tail leaves many codes unused
+    assert torch.allclose(q.embedding.weight[dead], wd[dead], atol=2e-7)     # dead codes keep their row
+    assert (q.embedding.weight.norm(dim=-1) - 1).abs().max().item() < 1e-6
+    assert torch.equal(q.cluster_size, (0.01 * bins).float()) or torch.allclose(q.cluster_size, (0.01 * bins).float(), rtol=1e-6)
+    ref_loss = 0.25 * ((wd[idx] - zd).double() ** 2).mean().item()
+    assert abs(float(loss) - ref_loss) <= 1e-5 * ref_loss
+    print("clustered/Zipf counters:", cnt, "dead codes:", int(dead.sum()))
