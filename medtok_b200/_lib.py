@@ -12,7 +12,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libmedtok_vq.so")
+SO_PATH = os.environ.get("MEDTOK_VQ_LIB") or os.path.join(_HERE, "libmedtok_vq.so")   # override: A/B timing of two builds
 
 NORM_CONTIGUOUS = 0
 NORM_STRIDED = 1
