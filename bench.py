@@ -121,13 +121,13 @@ def synth_inputs(n, d, k, seed, device=None):
 # --------------------------------------------------------------------------------------------------
 # CPU arm: the reference's own CPU path (pure PyTorch -> its ATen port in oracle/torch_port.py)
 # --------------------------------------------------------------------------------------------------
-def cpu_port_throughput(sample_rows, steps=1, warmup=0, budget_s=20.0):
+def cpu_port_throughput(sample_rows, steps=1, warmup=0, budget_s=20.0, d=DIM, k=CODES):
     from oracle import torch_port
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    z, w = synth_inputs(sample_rows, DIM, CODES, seed=0)
-    z4 = z.view(sample_rows, DIM, 1, 1)
-    cs = torch.zeros(CODES)
+    z, w = synth_inputs(sample_rows, d, k, seed=0)
+    z4 = z.view(sample_rows, d, 1, 1)
+    cs = torch.zeros(k)
     times = []
     for i in range(warmup + steps):
         wi = w.clone()
@@ -181,7 +181,7 @@ def run_ours(args):
     from medtok_b200.host_pipeline import HostStream
     from medtok_b200.norm_ema_quantizer import NormEMAVectorQuantizer
 
-    n, d, k = N_ROWS, DIM, CODES
+    n, d, k = args.rows or N_ROWS, args.dim or DIM, args.codes or CODES      # defaults = BASELINE config 2
     # two different input batches (2 x 256 MiB > 126 MB L2), alternated so no step re-reads cached rows
     zs = [synth_inputs(n, d, k, seed=100 * rank + i, device=dev)[0].view(n, d, 1, 1) for i in range(2)]
     _, w0 = synth_inputs(8, d, k, seed=0, device=dev)
@@ -251,7 +251,9 @@ def run_ours(args):
             "ms_per_step": elapsed_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"BASELINE config 2: hard argmin + norm-EMA update, N={n} rows/GPU, D={d}, K={k}",
+            "config": {"workload": (f"BASELINE config 2: hard argmin + norm-EMA update, N={n} rows/GPU, D={d}, K={k}"
+                                    if (n, d, k) == (N_ROWS, DIM, CODES) else
+                                    f"config-5 sweep point: hard argmin + norm-EMA update, N={n} rows/GPU, D={d}, K={k}"),
                        "arithmetic": "results are the reference's fp32 results (exact re-scoring in reference order); the "
                                      "tcgen05 candidate pass uses fp16 operands with fp32 accumulation",
                        "rows_per_gpu": n, "dim": d, "codes": k, "parallelism": f"rows sharded x{world}, codebook replicated",
@@ -271,7 +273,7 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu:
             # bounded CPU sample of the same workload on this box's host cores (rank 0, N=1 only)
-            val, per, threads, done = cpu_port_throughput(32768, steps=2, warmup=0, budget_s=25.0)
+            val, per, threads, done = cpu_port_throughput(32768, steps=2, warmup=0, budget_s=25.0, d=d, k=k)
             line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{done} x 32768 rows (D={d}, K={k}), ATen port of the reference forward"}
         print(json.dumps(line))
@@ -365,6 +367,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--rows", type=int, default=0, help="rows per GPU (config-5 sweep points; default 2^20)")
+    ap.add_argument("--dim", type=int, default=0, help="embedding dim (default 64)")
+    ap.add_argument("--codes", type=int, default=0, help="codebook size (default 8192)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
                     help="c2 = BASELINE config 2 (headline: hard argmin + EMA); c3 = config 3 (soft top-5 forward)")
     args = ap.parse_args()
