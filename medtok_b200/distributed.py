@@ -64,10 +64,13 @@ class PeerExchange:
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.numel = numel
-        try:
-            symm_mem.enable_symm_mem_for_group(group.group_name)
-        except Exception:
-            pass                                                   # newer torch enables groups lazily
+        import warnings
+        with warnings.catch_warnings():                            # newer torch enables groups lazily and deprecates this
+            warnings.simplefilter("ignore")
+            try:
+                symm_mem.enable_symm_mem_for_group(group.group_name)
+            except Exception:
+                pass
         self.stats = [symm_mem.empty(numel, dtype=torch.float64, device=device) for _ in range(2)]
         self.flags = symm_mem.empty(64, dtype=torch.int32, device=device)
         self._handles = [symm_mem.rendezvous(t, group) for t in (*self.stats, self.flags)]
