@@ -46,6 +46,10 @@ extern "C" {
  * (b c h w inputs with h*w > 1, normalised through rearrange's permuted view). */
 #define MTVQ_NORM_CONTIGUOUS 0
 #define MTVQ_NORM_STRIDED    1
+#define MTVQ_NORM_NONE       2      /* rows are used as given (already normalised by the caller): denom = 1 exactly */
+/* or-ed into norm_mode of mtvq_hard_assign[_exact]: rank the codes by the inner product z.w alone, first index on
+ * ties -- `dists = samples @ means.t(); dists.max(dim=-1).indices` of kmeans (norm_ema_quantizer.py:34,41) */
+#define MTVQ_SCORE_DOT       4
 
 /* flags for mtvq_hard_forward */
 #define MTVQ_F_TRAINING        1u   /* module.training                          (norm_ema_quantizer.py:185,191) */
@@ -60,8 +64,9 @@ extern "C" {
 MTVQ_API int mtvq_abi_version(void);
 MTVQ_API const char * mtvq_last_error(void);
 
-/* Bytes of caller-provided scratch needed by the calls below for up to n rows, dim d, k codes
- * (top-k `topk` for the soft path, 1 for the hard path). */
+/* Bytes of caller-provided scratch needed by the calls below for up to n rows, dim d, k codes:
+ * topk = 0 for the hard-path calls, topk = the soft path's top-k (1..8) for mtvq_soft_forward (a soft
+ * workspace also serves the hard-path calls). */
 MTVQ_API size_t mtvq_workspace_bytes(int64_t n, int d, int k, int topk);
 
 /* Number of doubles in the packed statistics buffer: [ bins(k) | embed_sum(k*d) | sse | rows ].
@@ -131,10 +136,14 @@ MTVQ_API int mtvq_gather_ste(const float *z, const float *denom, const float *we
 MTVQ_API int mtvq_code_sums(const float *z, const float *denom, const int64_t *idx, int64_t n, int d, int k,
                    double *stats, void *workspace, size_t workspace_bytes, void *stream);
 
+/* k-means centre update (kmeans, norm_ema_quantizer.py:43-54, cosine branch) from packed statistics of
+ * mtvq_code_sums: means_k <- l2norm(embed_sum_k / bins_k); a cluster without members keeps its centre. */
+MTVQ_API int mtvq_kmeans_update(float *means, const double *stats, int k, int d, void *stream);
+
 /* Lookup-only quantizer, VectorQuantizer.forward of norm_ema_quantizer.py:222-268: z_q[n,d] = weight[idx]
  * (F.embedding :117-118,253).  z (raw rows, b h w c order) may be NULL; otherwise *sse (fp64, may be NULL) +=
  * sum (z_q - z)^2 for the loss of :262-264.  counts (fp32 [k], may be NULL) receives the per-code row counts the
- * eval branch feeds to the cluster-size EMA (:257-261); it needs a workspace of mtvq_workspace_bytes(n, d, k, 1). */
+ * eval branch feeds to the cluster-size EMA (:257-261); it needs a workspace of mtvq_workspace_bytes(n, d, k, 0). */
 MTVQ_API int mtvq_lookup(const float *z, const float *weight, const int64_t *idx, int64_t n, int d, int k,
                 float *z_q, double *sse, float *counts, void *workspace, size_t workspace_bytes, void *stream);
 

@@ -16,6 +16,8 @@ SO_PATH = os.environ.get("MEDTOK_VQ_LIB") or os.path.join(_HERE, "libmedtok_vq.s
 
 NORM_CONTIGUOUS = 0
 NORM_STRIDED = 1
+NORM_NONE = 2
+SCORE_DOT = 4
 F_TRAINING = 1
 F_UPDATE = 2
 F_SKIP_FINALIZE = 4
@@ -37,6 +39,7 @@ _SIGNATURES = {
     "mtvq_ema_finalize": (_int, [_vp, _vp, _vp, _int, _int, _dbl, _dbl, _int, _int, _vp, _vp]),
     "mtvq_ema_finalize_peers": (_int, [_vp, _vp, _vp, _vp, _int, _int, ctypes.c_uint, _int, _int, _dbl, _dbl, _int, _int,
                                        _vp, _vp]),
+    "mtvq_kmeans_update": (_int, [_vp, _vp, _int, _int, _vp]),
     "mtvq_hard_assign": (_int, [_vp, _i64, _int, _int, _vp, _int, _vp, _vp, _vp, _sz, _vp]),
     "mtvq_hard_assign_exact": (_int, [_vp, _i64, _int, _int, _vp, _int, _vp, _vp, _vp, _sz, _vp]),
     "mtvq_gather_ste": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _vp, _vp, _vp]),
@@ -84,6 +87,24 @@ def lib() -> ctypes.CDLL:
     return _LIB
 
 
+def on_tensor_device(fn):
+    """Decorator: the library launches on the CURRENT device (cudaGetDevice) while pointers and streams come from the
+    tensors, so make the device of the first CUDA tensor argument current around the call -- a module moved with
+    .to('cuda:1') then works whatever the process's current device is, like the PyTorch reference."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if a.device.index == torch.cuda.current_device():
+                    break
+                with torch.cuda.device(a.device):
+                    return fn(*args, **kwargs)
+        return fn(*args, **kwargs)
+    return wrapped
+
+
 def check(rc: int, what: str) -> None:
     if rc != 0:
         msg = lib().mtvq_last_error().decode(errors="replace")
@@ -129,7 +150,7 @@ def set_profile_events(before: "torch.cuda.Event | None", after: "torch.cuda.Eve
     check(lib().mtvq_debug_set_events(b, a), "mtvq_debug_set_events")
 
 
-def debug_counters(ws: torch.Tensor, n: int, d: int, k: int, topk: int = 1) -> dict:
+def debug_counters(ws: torch.Tensor, n: int, d: int, k: int, topk: int = 0) -> dict:
     out = (_i64 * 4)()
     check(lib().mtvq_debug_counters(ptr(ws), n, d, k, topk, out, stream_ptr(ws.device)), "mtvq_debug_counters")
     return {"near_tie_rows": out[0], "full_scan_rows": out[1], "candidates": out[2], "launches": out[3]}

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "_build")
 SO_PATH = os.path.join(HERE, "libmedtok_vq.so")
-SOURCES = ["api.cu", "assign_tc.cu", "assign_exact.cu", "rows.cu", "soft.cu", "microbench.cu"]
+SOURCES = ["api.cu", "assign_tc.cu", "assign_exact.cu", "rows.cu", "soft.cu", "small.cu", "microbench.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr"]
 
@@ -34,15 +34,22 @@ def _newest_dep():
     return t
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and os.path.exists(SO_PATH) and os.path.getmtime(SO_PATH) >= _newest_dep():
-        return SO_PATH
-    os.makedirs(OBJ_DIR, exist_ok=True)
+def build(force: bool = False, verbose: bool = False, variant: str = "", defines=()) -> str:
+    """`variant` + `defines` (-D flags) build an experimental copy into _build/variants/ for A/B timing
+    (tools_ab.py, MEDTOK_VQ_LIB); the product library is the default, flag-less build."""
+    so_path, obj_dir = SO_PATH, OBJ_DIR
+    if variant:
+        obj_dir = os.path.join(OBJ_DIR, "variants", variant)
+        so_path = os.path.join(OBJ_DIR, "variants", f"libmedtok_vq_{variant}.so")
+        force = True
+    if not force and os.path.exists(so_path) and os.path.getmtime(so_path) >= _newest_dep():
+        return so_path
+    os.makedirs(obj_dir, exist_ok=True)
     nvcc = _nvcc()
 
     def compile_one(src):
-        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, *defines, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -55,13 +62,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with concurrent.futures.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     # api.cu marks the exported symbols; everything else stays hidden
-    link = [nvcc, "-shared", "-o", SO_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
+    link = [nvcc, "-shared", "-o", so_path, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
             "-Xcompiler", "-fPIC", "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return SO_PATH
+    return so_path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    _variant = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else ""
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=_variant,
+                defines=[a for a in sys.argv[1:] if a.startswith("-D")]))

@@ -11,6 +11,7 @@
 #include "assign_tc.h"
 #include "microbench.h"
 #include "rows.h"
+#include "small.h"
 #include "soft.h"
 #include "workspace.h"
 
@@ -23,6 +24,7 @@ namespace {
 thread_local char g_err[512] = "";
 thread_local long long* g_trace = nullptr;
 thread_local int g_soft_route = 0;   // mtvq_debug_set_soft_route
+thread_local bool g_no_small = false; // mtvq_debug_set_soft_route(3): force the tensor route for small batches too
 thread_local cudaEvent_t g_ev_before = nullptr, g_ev_after = nullptr;
 
 int fail(int code, const char* fmt, const char* a = "", long b = 0, long c = 0) {
@@ -65,6 +67,11 @@ int device_info(DeviceInfo* out) {
     return 0;
 }
 
+int check_norm_mode(int norm_mode) {
+    if (norm_mode < 0 || (norm_mode & ~7) || (norm_mode & 3) == 3)
+        return fail(MTVQ_ERR_BAD_ARG, "norm_mode must be MTVQ_NORM_* optionally or-ed with MTVQ_SCORE_DOT%s (got %ld)", "", (long)norm_mode);
+    return 0;
+}
 int check_dims(int64_t n, int d, int k) {
     if (n < 0 || k <= 0 || d <= 0) return fail(MTVQ_ERR_BAD_ARG, "bad extents%s n=%ld k=%ld", "", (long)n, (long)k);
     if (d % 16 != 0 || d > kMaxDim)
@@ -81,13 +88,13 @@ bool desc_swap() {
 }
 
 void fill_coarse(CoarseParams& p, const float* z, int64_t n, int d, int norm_mode, int k, const Workspace& ws,
-                 float* denom, int topk, int64_t* idx_out = nullptr) {
+                 float* denom, int topk, bool soft, int64_t* idx_out = nullptr) {
     memset(&p, 0, sizeof(p));
     p.z = z; p.n = n; p.d = d; p.norm_mode = norm_mode;
     p.b_image = ws.b_image; p.kpad = pad_codes(k); p.k = k; p.meta = ws.meta;
     p.denom = denom; p.idx_out = idx_out; p.bins = ws.bins_i32; p.best_val = ws.best_val;
     p.flag_rows = ws.flag_rows; p.over_rows = ws.full_rows; p.counters = ws.counters;
-    p.cand = ws.cand; p.cand_cnt = ws.cand_cnt; p.cand_cap = cand_capacity(topk); p.topk = topk;
+    p.cand = ws.cand; p.cand_cnt = ws.cand_cnt; p.cand_cap = cand_capacity(soft); p.topk = topk;
     p.topk_scratch = ws.topk_scratch;
     p.trace = g_trace;
     p.lbo_bytes = desc_swap() ? 128 : 2048;
@@ -101,8 +108,16 @@ int assign_rows(const float* z, int64_t n, int d, int norm_mode, const float* co
                 const Workspace& ws, const DeviceInfo& di, bool exact_only, cudaStream_t st) {
     MTVQ_CUDA(cudaMemsetAsync(ws.counters, 0, sizeof(int) * CNT_COUNT, st), "memset counters");
     MTVQ_CUDA(cudaMemsetAsync(ws.bins_i32, 0, sizeof(int) * k, st), "memset bins");
-    MTVQ_CUDA(launch_codebook_prep(codes, k, d, 0, ws, st), "codebook_prep");
     if (n == 0) return 0;
+    if (!exact_only && small_route_ok(n, d, k) && !g_no_small) {
+        // small batch: every (row, code) distance directly in the reference's fp32 order (small.cu); no tensor pass
+        MTVQ_CUDA(launch_small_assign(z, n, d, norm_mode, codes, k, 0, 1, nullptr, ws.cc, denom, ws.small_part, nullptr,
+                                      nullptr, 0, idx, ws.bins_i32, ws.full_rows, ws.counters, st), "small_assign");
+        MTVQ_CUDA(launch_exact_scan(z, n, d, norm_mode, codes, k, ws.cc, ws.full_rows, ws.counters + CNT_FULL, idx,
+                                    ws.bins_i32, nullptr, di.num_sms, st), "exact_scan(NaN rows)");
+        return 0;
+    }
+    MTVQ_CUDA(launch_codebook_prep(codes, k, d, (norm_mode & MTVQ_SCORE_DOT) ? 2 : 0, ws, st), "codebook_prep");
     if (exact_only) {
         MTVQ_CUDA(launch_exact_scan(z, n, d, norm_mode, codes, k, ws.cc, nullptr, nullptr, idx, ws.bins_i32, denom,
                                     di.num_sms, st), "exact_scan");
@@ -110,7 +125,7 @@ int assign_rows(const float* z, int64_t n, int d, int norm_mode, const float* co
     }
     MTVQ_CUDA(cudaMemsetAsync(ws.cand_cnt, 0, sizeof(int) * n, st), "memset cand_cnt");
     CoarseParams p;
-    fill_coarse(p, z, n, d, norm_mode, k, ws, denom, 1, idx);
+    fill_coarse(p, z, n, d, norm_mode, k, ws, denom, 1, false, idx);
     if (g_ev_before) cudaEventRecord(g_ev_before, st);
     MTVQ_CUDA(launch_coarse(p, MODE_ARGMAX, coarse_row_tiles(d, n, di.num_sms), di.num_sms, st), "coarse argmax");
     if (g_ev_after) cudaEventRecord(g_ev_after, st);
@@ -138,19 +153,20 @@ const char* mtvq_last_error(void) { return g_err; }
 
 size_t mtvq_workspace_bytes(int64_t n, int d, int k, int topk) {
     if (n < 0 || d <= 0 || k <= 0) return 0;
-    return carve(nullptr, n, d, k, topk < 1 ? 1 : topk).total_bytes;
+    return carve(nullptr, n, d, k, topk < 0 ? 0 : topk).total_bytes;
 }
 size_t mtvq_stats_len(int d, int k) { return (size_t)k + (size_t)k * d + 2; }
 
 static int hard_assign_impl(const float* z, int64_t n, int d, int norm_mode, const float* weight, int k, int64_t* idx,
                             float* denom, void* workspace, size_t workspace_bytes, void* stream, bool exact_only) {
     if (int r = check_dims(n, d, k)) return r;
+    if (int r = check_norm_mode(norm_mode)) return r;
     if (!z || !weight || !idx || !workspace) return fail(MTVQ_ERR_BAD_ARG, "null pointer%s", "");
     if (!aligned16(z) || !aligned16(weight) || !aligned16(workspace))
         return fail(MTVQ_ERR_BAD_ARG, "z, weight and workspace must be 16-byte aligned%s", "");
     DeviceInfo di;
     if (int r = device_info(&di)) return r;
-    Workspace ws = carve(workspace, n, d, k, 1);
+    Workspace ws = carve(workspace, n, d, k, 0);
     if (ws.total_bytes > workspace_bytes)
         return fail(MTVQ_ERR_WORKSPACE, "workspace too small%s: need %ld, got %ld", "", (long)ws.total_bytes,
                     (long)workspace_bytes);
@@ -187,7 +203,7 @@ int mtvq_code_sums(const float* z, const float* denom, const int64_t* idx, int64
     if (!z || !denom || !idx || !stats || !workspace) return fail(MTVQ_ERR_BAD_ARG, "null pointer%s", "");
     DeviceInfo di;
     if (int r = device_info(&di)) return r;
-    Workspace ws = carve(workspace, n, d, k, 1);
+    Workspace ws = carve(workspace, n, d, k, 0);
     if (ws.total_bytes > workspace_bytes) return fail(MTVQ_ERR_WORKSPACE, "workspace too small%s", "");
     if (n > 0) {
         cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -206,6 +222,15 @@ int mtvq_ema_finalize(float* weight, float* cluster_size, const double* stats, i
     if (int r = device_info(&di)) return r;
     MTVQ_CUDA(launch_ema_finalize(weight, cluster_size, stats, k, d, beta, decay, update_cluster_size, update_weight, loss,
                                   static_cast<cudaStream_t>(stream)), "ema_finalize");
+    return 0;
+}
+
+int mtvq_kmeans_update(float* means, const double* stats, int k, int d, void* stream) {
+    if (int r = check_dims(0, d, k)) return r;
+    if (!means || !stats) return fail(MTVQ_ERR_BAD_ARG, "null pointer%s", "");
+    DeviceInfo di;
+    if (int r = device_info(&di)) return r;
+    MTVQ_CUDA(launch_kmeans_update(means, stats, k, d, static_cast<cudaStream_t>(stream)), "kmeans_update");
     return 0;
 }
 
@@ -228,13 +253,14 @@ int mtvq_hard_forward(const float* z, int64_t n, int d, int norm_mode, float* we
                       double beta, double decay, unsigned flags, float* z_q, int64_t* idx, float* loss, double* stats,
                       void* workspace, size_t workspace_bytes, void* stream) {
     if (int r = check_dims(n, d, k)) return r;
+    if (int r = check_norm_mode(norm_mode)) return r;
     if (!weight || !loss || !stats || !workspace || (n > 0 && (!z || !z_q || !idx)))
         return fail(MTVQ_ERR_BAD_ARG, "null pointer%s", "");
     if (!aligned16(z) || !aligned16(weight) || !aligned16(z_q) || !aligned16(workspace))
         return fail(MTVQ_ERR_BAD_ARG, "z, weight, z_q and workspace must be 16-byte aligned%s", "");
     DeviceInfo di;
     if (int r = device_info(&di)) return r;
-    Workspace ws = carve(workspace, n, d, k, 1);
+    Workspace ws = carve(workspace, n, d, k, 0);
     if (ws.total_bytes > workspace_bytes)
         return fail(MTVQ_ERR_WORKSPACE, "workspace too small%s: need %ld, got %ld", "", (long)ws.total_bytes,
                     (long)workspace_bytes);
@@ -276,7 +302,7 @@ int mtvq_lookup(const float* z, const float* weight, const int64_t* idx, int64_t
     if (n > 0) MTVQ_CUDA(launch_lookup(z, weight, idx, n, d, k, z_q, sse, di.num_sms, st), "lookup");
     if (counts) {
         if (!workspace) return fail(MTVQ_ERR_BAD_ARG, "counts need the workspace%s", "");
-        Workspace ws = carve(workspace, n, d, k, 1);
+        Workspace ws = carve(workspace, n, d, k, 0);
         if (ws.total_bytes > workspace_bytes) return fail(MTVQ_ERR_WORKSPACE, "workspace too small%s", "");
         MTVQ_CUDA(launch_hist_idx64(idx, n, ws.bins_i32, k, di.num_sms, st), "hist");
         MTVQ_CUDA(launch_counts_to_float(ws.bins_i32, k, counts, st), "counts");
@@ -311,11 +337,19 @@ int mtvq_soft_forward(const float* x, int64_t n, int d, const float* codes, int 
     if (ws.total_bytes > workspace_bytes) return fail(MTVQ_ERR_WORKSPACE, "workspace too small%s", "");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     MTVQ_CUDA(cudaMemsetAsync(ws.counters, 0, sizeof(int) * CNT_COUNT, st), "memset counters");
+    if (n > 0 && g_soft_route == 0 && !g_no_small && small_route_ok(n, d, k)) {
+        // small batch (MedTok's training batches): exact scores on the CUDA cores, k-way merge, then the usual row kernel
+        MTVQ_CUDA(launch_small_assign(x, n, d, MTVQ_NORM_CONTIGUOUS, codes, k, 1, topk, ws.codes_n, ws.cc, ws.denom,
+                                      ws.small_part, ws.cand, ws.cand_cnt, cand_capacity(true), nullptr, nullptr, nullptr,
+                                      ws.counters, st), "small_assign");
+        MTVQ_CUDA(launch_soft_resolve(x, n, d, k, topk, ws, idx, vals, wts, zq, out, sse, di.num_sms, st), "soft_resolve");
+        return 0;
+    }
     MTVQ_CUDA(launch_codebook_prep(codes, k, d, 1, ws, st), "codebook_prep(normalise)");
     if (n == 0) return 0;
     MTVQ_CUDA(cudaMemsetAsync(ws.cand_cnt, 0, sizeof(int) * n, st), "memset cand_cnt");
     CoarseParams p;
-    fill_coarse(p, x, n, d, MTVQ_NORM_CONTIGUOUS, k, ws, ws.denom, topk);
+    fill_coarse(p, x, n, d, MTVQ_NORM_CONTIGUOUS, k, ws, ws.denom, topk, true);
     const int rt = coarse_row_tiles(d, n, di.num_sms);
     // ONE tensor pass: every thread tracks its best granules (scores kept as fp16 records in an L2-resident scratch)
     // and the row block's end turns them into the per-row candidate lists.  Rows whose tracking overflowed (more than
@@ -387,7 +421,7 @@ int mtvq_soft_backward_fused(const float* x, int64_t n, int d, const float* code
 
 int mtvq_debug_counters(const void* workspace, int64_t n, int d, int k, int topk, int64_t* out_host, void* stream) {
     if (!workspace || !out_host) return fail(MTVQ_ERR_BAD_ARG, "null pointer%s", "");
-    Workspace ws = carve(const_cast<void*>(workspace), n, d, k, topk < 1 ? 1 : topk);
+    Workspace ws = carve(const_cast<void*>(workspace), n, d, k, topk < 0 ? 0 : topk);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int h[CNT_COUNT] = {0};
     cudaError_t e = cudaMemcpyAsync(h, ws.counters, sizeof(h), cudaMemcpyDeviceToHost, st);
@@ -407,7 +441,7 @@ int mtvq_debug_coarse_scores(const float* z, int64_t n, int d, int norm_mode, co
     if (int r = check_dims(n, d, k)) return r;
     DeviceInfo di;
     if (int r = device_info(&di)) return r;
-    Workspace ws = carve(workspace, n, d, k, 1);
+    Workspace ws = carve(workspace, n, d, k, 0);
     if (ws.total_bytes > workspace_bytes) return fail(MTVQ_ERR_WORKSPACE, "workspace too small%s", "");
     if (kpad_host) *kpad_host = pad_codes(k);
     if (!scores) return 0;
@@ -415,7 +449,7 @@ int mtvq_debug_coarse_scores(const float* z, int64_t n, int d, int norm_mode, co
     MTVQ_CUDA(cudaMemsetAsync(ws.counters, 0, sizeof(int) * CNT_COUNT, st), "memset counters");
     MTVQ_CUDA(launch_codebook_prep(weight, k, d, 0, ws, st), "codebook_prep");
     CoarseParams p;
-    fill_coarse(p, z, n, d, norm_mode, k, ws, ws.denom, 1);
+    fill_coarse(p, z, n, d, norm_mode, k, ws, ws.denom, 1, false);
     p.dump = scores;
     p.dump_rows = rows < n ? rows : n;
     const char* rt_env = getenv("MTVQ_DEBUG_ROW_TILES");
@@ -427,7 +461,9 @@ int mtvq_debug_coarse_scores(const float* z, int64_t n, int d, int norm_mode, co
 }
 
 int mtvq_debug_set_soft_route(int route) {
-    if (route < 0 || route > 2) return fail(MTVQ_ERR_BAD_ARG, "route must be 0, 1 or 2%s", "");
+    if (route < 0 || route > 4) return fail(MTVQ_ERR_BAD_ARG, "route must be 0..4%s", "");
+    if (route == 3) { g_no_small = true; return 0; }      // 3: small batches take the tensor route too (A/B, tests)
+    if (route == 4) { g_no_small = false; return 0; }     // 4: back to automatic
     g_soft_route = route;
     return 0;
 }

@@ -13,13 +13,15 @@ namespace mtvq {
 // ------------------------------------------------------------------------------------------------
 // codebook prep (one thread per code; K*D is tiny next to N*K*D)
 // ------------------------------------------------------------------------------------------------
-__global__ void codebook_prep_kernel(const float* __restrict__ w, int k, int kpad, int d, int normalize,
+__global__ void codebook_prep_kernel(const float* __restrict__ w, int k, int kpad, int d, int flags,
                                      unsigned char* __restrict__ image, float* __restrict__ cc,
                                      float* __restrict__ codes_n, float* __restrict__ meta) {
     // the block's 32 rows are staged into shared memory with coalesced loads, all in flight at once (one thread per
     // code reading its own row from global memory was bound by dependent-load latency: ~2 warps per SM)
     __shared__ float rows_s[32 * (kMaxDim + 1)];
     const int code = blockIdx.x * blockDim.x + threadIdx.x;
+    const int normalize = flags & 1;
+    const bool dot_only = (flags & 2) != 0;      // MTVQ_SCORE_DOT: codes are ranked by z.w alone -> no -||w||^2/2 term
     {
         const int code0 = blockIdx.x * blockDim.x;
         const int nrows = min(32, k - code0);
@@ -54,7 +56,7 @@ __global__ void codebook_prep_kernel(const float* __restrict__ w, int k, int kpa
         float den0 = 1.0f;
         if (normalize) den0 = canon_denom([&](int i) { return __ldg(w0 + i); }, d, 0);
         const float c0 = canon_sumsq([&](int i) { return normalize ? __fdiv_rn(__ldg(w0 + i), den0) : __ldg(w0 + i); }, d);
-        const float spread = 0.5f * fabsf(c2 - c0);
+        const float spread = dot_only ? 0.0f : 0.5f * fabsf(c2 - c0);
         if (spread == spread) atomicMax(reinterpret_cast<int*>(meta + META_SPREAD), __float_as_int(spread));
         else meta[META_SPREAD] = INFINITY;
     }
@@ -69,7 +71,7 @@ __global__ void codebook_prep_kernel(const float* __restrict__ w, int k, int kpa
         *reinterpret_cast<uint4*>(tile_base + j * 2048) = *reinterpret_cast<uint4*>(h);
     }
     // bias = -||w||^2 / 2 split into three fp16 terms (exact to ~2^-33 relative)
-    const float b = -0.5f * c2;
+    const float b = dot_only ? 0.0f : -0.5f * c2;
     const __half h0 = __float2half_rn(b);
     const float r1 = b - __half2float(h0);
     const __half h1 = __float2half_rn(r1);
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(kResWarps * 32, 4) resolve_kernel(
         // additions inside each chain and the order in which the chains are folded are exactly those of
         // canon_norm8 / canon_sumsq (common.cuh), only the chains run side by side
         float den;
-        if (norm_mode == 0) {
+        if (norm_kind(norm_mode) == 0) {
             const int v = lane & 7;
             float a = 0.f;
             for (int c = 0; c < d; c += 8) { const float x = xs[wib][c + v]; a = __fadd_rn(a, __fmul_rn(x, x)); }
@@ -172,6 +174,8 @@ __global__ void __launch_bounds__(kResWarps * 32, 4) resolve_kernel(
             for (int t = 0; t < 8; ++t) fin = __fadd_rn(fin, __shfl_sync(0xffffffffu, f, t));
             zz = fin;
         }
+        const bool dots = score_dot(norm_mode);      // argmax z.w == argmin fl(fl(0 + 0) - 2 dot), first index on ties
+        if (dots) zz = 0.0f;
         float best = 0.0f;
         int bcol = 0x7fffffff;
         const int mine = lane < cnt ? cand[(size_t)row * cand_cap + lane] : 0x7fffffff;   // cand_cap <= 32
@@ -192,7 +196,7 @@ __global__ void __launch_bounds__(kResWarps * 32, 4) resolve_kernel(
                     dot = __fmaf_rn(xv.w, wv[t].w, dot);
                 }
             }
-            best = canon_dist(zz, cc[mine], dot);
+            best = canon_dist(zz, dots ? 0.0f : cc[mine], dot);
             bcol = mine;
             ++ncands;
         }
@@ -234,7 +238,7 @@ __global__ void __launch_bounds__(kResWarps * 32, 4) resolve_kernel(
                 }
             }
             if (code < k) {
-                const float dist = canon_dist(zz, cc[code], dot);
+                const float dist = canon_dist(zz, dots ? 0.0f : cc[code], dot);
                 if (better(dist, code, best, bcol)) { best = dist; bcol = code; }
                 ++ncands;
             }
@@ -297,7 +301,7 @@ __global__ void __launch_bounds__(256) exact_scan_kernel(const float* __restrict
                 const float den = canon_denom([&](int i) { return __ldg(zr + i); }, d, norm_mode);
                 if (denom_out) denom_out[row] = den;
                 for (int i = 0; i < d; ++i) As[(size_t)i * XR + threadIdx.x] = __fdiv_rn(__ldg(zr + i), den);
-                zzs[threadIdx.x] = canon_sumsq([&](int i) { return As[(size_t)i * XR + threadIdx.x]; }, d);
+                zzs[threadIdx.x] = score_dot(norm_mode) ? 0.0f : canon_sumsq([&](int i) { return As[(size_t)i * XR + threadIdx.x]; }, d);
             } else {
                 for (int i = 0; i < d; ++i) As[(size_t)i * XR + threadIdx.x] = 0.0f;
                 zzs[threadIdx.x] = 0.0f;
@@ -349,7 +353,7 @@ __global__ void __launch_bounds__(256) exact_scan_kernel(const float* __restrict
                 for (int bi = 0; bi < 4; ++bi) {
                     const int code = c0 + tx * 4 + bi;
                     if (code < k) {
-                        const float dist = canon_dist(zz, __ldg(cc + code), acc[ai][bi]);
+                        const float dist = canon_dist(zz, score_dot(norm_mode) ? 0.0f : __ldg(cc + code), acc[ai][bi]);
                         const bool nan_new = dist != dist, nan_old = seen[ai] && (bestv[ai] != bestv[ai]);
                         if (!seen[ai] || (!nan_old && (nan_new || dist < bestv[ai]))) {
                             bestv[ai] = dist; besti[ai] = code; seen[ai] = true;
@@ -394,12 +398,12 @@ __global__ void __launch_bounds__(256) exact_scan_kernel(const float* __restrict
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-cudaError_t launch_codebook_prep(const float* w, int k, int d, int normalize, const Workspace& ws,
+cudaError_t launch_codebook_prep(const float* w, int k, int d, int flags, const Workspace& ws,
                                  cudaStream_t stream) {
     cudaError_t e = cudaMemsetAsync(ws.meta, 0, sizeof(float) * META_COUNT, stream);
     if (e != cudaSuccess) return e;
     const int kpad = pad_codes(k);
-    codebook_prep_kernel<<<(kpad + 31) / 32, 32, 0, stream>>>(w, k, kpad, d, normalize,
+    codebook_prep_kernel<<<(kpad + 31) / 32, 32, 0, stream>>>(w, k, kpad, d, flags,
                                                                   static_cast<unsigned char*>(ws.b_image), ws.cc,
                                                                   ws.codes_n, ws.meta);
     ++g_kernel_launches;

@@ -8,8 +8,9 @@
 namespace mtvq {
 
 // fp32 codebook [k,d] -> ws.b_image (fp16 operand tiles + bias planes), ws.cc, ws.meta (margin);
-// normalize != 0 (soft path): rows are l2-normalised first and also written to ws.codes_n
-cudaError_t launch_codebook_prep(const float* w, int k, int d, int normalize, const Workspace& ws,
+// flags bit 0 (soft path): rows are l2-normalised first and also written to ws.codes_n; bit 1 (MTVQ_SCORE_DOT): the
+// coarse score is the inner product alone (no -||w||^2/2 term)
+cudaError_t launch_codebook_prep(const float* w, int k, int d, int flags, const Workspace& ws,
                                  cudaStream_t stream);
 
 // near-tie rows (ws.flag_rows / counters[CNT_FLAGGED]) x their collected candidates -> idx[row] (int64) and

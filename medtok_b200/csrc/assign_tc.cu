@@ -241,7 +241,7 @@ __device__ __forceinline__ void consume_argmax64(const float (&va)[32], const fl
             const float lo = fminf(ma, mb);
             // the ROW's best so far is at least what the thread owning the other column half has published (its value
             // only grows, so a stale read is still a bound): a granule below that minus the margin cannot matter
-            const float other = *partner;
+            const float other = ld_relaxed_smem(partner);
             if (cmax > st.m1) {          // new record
                 const float nthr = cmax - margin;
                 // Only granules within the margin of the CURRENT best can matter at the end (the best only grows), so
@@ -253,7 +253,7 @@ __device__ __forceinline__ void consume_argmax64(const float (&va)[32], const fl
                     else            { st.m3 = fmaxf(fmaxf(st.m3, st.m2), lo);    st.m2 = st.m1; st.chunk2 = st.best_chunk; }
                 }
                 st.m1 = cmax;
-                *pub = cmax;
+                st_relaxed_smem(pub, cmax);
                 st.thr = fmaxf(nthr, other - margin);
                 if (b_wins) { st.best_chunk = chunk + 1; record_store<REC>(slots, rec, vb); }
                 else        { st.best_chunk = chunk;     record_store<REC>(slots, rec, va); }
@@ -289,13 +289,13 @@ __device__ __forceinline__ void consume_topk(const float (&v)[32], int gran, flo
             // owns the other column half has published (its values only grow, so a stale read is still a bound);
             // for k = 5 also the 3 + 2 splits.  Halves the trigger rate of the second half of a row block.
             float kth;
-            const float4 o = *partner;
+            const float4 o = ld_relaxed_smem4(partner);
             if (KSTATIC == 5) {
                 kth = fmaxf(fmaxf(top[4], o.z), fmaxf(fminf(top[2], o.x), fminf(top[1], o.y)));
-                *pub = make_float4(top[1], top[2], top[4], 0.f);
+                st_relaxed_smem4(pub, make_float4(top[1], top[2], top[4], 0.f));
             } else {
                 kth = fmaxf(select_kth(top, kidx), o.z);
-                *pub = make_float4(0.f, 0.f, select_kth(top, kidx), 0.f);
+                st_relaxed_smem4(pub, make_float4(0.f, 0.f, select_kth(top, kidx), 0.f));
             }
             thr = fmaxf(kth - margin, top[kTopSlots - 1]);
         }
@@ -776,7 +776,9 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                 float rden = 0.0f;
                 if (valid) {
                     float den;
-                    if (p.norm_mode == 0) {
+                    if (norm_kind(p.norm_mode) == 2) {
+                        den = 1.0f;                                   // MTVQ_NORM_NONE: rows are used as given
+                    } else if (norm_kind(p.norm_mode) == 0) {
                         // canon_norm8 on float4 loads: lane v accumulates x[8c+v]^2 in order of c
                         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f;
                         for (int j = 0; j < nplanes; ++j) {

@@ -57,9 +57,15 @@ __device__ __forceinline__ float canon_norm_seq(Get get, int d) {
     return __fsqrt_rn(s);
 }
 
+// norm_mode is a small bit field (include/medtok_vq.h): bits 0-1 = MTVQ_NORM_* (0 contiguous, 1 strided, 2 none: the
+// rows are used as they are, denominator exactly 1), bit 2 = MTVQ_SCORE_DOT (rank codes by the inner product alone)
+__device__ __forceinline__ int  norm_kind(int norm_mode) { return norm_mode & 3; }
+__device__ __forceinline__ bool score_dot(int norm_mode) { return (norm_mode & 4) != 0; }
+
 template <class Get>
 __device__ __forceinline__ float canon_denom(Get get, int d, int norm_mode) {
-    float nrm = norm_mode ? canon_norm_seq(get, d) : canon_norm8(get, d);
+    if (norm_kind(norm_mode) == 2) return 1.0f;
+    float nrm = norm_kind(norm_mode) ? canon_norm_seq(get, d) : canon_norm8(get, d);
     return nrm < kNormEps ? kNormEps : nrm;      // clamp_min(eps); NaN stays NaN like torch
 }
 
@@ -244,8 +250,34 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// Published bounds (assign_tc.cu): one thread keeps storing a value that only grows, another reads it without any
+// synchronisation and only needs SOME earlier value.  Relaxed CTA-scope accesses make that well defined in the PTX
+// memory model (a plain C++ load/store pair would be a data race); each 32-bit component is read or written whole.
+__device__ __forceinline__ float ld_relaxed_smem(const float* p) {
+    float v;
+    asm volatile("ld.relaxed.cta.shared::cta.f32 %0, [%1];" : "=f"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_smem(float* p, float v) {
+    asm volatile("st.relaxed.cta.shared::cta.f32 [%0], %1;" ::"r"(smem_u32(p)), "f"(v) : "memory");
+}
+__device__ __forceinline__ float4 ld_relaxed_smem4(const float4* p) {
+    float4 v;
+    asm volatile("ld.relaxed.cta.shared::cta.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_smem4(float4* p, float4 v) {
+    asm volatile("st.relaxed.cta.shared::cta.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w) : "memory");
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// non-blocking arrival of the whole (converged) warp on a named barrier that other warps bar.sync on
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -7,6 +7,9 @@
 //   ema_finalize_kernel cluster_size EMA + normalised-EMA codebook update + loss scalar    (:189,197-212)
 // Line numbers refer to /root/reference/MedTok/norm_ema_quantizer.py.
 #include "rows.h"
+
+#include <stdio.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace mtvq {
@@ -412,7 +415,14 @@ struct PeerTable {
     unsigned* const*     flags;   // [world] peer-mapped flag arrays, flags[r][q] = last epoch rank q announced to rank r
     int world, rank;
     unsigned epoch;
+    unsigned long long timeout_ns;   // upper bound on the wait for the peers' flags
 };
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -441,7 +451,17 @@ __global__ void __launch_bounds__(256) ema_finalize_kernel(float* __restrict__ w
                 st_release_sys(pt.flags[threadIdx.x] + pt.rank, pt.epoch);
             }
             const unsigned* mine = pt.flags[pt.rank] + threadIdx.x;
-            while ((int)(ld_acquire_sys(mine) - pt.epoch) < 0) __nanosleep(200);
+            // bounded wait: a peer that crashed (or never reaches this step) must not park every GPU inside a kernel
+            // where no watchdog can reach it -- after the limit the kernel traps and the host sees a launch failure
+            const unsigned long long t0 = global_timer_ns();
+            while ((int)(ld_acquire_sys(mine) - pt.epoch) < 0) {
+                __nanosleep(200);
+                if (global_timer_ns() - t0 > pt.timeout_ns) {
+                    printf("medtok_vq: rank %d waited more than %llu s for the statistics of rank %d (step %u)\n", pt.rank,
+                           pt.timeout_ns / 1000000000ull, (int)threadIdx.x, pt.epoch);
+                    __trap();
+                }
+            }
         }
         __syncthreads();
     }
@@ -508,6 +528,35 @@ __global__ void __launch_bounds__(256) ema_finalize_kernel(float* __restrict__ w
     for (int e = threadIdx.x; e < ncodes * d; e += blockDim.x) {
         const int c = e / d, i = e - c * d;
         weight[(size_t)(code0 + c) * d + i] = __fdiv_rn(tile[c * (d + 1) + i], den_s[c]);
+    }
+}
+
+// k-means centre update (norm_ema_quantizer.py:43-54, cosine branch): means_k <- l2norm(sum_k / bins_k), a cluster
+// without members keeps its centre.  The row is contiguous in the reference -> canon_norm8 order.
+__global__ void __launch_bounds__(256) kmeans_update_kernel(float* __restrict__ means, const double* __restrict__ stats,
+                                                             int k, int d) {
+    extern __shared__ float tile[];
+    __shared__ double bins_s[kEmaCodes];
+    __shared__ float den_s[kEmaCodes];
+    const int code0 = blockIdx.x * kEmaCodes;
+    const int ncodes = min(kEmaCodes, k - code0);
+    if (threadIdx.x < kEmaCodes) bins_s[threadIdx.x] = threadIdx.x < ncodes ? stats[code0 + threadIdx.x] : 0.0;
+    __syncthreads();
+    for (int e = threadIdx.x; e < ncodes * d; e += blockDim.x) {
+        const int c = e / d, i = e - c * d;
+        const double bins = bins_s[c];
+        if (bins != 0.0) tile[c * (d + 1) + i] = __fdiv_rn((float)stats[(size_t)k + (size_t)(code0 + c) * d + i], (float)bins);
+    }
+    __syncthreads();
+    if (threadIdx.x < ncodes && bins_s[threadIdx.x] != 0.0) {
+        const float* e = tile + threadIdx.x * (d + 1);
+        const float den = canon_norm8([&](int i) { return e[i]; }, d);
+        den_s[threadIdx.x] = den < kNormEps ? kNormEps : den;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < ncodes * d; e += blockDim.x) {
+        const int c = e / d, i = e - c * d;
+        if (bins_s[c] != 0.0) means[(size_t)(code0 + c) * d + i] = __fdiv_rn(tile[c * (d + 1) + i], den_s[c]);
     }
 }
 
@@ -631,8 +680,20 @@ cudaError_t launch_ema_finalize_peers(float* weight, float* cluster_size, const 
     pt.stats = reinterpret_cast<const double* const*>(peer_stats);
     pt.flags = reinterpret_cast<unsigned* const*>(peer_flags);
     pt.world = world; pt.rank = rank; pt.epoch = epoch;
+    {   // MEDTOK_EXCHANGE_TIMEOUT_S (default 600 s, the NCCL watchdog's order of magnitude)
+        static long long limit_s = -1;
+        if (limit_s < 0) { const char* e = getenv("MEDTOK_EXCHANGE_TIMEOUT_S"); limit_s = (e && atoll(e) > 0) ? atoll(e) : 600; }
+        pt.timeout_ns = (unsigned long long)limit_s * 1000000000ull;
+    }
     ema_finalize_kernel<true><<<(k + kEmaCodes - 1) / kEmaCodes, 256, smem, s>>>(
         weight, cluster_size, nullptr, pt, k, d, (float)beta, (float)decay, (float)(1.0 - decay), update_cs, update_w, loss);
+    ++g_kernel_launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_kmeans_update(float* means, const double* stats, int k, int d, cudaStream_t s) {
+    const size_t smem = sizeof(float) * kEmaCodes * (d + 1);
+    kmeans_update_kernel<<<(k + kEmaCodes - 1) / kEmaCodes, 256, smem, s>>>(means, stats, k, d);
     ++g_kernel_launches;
     return cudaGetLastError();
 }

@@ -27,6 +27,8 @@ cudaError_t launch_ema_finalize(float* weight, float* cluster_size, const double
 cudaError_t launch_ema_finalize_peers(float* weight, float* cluster_size, const void* const* peer_stats,
                                       void* const* peer_flags, int world, int rank, unsigned epoch, int k, int d,
                                       double beta, double decay, int update_cs, int update_w, float* loss, cudaStream_t s);
+// k-means centre update: means_k <- l2norm(embed_sum_k / bins_k) where bins_k > 0 (packed statistics as above)
+cudaError_t launch_kmeans_update(float* means, const double* stats, int k, int d, cudaStream_t s);
 cudaError_t launch_loss(const double* stats, int k, int d, double beta, float* loss, cudaStream_t s);
 
 }  // namespace mtvq

@@ -507,7 +507,7 @@ cudaError_t launch_norms(const float* x, int64_t n, int d, float* denom, int num
 cudaError_t launch_soft_resolve(const float* x, int64_t n, int d, int k, int topk, const Workspace& ws, int64_t* idx,
                                 float* vals, float* wts, float* zq, float* out, double* sse, int num_sms,
                                 cudaStream_t stream) {
-    const int cap = cand_capacity(topk);
+    const int cap = cand_capacity(true);
     if (cap > 8 * kLaneList) return cudaErrorInvalidValue;
     // shared memory: per 8-lane group the normalised row and an 8-candidate tile; d > 128 runs 4 warps per CTA
     const int warps = d <= 128 ? kSoftWarps : kSoftWarps / 2;

@@ -44,6 +44,7 @@ struct Workspace {
     int*     full_rows;    // [n]
     int*     counters;     // [CNT_COUNT]
     void*    topk_scratch; // soft path: per-CTA record scratch of the single-pass top-k kernel (L2 resident)
+    void*    small_part;   // small-batch route: per-(row, code slice) partial top-k lists (small.cu)
     // statistics side
     int*     bins_i32;     // [k]
     int*     offsets;      // [k+1]
@@ -55,9 +56,12 @@ struct Workspace {
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline int    pad_codes(int k) { return (int)align_up((size_t)k, 128); }
 // near-tie candidates kept per row before the row falls back to the full exact scan
-inline int    cand_capacity(int topk) { return topk > 1 ? 24 : 16; }
+inline int    cand_capacity(bool soft) { return soft ? 24 : 16; }
 inline size_t image_bytes(int d, int k) { return (size_t)(pad_codes(k) / 128) * (size_t)(d / 8 + 2) * 2048; }
 
+// topk == 0: hard path only; topk >= 1: the buffers of the soft path (normalised codebook, per-CTA record scratch, wider
+// candidate lists) as well -- also for top-1, which VectorQuantizer(..., k=1) may ask for.  Everything whose size does
+// not depend on the path comes first, so those offsets (counters, ...) are the same for both.
 inline Workspace carve(void* base, int64_t n, int d, int k, int topk) {
     Workspace w{};
     size_t off = 0;
@@ -67,24 +71,29 @@ inline Workspace carve(void* base, int64_t n, int d, int k, int topk) {
         off += align_up(bytes, 256);
         return r;
     };
+    const bool   soft     = topk >= 1;
     const int    kpad     = pad_codes(k);
-    const size_t cand_cap = (size_t)cand_capacity(topk);
+    const size_t cand_cap = (size_t)cand_capacity(soft);
     w.b_image   = take(image_bytes(d, k));
     w.cc        = (float*)take(sizeof(float) * kpad);
-    w.codes_n   = (float*)take(topk > 1 ? sizeof(float) * (size_t)k * d : 0);
     w.meta      = (float*)take(sizeof(float) * META_COUNT);
+    w.counters  = (int*)take(sizeof(int) * CNT_COUNT);
     w.denom     = (float*)take(sizeof(float) * n);
     w.best_val  = (float*)take(sizeof(float) * n);
     w.flag_rows = (int*)take(sizeof(int) * n);
-    w.cand      = (int*)take(sizeof(int) * n * cand_cap);
     w.cand_cnt  = (int*)take(sizeof(int) * n);
     w.full_rows = (int*)take(sizeof(int) * n);
-    w.counters  = (int*)take(sizeof(int) * CNT_COUNT);
-    w.topk_scratch = take(topk > 1 ? (size_t)160 * (8 * 4 * 1024 * 16) : 0);   // kTopkMaxCtas x kTopkScratchPerCta
     w.bins_i32  = (int*)take(sizeof(int) * k);
     w.offsets   = (int*)take(sizeof(int) * (k + 1));
     w.cursor    = (int*)take(sizeof(int) * k);
     w.perm      = (int*)take(sizeof(int) * n);
+    w.cand      = (int*)take(sizeof(int) * n * cand_cap);
+    w.codes_n   = (float*)take(soft ? sizeof(float) * (size_t)k * d : 0);
+    w.topk_scratch = take(soft ? (size_t)160 * (8 * 4 * 1024 * 16) : 0);   // kTopkMaxCtas x kTopkScratchPerCta
+    // small-batch route (small.cu): 8 bytes per (row, 64-code slice, list entry); the route's own bounds (n <= 4096,
+    // n * k <= 3e7) keep this below ~30 MB
+    const bool small = n > 0 && n <= 4096 && (double)n * (double)k * (double)d <= 1.6e9 && (double)n * (double)k <= 3.0e7;
+    w.small_part = take(small ? (size_t)n * (size_t)((k + 63) / 64) * (size_t)(soft ? topk : 1) * 8 : 0);
     w.total_bytes = off;
     return w;
 }

@@ -54,26 +54,39 @@ class PeerExchange:
     every rank holds device pointers into every peer's copy (NVLink P2P).  PyTorch only provides the mapping; the
     signalling, the waiting and the rank-ordered fp64 sum all happen inside the one kernel.
 
-    Construction is collective (every rank of `group` must call it with the same `numel`).  Raises if symmetric
-    memory cannot be set up -- the caller then keeps the all-reduce + finalize route."""
+    Set-up is split so that a failure on ONE rank can never leave the others inside a collective: `__init__` only
+    allocates (local, may raise), `connect()` is the collective rendezvous (every rank of the group must call it, which
+    the caller guarantees by voting on the allocation first), `arm()` zeroes the flags; the caller votes again and then
+    barriers before the first step (NormEMAVectorQuantizer._peer_exchange)."""
+
+    MAX_WORLD = 64                      # flag slots per rank (mtvq_ema_finalize_peers rejects larger worlds)
 
     def __init__(self, numel: int, device, group=None):
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
-        group = group if group is not None else dist.group.WORLD
-        self.world = dist.get_world_size(group)
-        self.rank = dist.get_rank(group)
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        if self.world > self.MAX_WORLD:
+            raise RuntimeError(f"fused exchange supports at most {self.MAX_WORLD} ranks, got {self.world}")
         self.numel = numel
+        self.device = device
         import warnings
         with warnings.catch_warnings():                            # newer torch enables groups lazily and deprecates this
             warnings.simplefilter("ignore")
             try:
-                symm_mem.enable_symm_mem_for_group(group.group_name)
+                symm_mem.enable_symm_mem_for_group(self.group.group_name)
             except Exception:
                 pass
         self.stats = [symm_mem.empty(numel, dtype=torch.float64, device=device) for _ in range(2)]
-        self.flags = symm_mem.empty(64, dtype=torch.int32, device=device)
-        self._handles = [symm_mem.rendezvous(t, group) for t in (*self.stats, self.flags)]
+        self.flags = symm_mem.empty(self.MAX_WORLD, dtype=torch.int32, device=device)
+        self.table = None
+        self.epoch = 0
+
+    def connect(self):
+        """Collective: exchange the peer mappings.  Raises if the handles do not describe our tensors."""
+        import torch.distributed._symmetric_memory as symm_mem
+        self._handles = [symm_mem.rendezvous(t, self.group) for t in (*self.stats, self.flags)]
         tables = []
         for t, h in zip((*self.stats, self.flags), self._handles):
             off = int(getattr(h, "offset", 0) or 0)
@@ -82,13 +95,15 @@ class PeerExchange:
                 raise RuntimeError("symmetric-memory handle does not describe the tensor it was made from")
             tables.append(ptrs)
         # device tables of peer pointers: [stats parity 0 | stats parity 1 | flags], `world` int64 each
-        self.table = torch.tensor(tables, dtype=torch.int64, device=device)
+        self.table = torch.tensor(tables, dtype=torch.int64, device=self.device)
+
+    def arm(self):
+        """Local: zero the flags and statistics (nobody signals before the caller's barrier that follows)."""
         self.flags.zero_()
         for t in self.stats:
             t.zero_()
         self.epoch = 0
-        torch.cuda.synchronize(device)
-        dist.barrier(group)                                        # nobody signals before every flag array is zero
+        torch.cuda.synchronize(self.device)
 
     def next_buffer(self) -> torch.Tensor:
         """Statistics buffer of the coming step (call once per step, before mtvq_hard_forward)."""

@@ -48,6 +48,7 @@ def _rows_f32(t: torch.Tensor) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 # thin functional layer over the C ABI (used by the modules, k-means and the tests)
 # ------------------------------------------------------------------------------------------------
+@_lib.on_tensor_device
 def hard_assign(z_rows: torch.Tensor, weight: torch.Tensor, norm_mode: int = _lib.NORM_CONTIGUOUS,
                 workspace: _lib.Workspace | None = None, exact: bool = False):
     """idx[n] = first-index argmin_k ||zf_n - w_k||^2-style distance of reference :175-179.
@@ -56,7 +57,7 @@ def hard_assign(z_rows: torch.Tensor, weight: torch.Tensor, norm_mode: int = _li
     z_rows, weight = _rows_f32(z_rows), _rows_f32(weight)
     n, d = z_rows.shape
     k = weight.shape[0]
-    ws = (workspace or _lib.Workspace()).get(n, d, k, 1, z_rows.device)
+    ws = (workspace or _lib.Workspace()).get(n, d, k, 0, z_rows.device)
     idx = torch.empty(n, dtype=torch.int64, device=z_rows.device)
     denom = torch.empty(n, dtype=torch.float32, device=z_rows.device)
     fn = _lib.lib().mtvq_hard_assign_exact if exact else _lib.lib().mtvq_hard_assign
@@ -65,6 +66,7 @@ def hard_assign(z_rows: torch.Tensor, weight: torch.Tensor, norm_mode: int = _li
     return idx, denom
 
 
+@_lib.on_tensor_device
 def code_statistics(z_rows, denom, weight, idx, workspace: _lib.Workspace | None = None):
     """Packed fp64 statistics [bins(k) | embed_sum(k*d) | sse | rows] and z_q for given indices
     (reference :181-202 without the one-hot)."""
@@ -72,7 +74,7 @@ def code_statistics(z_rows, denom, weight, idx, workspace: _lib.Workspace | None
     n, d = z_rows.shape
     k = weight.shape[0]
     dev = z_rows.device
-    ws = (workspace or _lib.Workspace()).get(n, d, k, 1, dev)
+    ws = (workspace or _lib.Workspace()).get(n, d, k, 0, dev)
     stats = torch.zeros(_lib.stats_len(d, k), dtype=torch.float64, device=dev)
     z_q = torch.empty_like(z_rows)
     L = _lib.lib()
@@ -93,32 +95,35 @@ def sample_vectors(samples, num):
     return samples[indices]
 
 
+@_lib.on_tensor_device
 def kmeans(samples, num_clusters, num_iters=10, use_cosine_sim=False, means=None, verbose=True):
-    """reference :24-57 (cosine branch on the CUDA assign/statistics kernels).  `samples` are the
-    l2-normalised rows the quantizer feeds in (:173); argmax of samples @ means.t() is taken as the
-    nearest code of the same kernel that serves the forward (means are unit rows, so the two agree
-    outside fp32 near-ties).  Returns (means, bins)."""
+    """reference :24-57, cosine branch, on the CUDA kernels: `buckets = (samples @ means.t()).max(-1).indices`
+    is the tensor-core assignment in inner-product mode (SCORE_DOT: exact fp32 re-scoring of near-ties by z.w alone,
+    first index on ties) on the samples as given (NORM_NONE: no second normalisation); bincount + scatter_add are the
+    packed statistics (fp64 sums of the samples); the centre update is mtvq_kmeans_update.  Returns (means, bins)."""
     if not use_cosine_sim:
         raise NotImplementedError("only the cosine-similarity branch is used by MedTok (:90)")
     _lib.require_cuda(samples, "samples")
     samples = _rows_f32(samples)
     if means is None:
         means = sample_vectors(samples, num_clusters)
-    means = means.clone()
+    means = means.clone().contiguous()
     ws = _lib.Workspace()
     d = samples.shape[1]
+    L = _lib.lib()
     bins = None
     for i in range(num_iters):
-        idx, denom = hard_assign(samples, means, workspace=ws)
-        _, stats = code_statistics(samples, denom, means, idx, workspace=ws)
+        idx, ones = hard_assign(samples, means, norm_mode=_lib.NORM_NONE | _lib.SCORE_DOT, workspace=ws)
+        stats = torch.zeros(_lib.stats_len(d, num_clusters), dtype=torch.float64, device=samples.device)
+        wsb = ws.get(samples.shape[0], d, num_clusters, 0, samples.device)
+        _lib.check(L.mtvq_code_sums(_lib.ptr(samples), _lib.ptr(ones), _lib.ptr(idx), samples.shape[0], d, num_clusters,
+                                    _lib.ptr(stats), _lib.ptr(wsb), wsb.numel(), _lib.stream_ptr(samples.device)),
+                   "mtvq_code_sums")
+        _lib.check(L.mtvq_kmeans_update(_lib.ptr(means), _lib.ptr(stats), num_clusters, d,
+                                        _lib.stream_ptr(samples.device)), "mtvq_kmeans_update")
         bins = stats[:num_clusters]
-        zero_mask = bins == 0
-        sums = stats[num_clusters:num_clusters + num_clusters * d].view(num_clusters, d)
-        new_means = (sums / bins.masked_fill(zero_mask, 1)[..., None]).float()
-        new_means = l2norm(new_means)
-        means = torch.where(zero_mask[..., None], means, new_means)
         if verbose:
-            print(f"Iteration {i + 1}/{num_iters} - Zero clusters: {int(zero_mask.sum().item())}")
+            print(f"Iteration {i + 1}/{num_iters} - Zero clusters: {int((bins == 0).sum().item())}")
     return means, bins.to(torch.int64)
 
 
@@ -246,28 +251,53 @@ class NormEMAVectorQuantizer(nn.Module):
 
     def _peer_exchange(self, dev, d, k):
         """PeerExchange for the fused finalize, or None (-> all-reduce route).  Only for the stock binding
-        (`all_reduce_fn is torch.distributed.all_reduce` on an NCCL group); set up once, collectively."""
+        (`all_reduce_fn is torch.distributed.all_reduce` on an NCCL group); set up once.  Every step that can fail on
+        one rank only (allocation, eligibility, the mapping check) is followed by a MIN vote, so all ranks issue the
+        same sequence of collectives and take the same route; the barrier comes last, after the final vote."""
         if self._peers is not None or not self.fused_exchange:
             return self._peers or None
         self.fused_exchange = False
         if self.all_reduce_fn is not distributed.all_reduce or distributed.get_backend() != "nccl":
-            return None
-        ok = torch.ones(1, device=dev)
-        try:
-            peers = PeerExchange(_lib.stats_len(d, k), dev)
-        except Exception as e:                       # no P2P / symmetric memory: every rank must take the same route
-            print(f"medtok_b200: fused NVLink exchange unavailable ({type(e).__name__}: {e}); using all_reduce",
+            return None                  # (a property of how the job was launched: the same on every rank)
+
+        def all_agree(ok_local: bool) -> bool:
+            ok = torch.full((1,), 1.0 if ok_local else 0.0, device=dev)
+            distributed.all_reduce(ok, op=distributed.ReduceOp.MIN)
+            return float(ok) != 0.0
+
+        def note(stage, e):
+            print(f"medtok_b200: fused NVLink exchange unavailable ({stage}: {type(e).__name__}: {e}); using all_reduce",
                   file=sys.stderr)
+
+        peers = None
+        try:
+            world = distributed.get_world_size()
+            # one node only: the exchange reads peer memory over NVLink (LOCAL_WORLD_SIZE is set by torchrun)
+            local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+            if local_world != world or world > torch.cuda.device_count():
+                raise RuntimeError(f"multi-node world ({world} ranks, {local_world} on this node)")
+            peers = PeerExchange(_lib.stats_len(d, k), dev)
+        except Exception as e:
+            note("allocation", e)
             peers = None
-            ok.zero_()
-        distributed.all_reduce(ok, op=distributed.ReduceOp.MIN)
-        if float(ok) == 0.0:
+        if not all_agree(peers is not None):
             return None
+        try:
+            peers.connect()                                   # collective; every rank is here
+            peers.arm()
+            ok = True
+        except Exception as e:
+            note("rendezvous", e)
+            ok = False
+        if not all_agree(ok):
+            return None
+        distributed.barrier()                                 # nobody signals before every flag array is zero
         self._peers = peers
         self.fused_exchange = True
         return peers
 
     # -- one forward on rows [N, D] -------------------------------------------------------------
+    @_lib.on_tensor_device
     def _run(self, z_rows_in: torch.Tensor, norm_mode: int):
         L = _lib.lib()
         z_rows = _rows_f32(z_rows_in)
@@ -283,7 +313,7 @@ class NormEMAVectorQuantizer(nn.Module):
         flags = (_lib.F_TRAINING if self.training else 0) | (_lib.F_UPDATE if self.embedding.update else 0)
         if distributed_on or not has_cs:
             flags |= _lib.F_SKIP_FINALIZE
-        ws = self._ws.get(n, d, k, 1, dev)
+        ws = self._ws.get(n, d, k, 0, dev)
         z_q = torch.empty_like(z_rows)
         idx = torch.empty(n, dtype=torch.int64, device=dev)
         loss = torch.empty(1, dtype=torch.float32, device=dev)
@@ -371,6 +401,7 @@ class VectorQuantizer(nn.Module):
             self.register_buffer('cluster_size', torch.zeros(self.num_tokens))
             self.cluster_size = self.cluster_size.to(device)
 
+    @_lib.on_tensor_device
     def _run(self, idx: torch.Tensor, z_rows: torch.Tensor | None):
         weight = self.embedding.weight.data
         _lib.require_cuda(weight, "embedding.weight")
@@ -388,7 +419,7 @@ class VectorQuantizer(nn.Module):
         # the reference only needs cluster_size when statistic_code_usage registered it (:236-238,257-261)
         want_counts = (not self.training) and self.statistic_code_usage
         counts = torch.empty(k, dtype=torch.float32, device=dev) if want_counts else None
-        ws = self._ws.get(n, d, k, 1, dev) if want_counts else None
+        ws = self._ws.get(n, d, k, 0, dev) if want_counts else None
         _lib.check(_lib.lib().mtvq_lookup(_lib.ptr(z_rows), _lib.ptr(weight), _lib.ptr(flat), n, d, k, _lib.ptr(z_q),
                                           _lib.ptr(sse), _lib.ptr(counts), _lib.ptr(ws), 0 if ws is None else ws.numel(),
                                           _lib.stream_ptr(dev)), "mtvq_lookup")

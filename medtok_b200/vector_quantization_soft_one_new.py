@@ -59,6 +59,7 @@ class _SoftQuantizeFn(torch.autograd.Function):
     reference :195-214 against rows [lo, hi) of the table."""
 
     @staticmethod
+    @_lib.on_tensor_device
     def forward(ctx, x, table, lo, hi, topk, beta, training, workspace):
         L = _lib.lib()
         x32 = x.detach().float().contiguous()
@@ -90,6 +91,7 @@ class _SoftQuantizeFn(torch.autograd.Function):
         return out.to(x.dtype), vq, commit, idx, wts
 
     @staticmethod
+    @_lib.on_tensor_device
     def backward(ctx, g_out, g_vq, g_commit, _gi, _gw):
         """One fused kernel (mtvq_soft_backward_fused): straight-through + commitment term + the path through the
         softmax weights and F.normalize for x, and the gathered rows' gradient for the raw table (atomic adds)."""
@@ -196,6 +198,7 @@ class VectorQuantizer(nn.Module):
         self._last_specific = (idx, wts)
         return z_q, (vq, commit, F.normalize(original_embedding, p=2, dim=-1), z_q), usage
 
+    @_lib.on_tensor_device
     def codebook_usage(self, min_encoding_indices, types='shared'):
         """reference :219-236: sliding float32 window of the last 300000 code ids, len(unique)/n_e (quirks kept: the
         zero padding is counted and slice-relative indices are divided by the full table size).  The shift and
@@ -223,8 +226,9 @@ class VectorQuantizer(nn.Module):
                                                       _lib.ptr(self._usage_next), _lib.ptr(self._usage_scratch),
                                                       4 * words, _lib.ptr(distinct), _lib.stream_ptr(dev)),
                        "mtvq_codebook_usage")
-            # swap the two window buffers; `codebook_used` stays the registered buffer (same state_dict key)
-            self._usage_next, self.codebook_used = window, self._usage_next
+            # the registered buffer keeps its identity (DDP buffer broadcasts, hooks and anything else that cached the
+            # tensor object keep seeing the live window): the shifted window is copied back in place (1.2 MB)
+            window.copy_(self._usage_next)
             self._usage_last = int(distinct.item()) / self.n_e
             return self._usage_last
 

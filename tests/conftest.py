@@ -13,6 +13,7 @@ GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "single_route: full-size case, far above the small-batch bound: run once")
 
 
 def load_golden(name):
@@ -32,3 +33,22 @@ def golden_names(prefix):
 def oracle():
     from oracle import vq_oracle
     return vq_oracle
+
+
+@pytest.fixture(params=["auto", "tensor"])
+def assign_route(request):
+    """GPU parity tests run twice: with the automatic route choice (small batches are scored exactly on the CUDA cores,
+    medtok_b200/csrc/small.cu) and with the tensor-core route forced for every size, so that the small shapes keep
+    exercising the tcgen05 kernels' edge cases (ragged tiles, padding codes, duplicated codes ...)."""
+    import torch
+    if request.param == "tensor" and request.node.get_closest_marker("single_route"):
+        pytest.skip("full-size case: both settings take the tensor route")
+    if not torch.cuda.is_available():
+        yield request.param
+        return
+    from medtok_b200 import _lib
+    _lib.check(_lib.lib().mtvq_debug_set_soft_route(3 if request.param == "tensor" else 4), "route")
+    try:
+        yield request.param
+    finally:
+        _lib.lib().mtvq_debug_set_soft_route(4)

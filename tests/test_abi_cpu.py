@@ -29,9 +29,11 @@ def test_header_symbols_are_exported(lib):
 def test_host_side_sizes_and_validation(lib):
     assert lib.mtvq_abi_version() == 1
     assert lib.mtvq_stats_len(64, 8192) == 8192 + 8192 * 64 + 2
-    small, big = lib.mtvq_workspace_bytes(1000, 64, 512, 1), lib.mtvq_workspace_bytes(1 << 20, 64, 8192, 1)
+    small, big = lib.mtvq_workspace_bytes(1000, 64, 512, 0), lib.mtvq_workspace_bytes(1 << 20, 64, 8192, 0)
     assert 0 < small < big < (1 << 30)
+    # topk >= 1 adds the soft path's buffers -- for top-1 too (VectorQuantizer(..., k=1) is a legal configuration)
     assert lib.mtvq_workspace_bytes(1000, 64, 512, 5) > small
+    assert lib.mtvq_workspace_bytes(1000, 64, 512, 1) > small + (80 << 20)        # record scratch of the top-k pass
     # D not a multiple of 16 is rejected on the host before any CUDA call
     rc = lib.mtvq_hard_assign(None, 10, 20, 0, None, 16, None, None, None, 0, None)
     assert rc == -2 and b"multiple of 16" in lib.mtvq_last_error()

@@ -7,7 +7,7 @@ import torch
 
 from conftest import golden_names, load_golden
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("assign_route")]
 
 
 @pytest.fixture(scope="module")
@@ -108,7 +108,7 @@ def test_accumulated_batches_equal_one_pass(dev):
     lo = 0
     for rows in (12345, 1, 20000, 0, 17654):
         zb = z[lo:lo + rows].contiguous()
-        ws = wsb.get(max(rows, 1), d, k, 1, dev)
+        ws = wsb.get(max(rows, 1), d, k, 0, dev)
         _lib.check(L.mtvq_hard_forward(_lib.ptr(zb), rows, d, 0, _lib.ptr(w2), k, _lib.ptr(cs2), 0.25, 0.99, flags,
                                        _lib.ptr(z_q2[lo:lo + rows]), _lib.ptr(idx2[lo:lo + rows]), _lib.ptr(loss),
                                        _lib.ptr(stats), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "batch")

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("assign_route")]
 
 
 @pytest.fixture(scope="module")
@@ -45,7 +45,7 @@ def test_config4_sharded_vocabulary_equals_one_pass(dev):
     flags = _lib.F_TRAINING | _lib.F_UPDATE | _lib.F_SKIP_FINALIZE | _lib.F_ACCUMULATE
     for r in range(world):
         lo, hi = shard_rows(n, world, r)
-        ws = wsb.get(hi - lo, d, k, 1, dev)
+        ws = wsb.get(hi - lo, d, k, 0, dev)
         _lib.check(L.mtvq_hard_forward(_lib.ptr(z[lo:hi]), hi - lo, d, 0, _lib.ptr(w2), k, _lib.ptr(cs2), 0.25, 0.99, flags,
                                        _lib.ptr(z_q2[lo:hi]), _lib.ptr(idx2[lo:hi]), _lib.ptr(loss), _lib.ptr(stats),
                                        _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "shard")

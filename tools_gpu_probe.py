@@ -44,7 +44,7 @@ if what in ("all", "scores"):
     n, d, k = 700, 64, 1000
     z = torch.randn(n, d, device=dev)
     w = torch.nn.functional.normalize(torch.randn(k, d, device=dev), dim=-1)
-    ws = _lib.Workspace().get(n, d, k, 1, dev)
+    ws = _lib.Workspace().get(n, d, k, 0, dev)
     kpad = ctypes.c_int(0)
     _lib.check(L.mtvq_debug_coarse_scores(_lib.ptr(z), n, d, 0, _lib.ptr(w), k, None, 0, ctypes.byref(kpad),
                                           _lib.ptr(ws), ws.numel(), st), "kpad")
