@@ -109,7 +109,7 @@ int assign_rows(const float* z, int64_t n, int d, int norm_mode, const float* co
     MTVQ_CUDA(cudaMemsetAsync(ws.counters, 0, sizeof(int) * CNT_COUNT, st), "memset counters");
     MTVQ_CUDA(cudaMemsetAsync(ws.bins_i32, 0, sizeof(int) * k, st), "memset bins");
     if (n == 0) return 0;
-    if (!exact_only && small_route_ok(n, d, k) && !g_no_small) {
+    if (!exact_only && small_route_ok(n, d, k, norm_mode) && !g_no_small) {
         // small batch: every (row, code) distance directly in the reference's fp32 order (small.cu); no tensor pass
         MTVQ_CUDA(launch_small_assign(z, n, d, norm_mode, codes, k, 0, 1, nullptr, ws.cc, denom, ws.small_part, nullptr,
                                       nullptr, 0, idx, ws.bins_i32, ws.full_rows, ws.counters, st), "small_assign");
@@ -337,7 +337,7 @@ int mtvq_soft_forward(const float* x, int64_t n, int d, const float* codes, int 
     if (ws.total_bytes > workspace_bytes) return fail(MTVQ_ERR_WORKSPACE, "workspace too small%s", "");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     MTVQ_CUDA(cudaMemsetAsync(ws.counters, 0, sizeof(int) * CNT_COUNT, st), "memset counters");
-    if (n > 0 && g_soft_route == 0 && !g_no_small && small_route_ok(n, d, k)) {
+    if (n > 0 && g_soft_route == 0 && !g_no_small && small_route_ok(n, d, k, MTVQ_NORM_CONTIGUOUS)) {
         // small batch (MedTok's training batches): exact scores on the CUDA cores, k-way merge, then the usual row kernel
         MTVQ_CUDA(launch_small_assign(x, n, d, MTVQ_NORM_CONTIGUOUS, codes, k, 1, topk, ws.codes_n, ws.cc, ws.denom,
                                       ws.small_part, ws.cand, ws.cand_cnt, cand_capacity(true), nullptr, nullptr, nullptr,

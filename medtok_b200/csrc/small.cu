@@ -8,8 +8,9 @@
 // arithmetic -- sequential fmaf chain over d, fl(fl(zz + cc) - 2 dot) -- on the CUDA cores, spread over the whole GPU
 // by code slice; nothing is approximate, so there is no candidate list, no margin and no resolve step:
 //
-//   small_slice_kernel  CTA = one slice of 64 codes x ALL rows: (optionally normalises its codes exactly like the
-//                       prep kernel and publishes them to codes_n / cc), 64 x 64 register-tiled distance blocks,
+//   small_prep_kernel   one warp per row and per code: the canonical l2-normalisation / squared norms (same operation
+//                       order as the loader and prep kernels of the tensor route), rows stored d-major for the tiles
+//   small_slice_kernel  CTA = one slice of 64 codes x a group of 64-row tiles: 64 x 64 register-tiled distance blocks,
 //                       per-row ascending top-k of the slice -> partial lists in an L2-resident scratch
 //   small_merge_kernel  one warp per row: k-way merge of the slices' lists -> the row's final top-k / argmin
 //
@@ -29,7 +30,7 @@ constexpr int kNanMark = -2;  // list entry: "this slice saw a NaN distance for 
 
 struct PartEntry { float v; int i; };
 
-// shared-memory layout (floats): As[d][SR] | Bs[d][SC] | raw[SC or SR][d + 1] | dist[SR][SC + 1] | zz[SR] | cc[SC]
+// shared-memory layout (floats): As[d][SR] | Bs[d][SC] | raw[64][d + 1] | dist[SR][SC + 1] | zz[SR] | cc[SC]
 __host__ __device__ inline size_t small_smem_floats(int d) {
     return (size_t)d * SR + (size_t)d * SC + (size_t)SR * (d + 1) + (size_t)SR * (SC + 1) + SR + SC;
 }
@@ -38,17 +39,84 @@ __device__ __forceinline__ bool less_vi(float v, int i, float bv, int bi) {     
     return v < bv || (v == bv && i < bi);
 }
 
+// One warp normalises one row held in shared memory IN PLACE exactly like canon_denom / canon_sumsq do with one thread:
+// the eight lane-accumulators of canon_norm8 run on lanes 0-7 and are folded in lane order, every lane then divides its
+// elements, and warp_canon_sumsq folds the 32 cascade accumulators.  Returns den (all lanes) and *sumsq.
+// kind: 0 = contiguous norm, 2 = none (do_norm false).
+__device__ __forceinline__ float warp_normalise_row(float* row, int d, bool do_norm, int lane, float* sumsq) {
+    float den = 1.0f;
+    if (do_norm) {
+        const int v = lane & 7;
+        float a = 0.f;
+        for (int c = 0; c < d; c += 8) { const float x = row[c + v]; a = __fadd_rn(a, __fmul_rn(x, x)); }
+        float sm = __shfl_sync(0xffffffffu, a, 0);
+#pragma unroll
+        for (int t = 1; t < 8; ++t) sm = __fadd_rn(sm, __shfl_sync(0xffffffffu, a, t));
+        den = __fsqrt_rn(sm);
+        den = den < kNormEps ? kNormEps : den;
+        __syncwarp();
+        for (int i = lane; i < d; i += 32) row[i] = __fdiv_rn(row[i], den);
+        __syncwarp();
+    }
+    *sumsq = warp_canon_sumsq(row, d, lane);
+    return den;
+}
+
+// raw[64][d + 1] (row-major) -> T[d][64] (d-major); rows >= nvalid become zero.  Conflict free on both sides.
+__device__ __forceinline__ void transpose_tile(const float* raw, float* T, int d, int nvalid, int tid) {
+    const int r = tid & 63;
+    for (int i = tid >> 6; i < d; i += 4) T[(size_t)i * 64 + r] = r < nvalid ? raw[r * (d + 1) + i] : 0.0f;
+}
+
+// global [rows][d] -> raw[64][d + 1] for a 16-byte vector `e` of the tile (four scalar stores: the odd row stride)
+__device__ __forceinline__ void stage_vec(float* raw, int e, int nv, int d, float4 v) {
+    const int r = e / nv, i = 4 * (e - r * nv);
+    float* dst = raw + r * (d + 1) + i;
+    dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+}
+
 }  // namespace
 
-__global__ void __launch_bounds__(256) small_slice_kernel(const float* __restrict__ x, int n, int d, int norm_mode,
-                                                           const float* __restrict__ codes, int k, int normalize,
-                                                           int topk, float* __restrict__ codes_n_out,
-                                                           float* __restrict__ cc_out, float* __restrict__ denom_out,
-                                                           PartEntry* __restrict__ part, int nslices, int nan_first) {
+// Pre-pass: one WARP per row and per code, in the canonical orders (so every slice CTA below reads finished operands
+// instead of re-deriving them): rows -> xnT[d][n_pad] (d-major: a 64-row tile of As is then a straight coalesced copy),
+// zz[n], denom[n]; codes -> cn[k][d] (when normalising), cc[k].
+__global__ void __launch_bounds__(256) small_prep_kernel(const float* __restrict__ x, int n, int n_pad, int d, int norm_mode,
+                                                          const float* __restrict__ codes, int k, int normalize,
+                                                          float* __restrict__ xnT, float* __restrict__ zz_out,
+                                                          float* __restrict__ denom_out, float* __restrict__ cn_out,
+                                                          float* __restrict__ cc_out) {
+    extern __shared__ __align__(16) float sm[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float* row = sm + wib * d;
+    const int item = blockIdx.x * 8 + wib;
+    if (item >= n + k) return;
+    const bool is_row = item < n;
+    const float* src = is_row ? x + (size_t)item * d : codes + (size_t)(item - n) * d;
+    for (int i = lane; i < d; i += 32) row[i] = __ldg(src + i);
+    __syncwarp();
+    float ss;
+    const bool do_norm = is_row ? (norm_kind(norm_mode) != 2) : (normalize != 0);
+    const float den = warp_normalise_row(row, d, do_norm, lane, &ss);
+    if (is_row) {
+        for (int i = lane; i < d; i += 32) xnT[(size_t)i * n_pad + item] = row[i];
+        if (lane == 0) { zz_out[item] = ss; if (denom_out) denom_out[item] = den; }
+    } else {
+        const int c = item - n;
+        if (cn_out && normalize) for (int i = lane; i < d; i += 32) cn_out[(size_t)c * d + i] = row[i];
+        if (lane == 0 && cc_out) cc_out[c] = ss;
+    }
+}
+
+template <int KT>   // list length kept per thread: 1 (argmin), 5 (MedTok's k) or 8
+__global__ void __launch_bounds__(256) small_slice_kernel(const float* __restrict__ xnT, const float* __restrict__ zz_in, int n,
+                                                           int n_pad, int d, int norm_mode, const float* __restrict__ cn,
+                                                           const float* __restrict__ cc_in, int k, int topk,
+                                                           PartEntry* __restrict__ part, int nslices, int nan_first,
+                                                           int rows_per_cta) {
     extern __shared__ __align__(16) float sm[];
     float* As   = sm;                                   // [d][SR]   normalised rows, d-major
     float* Bs   = As + (size_t)d * SR;                  // [d][SC]   (normalised) codes of the slice, d-major
-    float* raw  = Bs + (size_t)d * SC;                  // [64][d + 1] staging for coalesced global loads
+    float* raw  = Bs + (size_t)d * SC;                  // [64][d + 1] staging (row stride d + 1: conflict-free transpose)
     float* dist = raw + (size_t)SR * (d + 1);           // [SR][SC + 1]
     float* zzs  = dist + SR * (SC + 1);                 // [SR]
     float* ccs  = zzs + SR;                             // [SC]
@@ -57,57 +125,59 @@ __global__ void __launch_bounds__(256) small_slice_kernel(const float* __restric
     const int code0 = slice * SC;
     const int ncodes = min(SC, k - code0);
     const bool dots = score_dot(norm_mode);
+    const int nv = d >> 2;                              // float4 per row
 
-    // ---- the slice's codes: coalesced load, then one thread per code in the canonical orders of the prep kernel ----
-    for (int e = tid; e < ncodes * d; e += 256) {
-        const int c = e / d, i = e - c * d;
-        raw[c * (d + 1) + i] = __ldg(codes + (size_t)code0 * d + e);
-    }
-    __syncthreads();
-    if (tid < SC) {
-        if (tid < ncodes) {
-            const float* wr = raw + tid * (d + 1);
-            float den = 1.0f;
-            if (normalize) den = canon_denom([&](int i) { return wr[i]; }, d, 0);
-            for (int i = 0; i < d; ++i) Bs[(size_t)i * SC + tid] = normalize ? __fdiv_rn(wr[i], den) : wr[i];
-            const float c2 = canon_sumsq([&](int i) { return Bs[(size_t)i * SC + tid]; }, d);
-            ccs[tid] = dots ? 0.0f : c2;
-            if (cc_out) cc_out[code0 + tid] = c2;
-        } else {
-            for (int i = 0; i < d; ++i) Bs[(size_t)i * SC + tid] = 0.0f;
-            ccs[tid] = 0.0f;
-        }
-    }
-    __syncthreads();
-    if (codes_n_out && normalize) {                     // publish the normalised rows (soft_resolve reads them)
-        for (int e = tid; e < ncodes * d; e += 256) {
-            const int c = e / d, i = e - c * d;
-            codes_n_out[(size_t)code0 * d + e] = Bs[(size_t)i * SC + c];
-        }
-    }
-
-    const int tx = tid & 15, ty = tid >> 4;             // 4 codes x 4 rows per thread
-    for (int row0 = 0; row0 < n; row0 += SR) {
-        const int nrows = min(SR, n - row0);
-        __syncthreads();                                // previous tile: raw / As / dist are free again
-        for (int e = tid; e < nrows * d; e += 256) {
-            const int r = e / d, i = e - r * d;
-            raw[r * (d + 1) + i] = __ldg(x + (size_t)row0 * d + e);
-        }
-        __syncthreads();
-        if (tid < SR) {
-            if (tid < nrows) {
-                const float* xr = raw + tid * (d + 1);
-                const float den = canon_denom([&](int i) { return xr[i]; }, d, norm_mode);
-                if (denom_out && slice == 0) denom_out[row0 + tid] = den;
-                for (int i = 0; i < d; ++i) As[(size_t)i * SR + tid] = __fdiv_rn(xr[i], den);
-                zzs[tid] = dots ? 0.0f : canon_sumsq([&](int i) { return As[(size_t)i * SR + tid]; }, d);
-            } else {
-                for (int i = 0; i < d; ++i) As[(size_t)i * SR + tid] = 0.0f;
-                zzs[tid] = 0.0f;
+    // grid.y splits the rows: a small batch must still fill the GPU (a CTA is 8 warps; with one CTA per SM every
+    // dependent chain's latency is exposed)
+    const int row_lo = blockIdx.y * rows_per_cta, row_hi = min(n, row_lo + rows_per_cta);
+    // As tile = rows [row0, row0 + 64) of xnT: for every dimension 64 consecutive floats -> 16 d float4, d / 16 per thread
+    const int a_vecs = d * (SR / 4);
+    auto load_a = [&](int row0) {
+        for (int e0 = tid; e0 < a_vecs; e0 += 4 * 256) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * 256;
+                if (e < a_vecs) {
+                    const int i = e >> 4, r4 = e & 15;                       // dimension, float4 within the 64-row span
+                    v[u] = __ldg(reinterpret_cast<const float4*>(xnT + (size_t)i * n_pad + row0) + r4);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * 256;
+                if (e < a_vecs) reinterpret_cast<float4*>(As)[e] = v[u];
             }
         }
-        __syncthreads();
+    };
+    // ---- the slice's codes (finished by the pre-pass): coalesced 16-byte loads, transposed through `raw` ----
+    {
+        const float4* src = reinterpret_cast<const float4*>(cn + (size_t)code0 * d);
+        const int tot = ncodes * nv;
+        for (int e0 = tid; e0 < tot; e0 += 4 * 256) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (e0 + u * 256 < tot) v[u] = __ldg(src + e0 + u * 256);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (e0 + u * 256 < tot) stage_vec(raw, e0 + u * 256, nv, d, v[u]);
+        }
+        if (tid < SC) ccs[tid] = (tid < ncodes && !dots) ? __ldg(cc_in + code0 + tid) : 0.0f;
+    }
+    load_a(row_lo);                                     // (xnT is padded to whole tiles: no bounds inside a tile)
+    if (tid < SR) zzs[tid] = (row_lo + tid < n && !dots) ? __ldg(zz_in + row_lo + tid) : 0.0f;
+    __syncthreads();
+    transpose_tile(raw, Bs, d, ncodes, tid);
+    __syncthreads();
+
+    const int tx = tid & 15, ty = tid >> 4;             // 4 codes x 4 rows per thread
+    for (int row0 = row_lo; row0 < row_hi; row0 += SR) {
+        const int nrows = min(SR, n - row0);
+        if (row0 != row_lo) {
+            __syncthreads();                            // previous tile: As / zz / dist are free again
+            load_a(row0);
+            if (tid < SR) zzs[tid] = (row0 + tid < n && !dots) ? __ldg(zz_in + row0 + tid) : 0.0f;
+            __syncthreads();
+        }
         float acc[4][4];
 #pragma unroll
         for (int a = 0; a < 4; ++a)
@@ -134,19 +204,20 @@ __global__ void __launch_bounds__(256) small_slice_kernel(const float* __restric
         // per-row ascending top-k of the slice: four threads per row scan 16 codes each, then merge through shuffles
         {
             const int r = tid >> 2, q = tid & 3;        // row within the tile, quarter of the slice
-            float lv[kMaxTopS];
-            int li[kMaxTopS];
+            float lv[KT];
+            int li[KT];
             bool saw_nan = false;
 #pragma unroll
-            for (int t = 0; t < kMaxTopS; ++t) { lv[t] = INFINITY; li[t] = 0x7fffffff; }
+            for (int t = 0; t < KT; ++t) { lv[t] = INFINITY; li[t] = 0x7fffffff; }
             for (int c = q * 16; c < q * 16 + 16; ++c) {
                 if (c >= ncodes) break;
                 float v = dist[r * (SC + 1) + c];
                 int ci = code0 + c;
                 if (v != v) { saw_nan = true; continue; }   // NaN never enters a list (hard path: see below)
+                if (!less_vi(v, ci, lv[KT - 1], li[KT - 1])) continue;      // not among the KT best so far
 #pragma unroll
-                for (int t = 0; t < kMaxTopS; ++t) {
-                    if (t < topk && less_vi(v, ci, lv[t], li[t])) {
+                for (int t = 0; t < KT; ++t) {
+                    if (less_vi(v, ci, lv[t], li[t])) {
                         const float tv = lv[t]; const int ti = li[t];
                         lv[t] = v; li[t] = ci; v = tv; ci = ti;
                     }
@@ -164,8 +235,8 @@ __global__ void __launch_bounds__(256) small_slice_kernel(const float* __restric
                 }
                 if (li[0] == bi && bi != 0x7fffffff) {  // owner pops its head
 #pragma unroll
-                    for (int u = 0; u + 1 < kMaxTopS; ++u) { lv[u] = lv[u + 1]; li[u] = li[u + 1]; }
-                    lv[kMaxTopS - 1] = INFINITY; li[kMaxTopS - 1] = 0x7fffffff;
+                    for (int u = 0; u + 1 < KT; ++u) { lv[u] = lv[u + 1]; li[u] = li[u + 1]; }
+                    lv[KT - 1] = INFINITY; li[KT - 1] = 0x7fffffff;
                 }
                 if (q == 0 && r < nrows) { dst[t].v = bv; dst[t].i = bi; }
             }
@@ -178,6 +249,7 @@ __global__ void __launch_bounds__(256) small_slice_kernel(const float* __restric
 
 // one warp per row: merge the slices' ascending lists.  Soft path: cand[row] = the k winners (soft_resolve_kernel
 // re-derives their distances and does the rest); hard path (idx_out != nullptr): idx + per-code counts.
+template <int KT>
 __global__ void __launch_bounds__(256) small_merge_kernel(const PartEntry* __restrict__ part, int n, int nslices, int topk,
                                                            int* __restrict__ cand, int* __restrict__ cand_cnt, int cand_cap,
                                                            int64_t* __restrict__ idx_out, int* __restrict__ bins,
@@ -185,22 +257,31 @@ __global__ void __launch_bounds__(256) small_merge_kernel(const PartEntry* __res
     const int lane = threadIdx.x & 31;
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= n) return;
-    float lv[kMaxTopS];
-    int li[kMaxTopS];
+    float lv[KT];
+    int li[KT];
     bool nan_row = false;
 #pragma unroll
-    for (int t = 0; t < kMaxTopS; ++t) { lv[t] = INFINITY; li[t] = 0x7fffffff; }
+    for (int t = 0; t < KT; ++t) { lv[t] = INFINITY; li[t] = 0x7fffffff; }
     const PartEntry* src = part + (size_t)row * nslices * topk;
-    for (int e = lane; e < nslices * topk; e += 32) {
-        PartEntry p = src[e];
-        float v = p.v; int ci = p.i;
-        if (ci == kNanMark) { nan_row = true; continue; }
-        if (ci == 0x7fffffff) continue;
+    const int tot = nslices * topk;
+    for (int e0 = lane; e0 < tot; e0 += 8 * 32) {       // eight independent 8-byte loads in flight per lane
+        PartEntry p[8];
 #pragma unroll
-        for (int t = 0; t < kMaxTopS; ++t) {
-            if (t < topk && less_vi(v, ci, lv[t], li[t])) {
-                const float tv = lv[t]; const int ti = li[t];
-                lv[t] = v; li[t] = ci; v = tv; ci = ti;
+        for (int u = 0; u < 8; ++u) {
+            p[u].v = INFINITY; p[u].i = 0x7fffffff;
+            if (e0 + u * 32 < tot) p[u] = src[e0 + u * 32];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            float v = p[u].v; int ci = p[u].i;
+            if (ci == kNanMark) { nan_row = true; continue; }
+            if (ci == 0x7fffffff || !less_vi(v, ci, lv[KT - 1], li[KT - 1])) continue;   // empty / not among the best KT
+#pragma unroll
+            for (int t = 0; t < KT; ++t) {
+                if (less_vi(v, ci, lv[t], li[t])) {
+                    const float tv = lv[t]; const int ti = li[t];
+                    lv[t] = v; li[t] = ci; v = tv; ci = ti;
+                }
             }
         }
     }
@@ -217,8 +298,8 @@ __global__ void __launch_bounds__(256) small_merge_kernel(const PartEntry* __res
         }
         if (li[0] == bi && bi != 0x7fffffff) {
 #pragma unroll
-            for (int u = 0; u + 1 < kMaxTopS; ++u) { lv[u] = lv[u + 1]; li[u] = li[u + 1]; }
-            lv[kMaxTopS - 1] = INFINITY; li[kMaxTopS - 1] = 0x7fffffff;
+            for (int u = 0; u + 1 < KT; ++u) { lv[u] = lv[u + 1]; li[u] = li[u + 1]; }
+            lv[KT - 1] = INFINITY; li[KT - 1] = 0x7fffffff;
         }
         if (bi != 0x7fffffff) {
             ++found;
@@ -235,15 +316,9 @@ __global__ void __launch_bounds__(256) small_merge_kernel(const PartEntry* __res
     }
 }
 
-size_t small_scratch_bytes(int64_t n, int k, int topk) {
-    const size_t nslices = (size_t)(k + SC - 1) / SC;
-    return (size_t)n * nslices * (size_t)(topk < 1 ? 1 : topk) * sizeof(PartEntry);
-}
-
-bool small_route_ok(int64_t n, int d, int k) {
-    // work bound: below it the direct fp32 scan beats the tensor pass's fixed cost (tools_small_batch_probe.py); the
-    // second bound keeps the partial-list scratch at a few MB
-    return n > 0 && n <= 4096 && (double)n * (double)k * (double)d <= 1.6e9 && (double)n * (double)k <= 3.0e7;
+bool small_route_ok(int64_t n, int d, int k, int norm_mode) {
+    if ((norm_mode & 3) == 1) return false;   // the strided-view norm is a sequential sum: left to the tensor route
+    return small_route_fits(n, d, k);
 }
 
 cudaError_t launch_small_assign(const float* x, int64_t n, int d, int norm_mode, const float* codes, int k, int normalize,
@@ -255,18 +330,41 @@ cudaError_t launch_small_assign(const float* x, int64_t n, int d, int norm_mode,
     static PerDeviceOnce once;
     bool& configured = once.flag();
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(small_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(small_slice_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(small_slice_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(small_slice_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
         if (e != cudaSuccess) return e;
         configured = true;
     }
+    if (normalize && (!codes_n_out || !cc_out)) return cudaErrorInvalidValue;
+    const int n_pad = (int)small_npad(n);
     PartEntry* part = static_cast<PartEntry*>(scratch);
-    small_slice_kernel<<<nslices, 256, smem, stream>>>(x, (int)n, d, norm_mode, codes, k, normalize, topk, codes_n_out, cc_out,
-                                                       denom_out, part, nslices, idx_out != nullptr);
+    float* xnT = reinterpret_cast<float*>(static_cast<char*>(scratch) + small_part_bytes(n, k, topk));
+    float* zz = xnT + (size_t)n_pad * d;
+    // 1. canonical normalisation of rows and codes, one warp each
+    small_prep_kernel<<<(int)((n + k + 7) / 8), 256, sizeof(float) * 8 * d, stream>>>(x, (int)n, n_pad, d, norm_mode, codes, k,
+                                                                                      normalize, xnT, zz, denom_out,
+                                                                                      codes_n_out, cc_out);
     ++g_kernel_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    small_merge_kernel<<<(int)((n * 32 + 255) / 256), 256, 0, stream>>>(part, (int)n, nslices, topk, cand, cand_cnt, cand_cap,
-                                                                         idx_out, bins, full_rows, counters);
+    // 2. (slice, row group) grid: at least ~3 CTAs per SM when the problem allows, whole 64-row tiles per CTA
+    auto kern = topk == 1 ? small_slice_kernel<1> : (topk <= 5 ? small_slice_kernel<5> : small_slice_kernel<8>);
+    const int ntiles = (int)((n + SR - 1) / SR);
+    int tiles_per_cta = (int)(((int64_t)ntiles * nslices) / 444);
+    if (tiles_per_cta < 1) tiles_per_cta = 1;
+    const int groups = (ntiles + tiles_per_cta - 1) / tiles_per_cta;
+    kern<<<dim3(nslices, groups), 256, smem, stream>>>(xnT, zz, (int)n, n_pad, d, norm_mode, normalize ? codes_n_out : codes,
+                                                      cc_out, k, topk, part, nslices, idx_out != nullptr, tiles_per_cta * SR);
+    ++g_kernel_launches;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    // 3. per-row merge of the slices' lists
+    auto merge = topk == 1 ? small_merge_kernel<1> : (topk <= 5 ? small_merge_kernel<5> : small_merge_kernel<8>);
+    merge<<<(int)((n * 32 + 255) / 256), 256, 0, stream>>>(part, (int)n, nslices, topk, cand, cand_cnt, cand_cap, idx_out, bins,
+                                                            full_rows, counters);
     ++g_kernel_launches;
     return cudaGetLastError();
 }

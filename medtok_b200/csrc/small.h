@@ -9,8 +9,7 @@ namespace mtvq {
 
 // true when n rows x k codes x d dims is small enough that scoring every pair exactly on the CUDA cores beats the
 // fixed cost of the tensor pass (the batch sizes MedTok's training loop uses)
-bool   small_route_ok(int64_t n, int d, int k);
-size_t small_scratch_bytes(int64_t n, int k, int topk);
+bool   small_route_ok(int64_t n, int d, int k, int norm_mode);
 
 // exact top-k (soft: cand / cand_cnt get the k winners per row; codes normalised when `normalize`, published to
 // codes_n_out / cc_out) or exact argmin (hard: idx_out + bins; rows with NaN distances go to full_rows / CNT_FULL for

@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(kSoftWarps * 32) soft_resolve_kernel(
     const float* __restrict__ cn, const float* __restrict__ cc, const int* __restrict__ cand,
     const int* __restrict__ cand_cnt, int cand_cap, int64_t* __restrict__ idx_out, float* __restrict__ val_out,
     float* __restrict__ wts_out, float* __restrict__ zq_out, float* __restrict__ out, double* __restrict__ sse_out,
-    int* __restrict__ full_rows, int* __restrict__ counters) {
+    int* __restrict__ full_rows, int* __restrict__ counters, int split) {
     extern __shared__ __align__(16) float soft_smem[];
     const int topk = (KT == 5) ? 5 : topk_rt;    // compile-time for MedTok's k = 5: the per-row loops below fully unroll
     const int lane = threadIdx.x & 31;
@@ -94,9 +94,15 @@ __global__ void __launch_bounds__(kSoftWarps * 32) soft_resolve_kernel(
     // per step; while a step is being scored the raw rows and candidate lists of the next step are already in flight,
     // so no HBM round trip sits on the critical path (L2 gather of the candidates -> fmaf chain -> merge -> gather of
     // the top-k rows, which the staging has just pulled into L1).
+    // (`split`: few rows -- a warp takes ONE four-row step of a 32-row block instead of all eight, so that a small batch
+    //  spreads over the GPU instead of serialising eight dependent gather chains in a handful of warps)
     const int64_t nblk = (n + 31) >> 5;
-    for (int64_t blk = warp; blk < nblk; blk += nwarps) {
+    const int64_t nitems = split ? nblk * 8 : nblk;
+    for (int64_t item = warp; item < nitems; item += nwarps) {
+      const int64_t blk = split ? (item >> 3) : item;
+      const int s_lo = split ? (int)(item & 7) : 0, s_hi = split ? s_lo + 1 : 8;
       const int64_t base = blk << 5;
+      if (base + 4 * s_lo >= n) continue;
       int cnt_l = 0;
       float den_l = 1.0f;
       if (base + lane < n) { cnt_l = cand_cnt[base + lane]; den_l = denom[base + lane]; }
@@ -114,8 +120,8 @@ __global__ void __launch_bounds__(kSoftWarps * 32) soft_resolve_kernel(
           for (int b = 0; b < kLaneList; ++b)
               ncl[b] = (row < n && g + 8 * b < cand_cap) ? __ldcs(cand + row * cand_cap + g + 8 * b) : -1;
       };
-      fetch(0);
-      for (int step = 0; step < 8 && base + 4 * step < n; ++step) {
+      fetch(s_lo);
+      for (int step = s_lo; step < s_hi && base + 4 * step < n; ++step) {
         const int64_t row = base + 4 * step + grp;
         const int cnt = __shfl_sync(0xffffffffu, cnt_l, 4 * step + grp);
         const float den = __shfl_sync(0xffffffffu, den_l, 4 * step + grp);
@@ -133,7 +139,7 @@ __global__ void __launch_bounds__(kSoftWarps * 32) soft_resolve_kernel(
                 *reinterpret_cast<float4*>(xs + 4 * f) = make_float4(__fdiv_rn(xr[q].x, den), __fdiv_rn(xr[q].y, den),
                                                                      __fdiv_rn(xr[q].z, den), __fdiv_rn(xr[q].w, den));
         }
-        if (step + 1 < 8 && base + 4 * (step + 1) < n) fetch(step + 1);
+        if (step + 1 < s_hi && base + 4 * (step + 1) < n) fetch(step + 1);
         const bool active = row < n && cnt >= topk && cnt <= cand_cap;
         if (row < n && !active && g == 0) full_rows[atomicAdd(&counters[CNT_FULL], 1)] = (int)row;
         __syncwarp();
@@ -526,9 +532,12 @@ cudaError_t launch_soft_resolve(const float* x, int64_t n, int d, int k, int top
     }
     const int per_sm = (int)((220 * 1024) / (smem + 1024)) < 1 ? 1 : (int)((220 * 1024) / (smem + 1024));
     int64_t blocks = (n + 32 * warps - 1) / (32 * warps);
+    // small batches: one four-row step per warp when that still fits the resident warps
+    const int split = ((n + 3) / 4 <= (int64_t)num_sms * per_sm * warps) ? 1 : 0;
+    if (split) blocks = ((n + 31) / 32 * 8 + warps - 1) / warps;
     if (blocks > (int64_t)num_sms * per_sm) blocks = (int64_t)num_sms * per_sm;   // all resident; warps stride over 32-row blocks
 #define MTVQ_SOFT_ARGS x, ws.denom, n, d, k, topk, ws.codes_n, ws.cc, ws.cand, ws.cand_cnt, cap, idx, vals, wts, zq, out, sse, \
-                       ws.full_rows, ws.counters
+                       ws.full_rows, ws.counters, split
 #define MTVQ_SOFT_LAUNCH(NQ_)                                                                                      \
     do {                                                                                                           \
         if (topk == 5) soft_resolve_kernel<NQ_, 5><<<(int)blocks, warps * 32, smem, stream>>>(MTVQ_SOFT_ARGS);     \

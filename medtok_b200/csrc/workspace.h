@@ -59,6 +59,22 @@ inline int    pad_codes(int k) { return (int)align_up((size_t)k, 128); }
 inline int    cand_capacity(bool soft) { return soft ? 24 : 16; }
 inline size_t image_bytes(int d, int k) { return (size_t)(pad_codes(k) / 128) * (size_t)(d / 8 + 2) * 2048; }
 
+// Small-batch route (small.cu): work bound below which scoring every (row, code) pair exactly on the CUDA cores beats the
+// tensor pass's fixed cost, and its scratch: the partial top-k lists -- 8 bytes per (row, 64-code slice, list entry), a few
+// MB under the second bound -- followed by the normalised rows stored d-major (xnT[d][n_pad]) and their squared norms.
+inline bool   small_route_fits(int64_t n, int d, int k) {
+    // measured crossover on B200 (tools_small_batch_probe.py, D = 64): N = 256 x K = 21000 -> 100 us here vs 164 us on the
+    // tensor route; N = 1024 x K = 7000 -> 103 vs 104 us; N = 1024 x K = 21000 -> 230 vs 169 us
+    return n > 0 && n <= 4096 && (double)n * (double)k * (double)d <= 6.0e8 && (double)n * (double)k <= 3.0e7;
+}
+inline size_t small_npad(int64_t n) { return align_up((size_t)n, 64); }
+inline size_t small_part_bytes(int64_t n, int k, int topk) {
+    return align_up((size_t)n * (size_t)((k + 63) / 64) * (size_t)(topk < 1 ? 1 : topk) * 8, 256);
+}
+inline size_t small_scratch_bytes(int64_t n, int d, int k, int topk) {
+    return small_part_bytes(n, k, topk) + sizeof(float) * small_npad(n) * ((size_t)d + 1);
+}
+
 // topk == 0: hard path only; topk >= 1: the buffers of the soft path (normalised codebook, per-CTA record scratch, wider
 // candidate lists) as well -- also for top-1, which VectorQuantizer(..., k=1) may ask for.  Everything whose size does
 // not depend on the path comes first, so those offsets (counters, ...) are the same for both.
@@ -90,10 +106,7 @@ inline Workspace carve(void* base, int64_t n, int d, int k, int topk) {
     w.cand      = (int*)take(sizeof(int) * n * cand_cap);
     w.codes_n   = (float*)take(soft ? sizeof(float) * (size_t)k * d : 0);
     w.topk_scratch = take(soft ? (size_t)160 * (8 * 4 * 1024 * 16) : 0);   // kTopkMaxCtas x kTopkScratchPerCta
-    // small-batch route (small.cu): 8 bytes per (row, 64-code slice, list entry); the route's own bounds (n <= 4096,
-    // n * k <= 3e7) keep this below ~30 MB
-    const bool small = n > 0 && n <= 4096 && (double)n * (double)k * (double)d <= 1.6e9 && (double)n * (double)k <= 3.0e7;
-    w.small_part = take(small ? (size_t)n * (size_t)((k + 63) / 64) * (size_t)(soft ? topk : 1) * 8 : 0);
+    w.small_part = take(small_route_fits(n, d, k) ? small_scratch_bytes(n, d, k, soft ? topk : 1) : 0);
     w.total_bytes = off;
     return w;
 }

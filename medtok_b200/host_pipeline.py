@@ -12,7 +12,7 @@ import torch
 
 
 class HostStream:
-    def __init__(self, module, rows: int, dim: int, device, depth: int = 2):
+    def __init__(self, module, rows: int, dim: int, device, depth: int = 2, return_zq: bool = False):
         self.module = module
         self.device = torch.device(device)
         self.depth = depth
@@ -21,11 +21,14 @@ class HostStream:
         self.z_dev = [torch.empty(rows, dim, 1, 1, device=self.device) for _ in range(depth)]
         self.idx_host = [torch.empty(rows, dtype=torch.int64).pin_memory() for _ in range(depth)]
         self.loss_host = [torch.empty(1).pin_memory() for _ in range(depth)]
+        # return_zq: the quantised rows come back too (the reference's whole return tuple); otherwise a consumer that
+        # only needs tokens reconstructs them host-side as codebook[idx]
+        self.zq_host = [torch.empty(rows, dim).pin_memory() for _ in range(depth)] if return_zq else None
         self.uploaded = [torch.cuda.Event() for _ in range(depth)]
         self.computed = [torch.cuda.Event() for _ in range(depth)]
         self.downloaded = [torch.cuda.Event() for _ in range(depth)]
         self.h2d_bytes = rows * dim * 4
-        self.d2h_bytes = rows * 8 + 4
+        self.d2h_bytes = rows * 8 + 4 + (rows * dim * 4 if return_zq else 0)
 
     @torch.no_grad()
     def run(self, host_batches):
@@ -48,9 +51,12 @@ class HostStream:
                 self.copy_out.wait_event(self.computed[s])
                 self.idx_host[s].copy_(idx, non_blocking=True)
                 self.loss_host[s].copy_(loss.reshape(1), non_blocking=True)
+                if self.zq_host is not None:
+                    self.zq_host[s].copy_(z_q.reshape(self.zq_host[s].shape), non_blocking=True)
                 self.downloaded[s].record(self.copy_out)
             idx.record_stream(self.copy_out)
             loss.record_stream(self.copy_out)
+            z_q.record_stream(self.copy_out)
             n += 1
         return n
 

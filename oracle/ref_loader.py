@@ -1,12 +1,15 @@
-"""Import the UNMODIFIED reference quantizer modules from /root/reference (authoring container
-only; the GPU box has no /root/reference, so nothing in tests -m gpu, smoke() or bench.py may
-call this).  Recipe from SURVEY.md Appendix C: skip MedTok/__init__.py (it pulls dgl) by
+"""Import the UNMODIFIED reference quantizer modules: from /root/reference in the authoring container, from the
+byte-identical copies under oracle/_ref/ (oracle/build_ref.py) on the GPU box, where only bench.py's CPU legs
+(`--impl reference`, `cpu_baseline`) use them.  Recipe from SURVEY.md Appendix C: skip MedTok/__init__.py (it pulls dgl) by
 registering a stub package, and shim two unused names that transformers>=5 dropped."""
 import os
 import sys
 import types
 
 REF_ROOT = os.environ.get("MEDTOK_REFERENCE", "/root/reference")
+if not os.path.isfile(os.path.join(REF_ROOT, "MedTok", "norm_ema_quantizer.py")):
+    # GPU box: the byte-identical copies staged by oracle/build_ref.py (git-ignored, travel with the tree)
+    REF_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 
 
 def available() -> bool:
