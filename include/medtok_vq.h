@@ -112,6 +112,13 @@ MTVQ_API int mtvq_ema_finalize_peers(float *weight, float *cluster_size, const v
                             void *const *peer_flags, int world, int rank, unsigned epoch, int k, int d, double beta,
                             double decay, int update_cluster_size, int update_weight, float *loss, void *stream);
 
+/* Backward of mtvq_hard_forward w.r.t. z (the codebook gets no gradient, norm_ema_quantizer.py:212-214):
+ *   g = g_zq + g_loss * 2 beta / (n d) * (zf - z_q);   grad_z = (g - zf (zf . g)) / max(||z||, 1e-12)
+ * z: the raw rows of the forward (contiguous [n,d]); z_q: its output; g_zq [n,d] may be NULL (no gradient through the
+ * straight-through output); g_loss [1] (device) may be NULL.  fp32. */
+MTVQ_API int mtvq_hard_backward(const float *z, const float *z_q, const float *g_zq, const float *g_loss,
+                       int64_t n, int d, double beta, float *grad_z, void *stream);
+
 /* Pieces of the forward, exposed for tests, k-means and the lookup-only VectorQuantizer
  * (norm_ema_quantizer.py:222-268). */
 

@@ -39,6 +39,7 @@ _SIGNATURES = {
     "mtvq_ema_finalize": (_int, [_vp, _vp, _vp, _int, _int, _dbl, _dbl, _int, _int, _vp, _vp]),
     "mtvq_ema_finalize_peers": (_int, [_vp, _vp, _vp, _vp, _int, _int, ctypes.c_uint, _int, _int, _dbl, _dbl, _int, _int,
                                        _vp, _vp]),
+    "mtvq_hard_backward": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _dbl, _vp, _vp]),
     "mtvq_kmeans_update": (_int, [_vp, _vp, _int, _int, _vp]),
     "mtvq_hard_assign": (_int, [_vp, _i64, _int, _int, _vp, _int, _vp, _vp, _vp, _sz, _vp]),
     "mtvq_hard_assign_exact": (_int, [_vp, _i64, _int, _int, _vp, _int, _vp, _vp, _vp, _sz, _vp]),

@@ -291,6 +291,20 @@ int mtvq_hard_forward(const float* z, int64_t n, int d, int norm_mode, float* we
     return 0;
 }
 
+int mtvq_hard_backward(const float* z, const float* z_q, const float* g_zq, const float* g_loss, int64_t n, int d,
+                       double beta, float* grad_z, void* stream) {
+    if (int r = check_dims(n, d, 1)) return r;
+    if (n > 0 && (!z || !z_q || !grad_z)) return fail(MTVQ_ERR_BAD_ARG, "null pointer%s", "");
+    if (!aligned16(z) || !aligned16(z_q) || !aligned16(grad_z) || (g_zq && !aligned16(g_zq)))
+        return fail(MTVQ_ERR_BAD_ARG, "16-byte alignment%s", "");
+    DeviceInfo di;
+    if (int r = device_info(&di)) return r;
+    if (n > 0)
+        MTVQ_CUDA(launch_hard_backward(z, z_q, g_zq, g_loss, n, d, beta, grad_z, di.num_sms, static_cast<cudaStream_t>(stream)),
+                  "hard_backward");
+    return 0;
+}
+
 int mtvq_lookup(const float* z, const float* weight, const int64_t* idx, int64_t n, int d, int k, float* z_q,
                 double* sse, float* counts, void* workspace, size_t workspace_bytes, void* stream) {
     if (int r = check_dims(n, d, k)) return r;

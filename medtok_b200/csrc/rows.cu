@@ -96,6 +96,54 @@ __global__ void __launch_bounds__(256) gather_ste_kernel(const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
+// backward of the hard forward (norm_ema_quantizer.py:212-214 through l2norm :8-9): the only
+// gradient goes to z --  g = g_zq + g_loss * 2 beta / (N D) * (zf - z_q),  grad_z = (g - zf (zf . g)) / max(|z|, eps).
+// One warp per row, fp32 (a gradient, not part of the bit-exact contract).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) hard_backward_kernel(const float* __restrict__ z, const float* __restrict__ z_q,
+                                                             const float* __restrict__ g_zq, const float* __restrict__ g_loss,
+                                                             int64_t n, int d, float coef, float* __restrict__ grad_z) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float gl = g_loss ? __ldg(g_loss) * coef : 0.0f;
+    const int nv = d >> 2;
+    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += nwarps) {
+        const float4* zr = reinterpret_cast<const float4*>(z + row * d);
+        float ss = 0.f;
+        for (int v = lane; v < nv; v += 32) {
+            const float4 x = __ldg(zr + v);
+            ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        const float den = fmaxf(sqrtf(ss), kNormEps), rden = 1.0f / den;
+        float dotg = 0.f;
+        for (int v = lane; v < nv; v += 32) {
+            const float4 x = __ldg(zr + v);
+            const float4 q = __ldg(reinterpret_cast<const float4*>(z_q + row * d) + v);
+            const float4 go = g_zq ? __ldg(reinterpret_cast<const float4*>(g_zq + row * d) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float f0 = x.x * rden, f1 = x.y * rden, f2 = x.z * rden, f3 = x.w * rden;
+            dotg += f0 * (go.x + gl * (f0 - q.x)) + f1 * (go.y + gl * (f1 - q.y)) + f2 * (go.z + gl * (f2 - q.z)) +
+                    f3 * (go.w + gl * (f3 - q.w));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dotg += __shfl_xor_sync(0xffffffffu, dotg, o);
+        for (int v = lane; v < nv; v += 32) {
+            const float4 x = __ldg(zr + v);
+            const float4 q = __ldg(reinterpret_cast<const float4*>(z_q + row * d) + v);
+            const float4 go = g_zq ? __ldg(reinterpret_cast<const float4*>(g_zq + row * d) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float f0 = x.x * rden, f1 = x.y * rden, f2 = x.z * rden, f3 = x.w * rden;
+            float4 o;
+            o.x = (go.x + gl * (f0 - q.x) - f0 * dotg) * rden;
+            o.y = (go.y + gl * (f1 - q.y) - f1 * dotg) * rden;
+            o.z = (go.z + gl * (f2 - q.z) - f2 * dotg) * rden;
+            o.w = (go.w + gl * (f3 - q.w) - f3 * dotg) * rden;
+            __stcs(reinterpret_cast<float4*>(grad_z + row * d) + v, o);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // lookup-only quantizer (norm_ema_quantizer.py:222-268): z_q = w[idx]; optional SSE against raw z (:262-264)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) lookup_kernel(const float* __restrict__ z, const float* __restrict__ w,
@@ -613,6 +661,14 @@ cudaError_t launch_usage(const float* window, const int64_t* idx, int64_t cur, i
 cudaError_t launch_gather_ste(const float* z, const float* denom, const float* w, const int64_t* idx, int64_t n, int d,
                               int k, float* z_q, double* stats, int num_sms, cudaStream_t s) {
     gather_ste_kernel<<<grid_for(n * (d / 4), 256 * 4, num_sms, 6), 256, 0, s>>>(z, denom, w, idx, n, d, k, z_q, stats);
+    ++g_kernel_launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hard_backward(const float* z, const float* z_q, const float* g_zq, const float* g_loss, int64_t n, int d,
+                                 double beta, float* grad_z, int num_sms, cudaStream_t s) {
+    const float coef = (float)(2.0 * beta / ((double)n * (double)d));
+    hard_backward_kernel<<<grid_for(n * 32, 256, num_sms, 16), 256, 0, s>>>(z, z_q, g_zq, g_loss, n, d, coef, grad_z);
     ++g_kernel_launches;
     return cudaGetLastError();
 }

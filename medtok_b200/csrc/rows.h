@@ -17,6 +17,9 @@ cudaError_t launch_usage(const float* window, const int64_t* idx, int64_t cur, i
                          unsigned* bitmap, int* distinct, int num_sms, cudaStream_t s);
 cudaError_t launch_gather_ste(const float* z, const float* denom, const float* w, const int64_t* idx, int64_t n, int d,
                               int k, float* z_q, double* stats, int num_sms, cudaStream_t s);
+// gradient of (z_q, loss) w.r.t. the raw rows z (straight-through + commitment term through l2norm)
+cudaError_t launch_hard_backward(const float* z, const float* z_q, const float* g_zq, const float* g_loss, int64_t n, int d,
+                                 double beta, float* grad_z, int num_sms, cudaStream_t s);
 cudaError_t launch_code_sums(const float* z, const float* denom, const int64_t* idx, int64_t n, int d, int k,
                              double* stats, const Workspace& ws, bool want_sums, int num_sms, cudaStream_t s);
 cudaError_t launch_sorted_rows(const float* z, const float* denom, const float* w, const int64_t* idx, int64_t n, int d,

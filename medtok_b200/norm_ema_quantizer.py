@@ -205,15 +205,19 @@ class _HardQuantizeFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_zq, g_loss, _g_idx):
+        """one fused row kernel (mtvq_hard_backward); a channel-strided forward input (h*w > 1) arrives here as the
+        [N, D] rows autograd made contiguous, so the same kernel serves both layouts"""
         z_rows, z_q = ctx.saved_tensors
-        z32 = z_rows.float()
-        den = z32.norm(dim=-1, keepdim=True).clamp_min(1e-12)
-        zf = z32 / den
-        g = torch.zeros_like(zf) if g_zq is None else g_zq.float().clone()
-        if g_loss is not None:
-            g = g + g_loss * (2.0 * ctx.beta / zf.numel()) * (zf - z_q)
-        gz = (g - zf * (zf * g).sum(-1, keepdim=True)) / den
-        return gz.to(z_rows.dtype), None, None
+        z32 = _rows_f32(z_rows)
+        n, d = z32.shape
+        grad = torch.empty_like(z32)
+        go = None if g_zq is None else g_zq.detach().float().contiguous()
+        gl = None if g_loss is None else g_loss.detach().float().reshape(1).contiguous()
+        with torch.cuda.device(z32.device):
+            _lib.check(_lib.lib().mtvq_hard_backward(_lib.ptr(z32), _lib.ptr(z_q), _lib.ptr(go), _lib.ptr(gl), n, d,
+                                                     float(ctx.beta), _lib.ptr(grad), _lib.stream_ptr(z32.device)),
+                       "mtvq_hard_backward")
+        return grad.to(z_rows.dtype), None, None
 
 
 class NormEMAVectorQuantizer(nn.Module):
