@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MTVQ_ABI_VERSION 1
+#define MTVQ_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define MTVQ_API __attribute__((visibility("default")))
@@ -100,17 +100,25 @@ MTVQ_API int mtvq_ema_finalize(float *weight, float *cluster_size, const double 
                       float *loss, void *stream);
 
 /* mtvq_ema_finalize fused with the cross-GPU exchange of the statistics (replaces the all-reduces of
- * norm_ema_quantizer.py:188,195,203 AND the update :197-210 with ONE kernel per rank).  peer_stats / peer_flags are
- * DEVICE arrays of `world` pointers: peer_stats[r] = rank r's packed statistics of this step (mtvq_hard_forward with
- * MTVQ_F_SKIP_FINALIZE), peer_flags[r] = rank r's flag array (>= world uint32, zero before the first step), both mapped
- * into this process (CUDA IPC / symmetric memory over NVLink).  `epoch` must grow by one per call and be the same on
- * every rank; the caller alternates between two statistics buffers (epoch parity) so that a rank running ahead never
- * overwrites what a peer still reads.  The kernel signals "rank's statistics complete" with one releasing system-scope
- * store per peer, waits for all peers, and sums the partial statistics in rank order in fp64, so every rank ends up
- * with bit-identical weight / cluster_size.  loss (may be NULL) receives beta * sum(sse) / (sum(rows) * d). */
+ * norm_ema_quantizer.py:188,195,203 AND the update :197-210 with ONE kernel per rank, reduce-scatter shape).
+ * peer_stats / peer_flags / peer_results are DEVICE arrays of `world` pointers into buffers mapped into this process
+ * (CUDA IPC / symmetric memory over NVLink):
+ *   peer_stats[r]    rank r's packed statistics of this step (mtvq_hard_forward with MTVQ_F_SKIP_FINALIZE)
+ *   peer_flags[r]    rank r's flag array, >= 129 uint32, zero before the first step
+ *   peer_results[r]  rank r's result buffer, k*d + k floats
+ * `epoch` must grow by one per call and be the same on every rank; the caller alternates between two statistics buffers
+ * (epoch parity) so that a rank running ahead never overwrites what a peer still reads.  Each rank owns a contiguous slice
+ * of the codes: it waits until every peer has announced its statistics (one releasing system-scope store per peer), sums
+ * the W partial statistics OF ITS SLICE in rank order in fp64 straight out of the peers' memory, applies the EMA step,
+ * pushes the new rows / cluster sizes into every peer's result buffer, announces the slice, and copies the other
+ * slices out of its own result buffer as their owners announce them.  Every row is computed once and copied, so all
+ * ranks end up with bit-identical weight / cluster_size, and a rank moves ~(statistics + codebook) bytes over NVLink
+ * instead of world x statistics.  loss (may be NULL) receives beta * sum(sse) / (sum(rows) * d).  A peer that never
+ * arrives makes the kernel trap after MEDTOK_EXCHANGE_TIMEOUT_S (default 600) seconds instead of hanging. */
 MTVQ_API int mtvq_ema_finalize_peers(float *weight, float *cluster_size, const void *const *peer_stats,
-                            void *const *peer_flags, int world, int rank, unsigned epoch, int k, int d, double beta,
-                            double decay, int update_cluster_size, int update_weight, float *loss, void *stream);
+                            void *const *peer_flags, void *const *peer_results, int world, int rank, unsigned epoch,
+                            int k, int d, double beta, double decay, int update_cluster_size, int update_weight,
+                            float *loss, void *stream);
 
 /* Backward of mtvq_hard_forward w.r.t. z (the codebook gets no gradient, norm_ema_quantizer.py:212-214):
  *   g = g_zq + g_loss * 2 beta / (n d) * (zf - z_q);   grad_z = (g - zf (zf . g)) / max(||z||, 1e-12)
@@ -224,11 +232,6 @@ MTVQ_API int mtvq_debug_set_trace(void *trace_dev);
  * rows), 1 = two tensor passes for every row (k-th score bound, then collect), 2 = no tensor pass, every row scored
  * against every code by the exact CUDA-core scan (cross-check; slow).  All three give bit-identical results. */
 MTVQ_API int mtvq_debug_set_soft_route(int route);
-
-/* micro-benchmarks used to size the epilogue (DESIGN.md "measured machine limits"):
- * which = 0: tcgen05.ld throughput, 1: FMNMX3 tree throughput; result_host[0] = device ms,
- * result_host[1] = bytes or ops processed. */
-MTVQ_API int mtvq_microbench(int which, int warps, int iters, double *result_host, void *stream);
 
 #ifdef __cplusplus
 }

@@ -37,8 +37,8 @@ _SIGNATURES = {
     "mtvq_hard_forward": (_int, [_vp, _i64, _int, _int, _vp, _int, _vp, _dbl, _dbl, ctypes.c_uint,
                                  _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mtvq_ema_finalize": (_int, [_vp, _vp, _vp, _int, _int, _dbl, _dbl, _int, _int, _vp, _vp]),
-    "mtvq_ema_finalize_peers": (_int, [_vp, _vp, _vp, _vp, _int, _int, ctypes.c_uint, _int, _int, _dbl, _dbl, _int, _int,
-                                       _vp, _vp]),
+    "mtvq_ema_finalize_peers": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _int, ctypes.c_uint, _int, _int, _dbl, _dbl, _int,
+                                       _int, _vp, _vp]),
     "mtvq_hard_backward": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _dbl, _vp, _vp]),
     "mtvq_kmeans_update": (_int, [_vp, _vp, _int, _int, _vp]),
     "mtvq_hard_assign": (_int, [_vp, _i64, _int, _int, _vp, _int, _vp, _vp, _vp, _sz, _vp]),
@@ -57,10 +57,11 @@ _SIGNATURES = {
     "mtvq_debug_set_events": (_int, [_vp, _vp]),
     "mtvq_debug_set_trace": (_int, [_vp]),
     "mtvq_debug_set_soft_route": (_int, [_int]),
-    "mtvq_microbench": (_int, [_int, _int, _int, ctypes.POINTER(_dbl), _vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+# diagnostics exported only by the `probe` build (medtok_b200/build.py --variant probe -DMTVQ_WITH_MICROBENCH)
+_PROBE_SIGNATURES = {"mtvq_microbench": (_int, [_int, _int, _int, ctypes.POINTER(_dbl), _vp])}
 
 _LIB = None
 
@@ -82,7 +83,12 @@ def lib() -> ctypes.CDLL:
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.mtvq_abi_version() != 1:
+        for name, (res, args) in _PROBE_SIGNATURES.items():
+            if hasattr(handle, name):
+                fn = getattr(handle, name)
+                fn.restype = res
+                fn.argtypes = args
+        if handle.mtvq_abi_version() != 2:
             raise MedTokVQError("libmedtok_vq.so ABI version mismatch")
         _LIB = handle
     return _LIB

@@ -14,7 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "_build")
 SO_PATH = os.path.join(HERE, "libmedtok_vq.so")
-SOURCES = ["api.cu", "assign_tc.cu", "assign_exact.cu", "rows.cu", "soft.cu", "small.cu", "microbench.cu"]
+SOURCES = ["api.cu", "assign_tc.cu", "assign_exact.cu", "rows.cu", "soft.cu", "small.cu"]
+PROBE_SOURCES = ["microbench.cu"]          # diagnostics: only in builds made with -DMTVQ_WITH_MICROBENCH
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr"]
 
@@ -59,8 +60,9 @@ def build(force: bool = False, verbose: bool = False, variant: str = "", defines
             sys.stderr.write(r.stderr)
         return obj
 
-    with concurrent.futures.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
-        objs = list(ex.map(compile_one, SOURCES))
+    sources = SOURCES + (PROBE_SOURCES if "-DMTVQ_WITH_MICROBENCH" in defines else [])
+    with concurrent.futures.ThreadPoolExecutor(max_workers=len(sources)) as ex:
+        objs = list(ex.map(compile_one, sources))
     # api.cu marks the exported symbols; everything else stays hidden
     link = [nvcc, "-shared", "-o", so_path, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
             "-Xcompiler", "-fPIC", "-lcudart_static", "-lpthread", "-ldl", "-lrt"]

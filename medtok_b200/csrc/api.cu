@@ -9,7 +9,9 @@
 #include "../../include/medtok_vq.h"
 #include "assign_exact.h"
 #include "assign_tc.h"
+#ifdef MTVQ_WITH_MICROBENCH
 #include "microbench.h"
+#endif
 #include "rows.h"
 #include "small.h"
 #include "soft.h"
@@ -235,16 +237,17 @@ int mtvq_kmeans_update(float* means, const double* stats, int k, int d, void* st
 }
 
 int mtvq_ema_finalize_peers(float* weight, float* cluster_size, const void* const* peer_stats, void* const* peer_flags,
-                            int world, int rank, unsigned epoch, int k, int d, double beta, double decay,
-                            int update_cluster_size, int update_weight, float* loss, void* stream) {
+                            void* const* peer_results, int world, int rank, unsigned epoch, int k, int d, double beta,
+                            double decay, int update_cluster_size, int update_weight, float* loss, void* stream) {
     if (int r = check_dims(0, d, k)) return r;
-    if (!peer_stats || !peer_flags || (update_weight && !weight) || (update_cluster_size && !cluster_size))
+    if (!peer_stats || !peer_flags || !peer_results || (update_weight && !weight) || (update_cluster_size && !cluster_size))
         return fail(MTVQ_ERR_BAD_ARG, "null pointer%s", "");
     if (world < 1 || world > 64 || rank < 0 || rank >= world) return fail(MTVQ_ERR_BAD_ARG, "bad world / rank%s", "");
     DeviceInfo di;
     if (int r = device_info(&di)) return r;
-    MTVQ_CUDA(launch_ema_finalize_peers(weight, cluster_size, peer_stats, peer_flags, world, rank, epoch, k, d, beta, decay,
-                                        update_cluster_size, update_weight, loss, static_cast<cudaStream_t>(stream)),
+    MTVQ_CUDA(launch_ema_finalize_peers(weight, cluster_size, peer_stats, peer_flags, peer_results, world, rank, epoch, k, d,
+                                        beta, decay, update_cluster_size, update_weight, loss, di.num_sms,
+                                        static_cast<cudaStream_t>(stream)),
               "ema_finalize_peers");
     return 0;
 }
@@ -493,11 +496,13 @@ int mtvq_debug_set_events(void* event_before, void* event_after) {
     return 0;
 }
 
+#ifdef MTVQ_WITH_MICROBENCH
 int mtvq_microbench(int which, int warps, int iters, double* result_host, void* stream) {
     DeviceInfo di;
     if (int r = device_info(&di)) return r;
     MTVQ_CUDA(run_microbench(which, warps, iters, di.num_sms, result_host, static_cast<cudaStream_t>(stream)), "microbench");
     return 0;
 }
+#endif
 
 }  // extern "C"

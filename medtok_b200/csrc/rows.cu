@@ -464,6 +464,7 @@ struct PeerTable {
     int world, rank;
     unsigned epoch;
     unsigned long long timeout_ns;   // upper bound on the wait for the peers' flags
+    float* const*        results;    // [world] peer-mapped result buffers: updated rows [k*d] | cluster_size [k]  (fp32)
 };
 
 __device__ __forceinline__ unsigned long long global_timer_ns() {
@@ -608,6 +609,177 @@ __global__ void __launch_bounds__(256) kmeans_update_kernel(float* __restrict__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Exchange fused into the finalize, reduce-scatter shape (norm_ema_quantizer.py:188,195,203 + :197-210 in ONE kernel per
+// rank).  The codes are split into `world` contiguous slices; rank r
+//   1. announces "my statistics of step `epoch` are complete" (one releasing system-scope store per peer) and waits for
+//      every peer's announcement;
+//   2. for the codes of ITS slice only: reads the W partial statistics straight out of the peers' memory over NVLink
+//      (16-byte loads, several in flight per thread), adds them in rank order in fp64, runs the EMA / re-normalisation
+//      and writes the new rows + cluster_size both into its own codebook and into every peer's result buffer;
+//   3. announces "my slice is final" to every peer (second flag bank), and copies the other slices, as their owners
+//      announce them, from its local result buffer into its codebook.
+// Every row is computed by exactly one rank and copied by the others, so the replicas are bit-identical by construction;
+// a rank moves ~ (stats + codebook) bytes over NVLink per step instead of world x stats.
+// The grid is persistent (all CTAs co-resident) and walks the CTA's own-slice blocks before any foreign block, so no CTA
+// can spin on a peer while one of its own blocks -- which that peer may be waiting for -- is still unscheduled.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 ld_cv_f64x2(const double* p) {
+    double2 v;
+    asm volatile("ld.global.cv.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void wait_flag(const unsigned* flag, unsigned epoch, const PeerTable& pt, int who) {
+    const unsigned long long t0 = global_timer_ns();
+    while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
+        __nanosleep(100);
+        if (global_timer_ns() - t0 > pt.timeout_ns) {
+            printf("medtok_vq: rank %d waited more than %llu s for rank %d (step %u)\n", pt.rank,
+                   pt.timeout_ns / 1000000000ull, who, epoch);
+            __trap();
+        }
+    }
+}
+
+constexpr int kPeerFlagBank = 64;     // flags[0..63]: statistics ready; flags[64..127]: slice final; flags[128]: local counter
+
+__global__ void __launch_bounds__(256) ema_finalize_peers_kernel(float* __restrict__ weight, float* __restrict__ cluster_size,
+                                                                  PeerTable pt, int k, int d, float beta, float decay,
+                                                                  float alpha, int update_cs, int update_w,
+                                                                  float* __restrict__ loss) {
+    extern __shared__ float tile[];
+    float* wold = tile + kEmaCodes * (d + 1);
+    __shared__ double bins_s[kEmaCodes];
+    __shared__ float den_s[kEmaCodes];
+    __shared__ float cs_s[kEmaCodes];
+    const int W = pt.world, me = pt.rank;
+    const int nblocks = (k + kEmaCodes - 1) / kEmaCodes;
+    const int per_rank = (nblocks + W - 1) / W;                       // code blocks per slice
+    const int own_lo = min(nblocks, me * per_rank), own_hi = min(nblocks, own_lo + per_rank);
+    const int n_own = own_hi - own_lo;
+    unsigned* my_flags = pt.flags[me];
+
+    // ---- 1. statistics of this step are complete on every rank ----
+    if (threadIdx.x < W) {
+        if (blockIdx.x == 0) {
+            __threadfence_system();
+            st_release_sys(pt.flags[threadIdx.x] + me, pt.epoch);
+        }
+        wait_flag(my_flags + threadIdx.x, pt.epoch, pt, threadIdx.x);
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0 && loss) {                // global-batch loss: rank-ordered totals
+        double sse = 0.0, rows = 0.0;
+        for (int r = 0; r < W; ++r) {
+            sse += __ldcv(pt.stats[r] + (size_t)k + (size_t)k * d);
+            rows += __ldcv(pt.stats[r] + (size_t)k + (size_t)k * d + 1);
+        }
+        *loss = __fmul_rn(beta, (float)(sse / (rows * (double)d)));
+    }
+    const size_t kd = (size_t)k * d;
+    for (int pb = blockIdx.x; pb < nblocks; pb += gridDim.x) {
+        // physical order: own slice first, then the other slices starting after mine (spreads the waits)
+        const int lb = (own_lo + pb) % nblocks;
+        const int owner = min(W - 1, lb / per_rank);
+        const int code0 = lb * kEmaCodes;
+        const int ncodes = min(kEmaCodes, k - code0);
+        if (owner != me) {
+            // ---- 3b. a foreign slice: wait for its owner, then copy from MY result buffer ----
+            if (threadIdx.x == 0) wait_flag(my_flags + kPeerFlagBank + owner, pt.epoch, pt, owner);
+            __syncthreads();
+            const float* res = pt.results[me];
+            if (update_w)
+                for (int e = threadIdx.x; e < ncodes * d; e += blockDim.x)
+                    weight[(size_t)code0 * d + e] = __ldcv(res + (size_t)code0 * d + e);
+            if (update_cs && threadIdx.x < ncodes) cluster_size[code0 + threadIdx.x] = __ldcv(res + kd + code0 + threadIdx.x);
+            __syncthreads();
+            continue;
+        }
+        // ---- 2. my slice: rank-ordered fp64 sums of the peers' partial statistics, EMA, push ----
+        if (threadIdx.x < kEmaCodes) {
+            double b = 0.0;
+            if (threadIdx.x < ncodes)
+                for (int r = 0; r < W; ++r) b += __ldcv(pt.stats[r] + code0 + threadIdx.x);
+            bins_s[threadIdx.x] = b;
+        }
+        __syncthreads();
+        if (threadIdx.x < ncodes) {
+            float cs = cluster_size ? cluster_size[code0 + threadIdx.x] : 0.0f;
+            if (update_cs) cs = __fmaf_rn((float)bins_s[threadIdx.x], alpha, __fmul_rn(cs, decay));   // ema_inplace
+            cs_s[threadIdx.x] = cs;
+        }
+        if (update_w) {
+            // element pairs: one 16-byte load per peer and pair, all W loads of a pair independent (in flight together)
+            const int npair = (ncodes * d) >> 1;                      // d is even
+            for (int e2 = threadIdx.x; e2 < npair; e2 += blockDim.x) {
+                const int e = 2 * e2, c = e / d, i = e - c * d;
+                double s0 = 0.0, s1 = 0.0;
+                const size_t off = (size_t)k + (size_t)(code0 + c) * d + i;   // even offset from an even base? k may be odd:
+                if ((off & 1) == 0) {
+                    for (int r = 0; r < W; ++r) { const double2 v = ld_cv_f64x2(pt.stats[r] + off); s0 += v.x; s1 += v.y; }
+                } else {
+                    for (int r = 0; r < W; ++r) { s0 += __ldcv(pt.stats[r] + off); s1 += __ldcv(pt.stats[r] + off + 1); }
+                }
+                const float2 wv = *reinterpret_cast<const float2*>(weight + (size_t)(code0 + c) * d + i);
+                const double bins = bins_s[c];
+                wold[c * (d + 1) + i] = wv.x; wold[c * (d + 1) + i + 1] = wv.y;
+                tile[c * (d + 1) + i]     = (bins == 0.0) ? wv.x : __fdiv_rn((float)s0, (float)bins);
+                tile[c * (d + 1) + i + 1] = (bins == 0.0) ? wv.y : __fdiv_rn((float)s1, (float)bins);
+            }
+            __syncthreads();
+            if (threadIdx.x < ncodes) {
+                float den = 1.0f;
+                if (bins_s[threadIdx.x] != 0.0) {
+                    const float* e = tile + threadIdx.x * (d + 1);
+                    den = canon_norm_seq([&](int i) { return e[i]; }, d);   // strided (.t()) view in the reference
+                    den = den < kNormEps ? kNormEps : den;
+                }
+                den_s[threadIdx.x] = den;
+            }
+            __syncthreads();
+            for (int e = threadIdx.x; e < ncodes * d; e += blockDim.x) {
+                const int c = e / d, i = e - c * d;
+                float v = tile[c * (d + 1) + i];
+                if (bins_s[c] != 0.0) v = __fdiv_rn(v, den_s[c]);
+                tile[c * (d + 1) + i] = __fmaf_rn(v, alpha, __fmul_rn(wold[c * (d + 1) + i], decay));
+            }
+            __syncthreads();
+            if (threadIdx.x < ncodes) {
+                const float* e = tile + threadIdx.x * (d + 1);
+                const float den = canon_norm8([&](int i) { return e[i]; }, d);
+                den_s[threadIdx.x] = den < kNormEps ? kNormEps : den;
+            }
+            __syncthreads();
+            for (int e = threadIdx.x; e < ncodes * d; e += blockDim.x) {
+                const int c = e / d, i = e - c * d;
+                const float v = __fdiv_rn(tile[c * (d + 1) + i], den_s[c]);
+                weight[(size_t)code0 * d + e] = v;
+                for (int r = 0; r < W; ++r)
+                    if (r != me) pt.results[r][(size_t)code0 * d + e] = v;     // push over NVLink
+            }
+        }
+        if (threadIdx.x < ncodes) {
+            if (update_cs) cluster_size[code0 + threadIdx.x] = cs_s[threadIdx.x];
+            for (int r = 0; r < W; ++r)
+                if (r != me) pt.results[r][kd + code0 + threadIdx.x] = cs_s[threadIdx.x];
+        }
+        // ---- 3a. last block of my slice: the slice is final everywhere -> tell the peers ----
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned done = atomicAdd(my_flags + 2 * kPeerFlagBank, 1u) + 1u;
+            if (done == (unsigned)n_own) {
+                my_flags[2 * kPeerFlagBank] = 0u;                       // ready for the next step (stream-ordered)
+                __threadfence_system();
+                for (int r = 0; r < W; ++r)
+                    if (r != me) st_release_sys(pt.flags[r] + kPeerFlagBank + me, pt.epoch);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void loss_kernel(const double* __restrict__ stats, int k, int d, float beta, float* __restrict__ loss) {
     const double sse = stats[(size_t)k + (size_t)k * d], rows = stats[(size_t)k + (size_t)k * d + 1];
     *loss = __fmul_rn(beta, (float)(sse / (rows * (double)d)));
@@ -707,8 +879,6 @@ static cudaError_t ema_finalize_configure() {
     bool& configured = once.flag();
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(ema_finalize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(ema_finalize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
         if (e != cudaSuccess) return e;
         configured = true;
     }
@@ -728,21 +898,32 @@ cudaError_t launch_ema_finalize(float* weight, float* cluster_size, const double
 }
 
 cudaError_t launch_ema_finalize_peers(float* weight, float* cluster_size, const void* const* peer_stats,
-                                      void* const* peer_flags, int world, int rank, unsigned epoch, int k, int d,
-                                      double beta, double decay, int update_cs, int update_w, float* loss, cudaStream_t s) {
+                                      void* const* peer_flags, void* const* peer_results, int world, int rank, unsigned epoch,
+                                      int k, int d, double beta, double decay, int update_cs, int update_w, float* loss,
+                                      int num_sms, cudaStream_t s) {
     const size_t smem = sizeof(float) * 2 * kEmaCodes * (d + 1);
-    if (cudaError_t e = ema_finalize_configure()) return e;
+    static PerDeviceOnce once;
+    bool& configured = once.flag();
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(ema_finalize_peers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
     PeerTable pt;
     pt.stats = reinterpret_cast<const double* const*>(peer_stats);
     pt.flags = reinterpret_cast<unsigned* const*>(peer_flags);
+    pt.results = reinterpret_cast<float* const*>(peer_results);
     pt.world = world; pt.rank = rank; pt.epoch = epoch;
     {   // MEDTOK_EXCHANGE_TIMEOUT_S (default 600 s, the NCCL watchdog's order of magnitude)
         static long long limit_s = -1;
         if (limit_s < 0) { const char* e = getenv("MEDTOK_EXCHANGE_TIMEOUT_S"); limit_s = (e && atoll(e) > 0) ? atoll(e) : 600; }
         pt.timeout_ns = (unsigned long long)limit_s * 1000000000ull;
     }
-    ema_finalize_kernel<true><<<(k + kEmaCodes - 1) / kEmaCodes, 256, smem, s>>>(
-        weight, cluster_size, nullptr, pt, k, d, (float)beta, (float)decay, (float)(1.0 - decay), update_cs, update_w, loss);
+    // persistent grid: every CTA resident at once (<= 2 per SM at 66 KB of shared memory for d = 256)
+    const int nblocks = (k + kEmaCodes - 1) / kEmaCodes;
+    int grid = nblocks < 2 * num_sms ? nblocks : 2 * num_sms;
+    ema_finalize_peers_kernel<<<grid, 256, smem, s>>>(weight, cluster_size, pt, k, d, (float)beta, (float)decay,
+                                                      (float)(1.0 - decay), update_cs, update_w, loss);
     ++g_kernel_launches;
     return cudaGetLastError();
 }

@@ -26,10 +26,12 @@ cudaError_t launch_sorted_rows(const float* z, const float* denom, const float* 
                                int k, float* z_q, double* stats, const Workspace& ws, int num_sms, cudaStream_t s);
 cudaError_t launch_ema_finalize(float* weight, float* cluster_size, const double* stats, int k, int d, double beta,
                                 double decay, int update_cs, int update_w, float* loss, cudaStream_t s);
-// finalize fused with the cross-GPU exchange: peer_stats / peer_flags are DEVICE arrays of `world` peer-mapped pointers
+// finalize fused with the cross-GPU exchange (reduce-scatter shape): peer_stats / peer_flags / peer_results are DEVICE
+// arrays of `world` peer-mapped pointers
 cudaError_t launch_ema_finalize_peers(float* weight, float* cluster_size, const void* const* peer_stats,
-                                      void* const* peer_flags, int world, int rank, unsigned epoch, int k, int d,
-                                      double beta, double decay, int update_cs, int update_w, float* loss, cudaStream_t s);
+                                      void* const* peer_flags, void* const* peer_results, int world, int rank, unsigned epoch,
+                                      int k, int d, double beta, double decay, int update_cs, int update_w, float* loss,
+                                      int num_sms, cudaStream_t s);
 // k-means centre update: means_k <- l2norm(embed_sum_k / bins_k) where bins_k > 0 (packed statistics as above)
 cudaError_t launch_kmeans_update(float* means, const double* stats, int k, int d, cudaStream_t s);
 cudaError_t launch_loss(const double* stats, int k, int d, double beta, float* loss, cudaStream_t s);

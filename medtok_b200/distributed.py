@@ -50,9 +50,10 @@ def all_reduce_stats(stats: torch.Tensor, all_reduce_fn) -> torch.Tensor:
 
 class PeerExchange:
     """Peer-mapped buffers for the exchange fused into the finalize kernel (mtvq_ema_finalize_peers): two packed
-    statistics buffers per rank (alternating by step) and one flag array, allocated as torch symmetric memory so that
-    every rank holds device pointers into every peer's copy (NVLink P2P).  PyTorch only provides the mapping; the
-    signalling, the waiting and the rank-ordered fp64 sum all happen inside the one kernel.
+    statistics buffers per rank (alternating by step), one flag array and one result buffer (the slice owners push the
+    updated rows into it), allocated as torch symmetric memory so that every rank holds device pointers into every
+    peer's copy (NVLink P2P).  PyTorch only provides the mapping; the signalling, the waiting, the rank-ordered fp64
+    sums of a rank's slice and the distribution of the results all happen inside the one kernel.
 
     Set-up is split so that a failure on ONE rank can never leave the others inside a collective: `__init__` only
     allocates (local, may raise), `connect()` is the collective rendezvous (every rank of the group must call it, which
@@ -61,7 +62,7 @@ class PeerExchange:
 
     MAX_WORLD = 64                      # flag slots per rank (mtvq_ema_finalize_peers rejects larger worlds)
 
-    def __init__(self, numel: int, device, group=None):
+    def __init__(self, numel: int, device, group=None, result_numel: int = 0):
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
         self.group = group if group is not None else dist.group.WORLD
@@ -79,22 +80,25 @@ class PeerExchange:
             except Exception:
                 pass
         self.stats = [symm_mem.empty(numel, dtype=torch.float64, device=device) for _ in range(2)]
-        self.flags = symm_mem.empty(self.MAX_WORLD, dtype=torch.int32, device=device)
+        # flags: [0, 64) "statistics ready" per peer, [64, 128) "slice final" per peer, [128] a local block counter
+        self.flags = symm_mem.empty(3 * self.MAX_WORLD, dtype=torch.int32, device=device)
+        # result buffer the slice owners push the updated rows / cluster sizes into (k*d + k floats)
+        self.results = symm_mem.empty(max(result_numel, 1), dtype=torch.float32, device=device)
         self.table = None
         self.epoch = 0
 
     def connect(self):
         """Collective: exchange the peer mappings.  Raises if the handles do not describe our tensors."""
         import torch.distributed._symmetric_memory as symm_mem
-        self._handles = [symm_mem.rendezvous(t, self.group) for t in (*self.stats, self.flags)]
+        self._handles = [symm_mem.rendezvous(t, self.group) for t in (*self.stats, self.flags, self.results)]
         tables = []
-        for t, h in zip((*self.stats, self.flags), self._handles):
+        for t, h in zip((*self.stats, self.flags, self.results), self._handles):
             off = int(getattr(h, "offset", 0) or 0)
             ptrs = [int(p) + off for p in h.buffer_ptrs]
             if len(ptrs) != self.world or ptrs[self.rank] != t.data_ptr():
                 raise RuntimeError("symmetric-memory handle does not describe the tensor it was made from")
             tables.append(ptrs)
-        # device tables of peer pointers: [stats parity 0 | stats parity 1 | flags], `world` int64 each
+        # device tables of peer pointers: [stats parity 0 | stats parity 1 | flags | results], `world` int64 each
         self.table = torch.tensor(tables, dtype=torch.int64, device=self.device)
 
     def arm(self):
@@ -115,3 +119,6 @@ class PeerExchange:
 
     def peer_flags_ptr(self) -> int:
         return self.table[2].data_ptr()
+
+    def peer_results_ptr(self) -> int:
+        return self.table[3].data_ptr()

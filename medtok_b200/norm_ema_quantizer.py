@@ -280,7 +280,7 @@ class NormEMAVectorQuantizer(nn.Module):
             local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
             if local_world != world or world > torch.cuda.device_count():
                 raise RuntimeError(f"multi-node world ({world} ranks, {local_world} on this node)")
-            peers = PeerExchange(_lib.stats_len(d, k), dev)
+            peers = PeerExchange(_lib.stats_len(d, k), dev, result_numel=k * d + k)
         except Exception as e:
             note("allocation", e)
             peers = None
@@ -334,7 +334,8 @@ class NormEMAVectorQuantizer(nn.Module):
         if peers is not None:
             # ONE kernel: signal / wait over NVLink, rank-ordered fp64 sum of the peers' statistics, EMA update
             _lib.check(L.mtvq_ema_finalize_peers(_lib.ptr(weight), _lib.ptr(cs), ctypes.c_void_p(peers.peer_stats_ptr()),
-                                                 ctypes.c_void_p(peers.peer_flags_ptr()), peers.world, peers.rank,
+                                                 ctypes.c_void_p(peers.peer_flags_ptr()),
+                                                 ctypes.c_void_p(peers.peer_results_ptr()), peers.world, peers.rank,
                                                  peers.epoch, k, d, float(self.beta), float(self.decay), int(upd_cs),
                                                  int(upd_w), _lib.ptr(loss) if self.global_loss else None,
                                                  _lib.stream_ptr(dev)), "mtvq_ema_finalize_peers")

@@ -27,7 +27,7 @@ def test_header_symbols_are_exported(lib):
 
 
 def test_host_side_sizes_and_validation(lib):
-    assert lib.mtvq_abi_version() == 1
+    assert lib.mtvq_abi_version() == 2
     assert lib.mtvq_stats_len(64, 8192) == 8192 + 8192 * 64 + 2
     small, big = lib.mtvq_workspace_bytes(1000, 64, 512, 0), lib.mtvq_workspace_bytes(1 << 20, 64, 8192, 0)
     assert 0 < small < big < (1 << 30)

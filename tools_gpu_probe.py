@@ -1,4 +1,6 @@
-"""First-contact GPU probe (run under gpurun): micro-benchmarks that size the epilogue, a raw
+"""First-contact GPU probe (run under gpurun; the `micro` part needs the probe build of the library:
+python -m medtok_b200.build --variant probe -DMTVQ_WITH_MICROBENCH, then
+MEDTOK_VQ_LIB=medtok_b200/_build/variants/libmedtok_vq_probe.so python tools_gpu_probe.py micro): micro-benchmarks that size the epilogue, a raw
 tensor-core score check, and a coarse timing of the hard forward at BASELINE config 2.
 Writes gpurun_out/probe.json.  Diagnostic tool, not part of the product or the tests."""
 import ctypes
