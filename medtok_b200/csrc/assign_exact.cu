@@ -11,26 +11,19 @@
 namespace mtvq {
 
 // ------------------------------------------------------------------------------------------------
-// codebook prep (one thread per code; K*D is tiny next to N*K*D)
+// codebook prep (K*D is tiny next to N*K*D, but it sits on the critical path of every step)
 // ------------------------------------------------------------------------------------------------
-__global__ void codebook_prep_kernel(const float* __restrict__ w, int k, int kpad, int d, int flags,
-                                     unsigned char* __restrict__ image, float* __restrict__ cc,
-                                     float* __restrict__ codes_n, float* __restrict__ meta) {
-    // the block's 32 rows are staged into shared memory with coalesced loads, all in flight at once (one thread per
-    // code reading its own row from global memory was bound by dependent-load latency: ~2 warps per SM)
-    __shared__ float rows_s[32 * (kMaxDim + 1)];
-    const int code = blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per code (a single thread per code ran every reduction as one dependent chain: 15 us for 8192 codes).  The
+// canonical orders are kept exactly: canon_norm8's eight lane-accumulators run on lanes 0-7 and are folded in lane order,
+// warp_canon_sumsq folds the 32 cascade accumulators (common.cuh).
+__global__ void __launch_bounds__(256) codebook_prep_kernel(const float* __restrict__ w, int k, int kpad, int d, int flags,
+                                                             unsigned char* __restrict__ image, float* __restrict__ cc,
+                                                             float* __restrict__ codes_n, float* __restrict__ meta) {
+    __shared__ __align__(16) float rows_s[8][kMaxDim];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int code = blockIdx.x * 8 + wib;
     const int normalize = flags & 1;
     const bool dot_only = (flags & 2) != 0;      // MTVQ_SCORE_DOT: codes are ranked by z.w alone -> no -||w||^2/2 term
-    {
-        const int code0 = blockIdx.x * blockDim.x;
-        const int nrows = min(32, k - code0);
-        for (int e = threadIdx.x; e < nrows * d; e += 32) {
-            const int r = e / d, c = e - r * d;
-            rows_s[r * (d + 1) + c] = __ldg(w + (size_t)code0 * d + e);
-        }
-        __syncwarp();
-    }
     if (code >= kpad) return;
     const int nplanes = d >> 3;
     const int tile = code >> 7, r = code & 127;
@@ -38,37 +31,52 @@ __global__ void codebook_prep_kernel(const float* __restrict__ w, int k, int kpa
     const __half hz = __float2half(0.0f);
 
     if (code >= k) {   // padding code: can never win (bias -60000), contributes nothing
-        uint4 z4 = make_uint4(0, 0, 0, 0);
-        for (int j = 0; j < nplanes + 2; ++j) *reinterpret_cast<uint4*>(tile_base + j * 2048) = z4;
-        __half hb[8] = {__float2half(-60000.0f), hz, hz, hz, hz, hz, hz, hz};
-        *reinterpret_cast<uint4*>(tile_base + nplanes * 2048) = *reinterpret_cast<uint4*>(hb);
-        cc[code] = 3.0e38f;
+        for (int j = lane; j < nplanes + 2; j += 32) {
+            uint4 z4 = make_uint4(0, 0, 0, 0);
+            if (j == nplanes) {
+                __half hb[8] = {__float2half(-60000.0f), hz, hz, hz, hz, hz, hz, hz};
+                z4 = *reinterpret_cast<uint4*>(hb);
+            }
+            *reinterpret_cast<uint4*>(tile_base + j * 2048) = z4;
+        }
+        if (lane == 0) cc[code] = 3.0e38f;
         return;
     }
-    const float* wr = rows_s + threadIdx.x * (d + 1);     // this thread's row, staged below
-    float den = 1.0f;
-    if (normalize) den = canon_denom([&](int i) { return wr[i]; }, d, 0);
-    auto elem = [&](int i) { return normalize ? __fdiv_rn(wr[i], den) : wr[i]; };
-    const float c2 = canon_sumsq(elem, d);
-    cc[code] = c2;
-    {   // spread of the squared norms around code 0's: if it is negligible the kernels drop the bias K-step
-        const float* w0 = w;
-        float den0 = 1.0f;
-        if (normalize) den0 = canon_denom([&](int i) { return __ldg(w0 + i); }, d, 0);
-        const float c0 = canon_sumsq([&](int i) { return normalize ? __fdiv_rn(__ldg(w0 + i), den0) : __ldg(w0 + i); }, d);
-        const float spread = dot_only ? 0.0f : 0.5f * fabsf(c2 - c0);
-        if (spread == spread) atomicMax(reinterpret_cast<int*>(meta + META_SPREAD), __float_as_int(spread));
-        else meta[META_SPREAD] = INFINITY;
+    float* row = rows_s[wib];
+    for (int i = lane; i < d; i += 32) row[i] = __ldg(w + (size_t)code * d + i);
+    __syncwarp();
+    auto warp_norm8 = [&](const float* x) {
+        const int v = lane & 7;
+        float a = 0.f;
+        for (int c = 0; c < d; c += 8) { const float e = x[c + v]; a = __fadd_rn(a, __fmul_rn(e, e)); }
+        float sm = __shfl_sync(0xffffffffu, a, 0);
+#pragma unroll
+        for (int t = 1; t < 8; ++t) sm = __fadd_rn(sm, __shfl_sync(0xffffffffu, a, t));
+        const float nrm = __fsqrt_rn(sm);
+        return nrm < kNormEps ? kNormEps : nrm;
+    };
+    if (normalize) {
+        const float den = warp_norm8(row);
+        __syncwarp();
+        for (int i = lane; i < d; i += 32) row[i] = __fdiv_rn(row[i], den);
+        __syncwarp();
     }
-    for (int j = 0; j < nplanes; ++j) {
+    const float c2 = warp_canon_sumsq(row, d, lane);
+    // the fp16 operand image: plane j holds elements [8j, 8j + 8) of the code as one 16-byte unit
+    for (int j = lane; j < nplanes; j += 32) {
         __half h[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float x = elem(8 * j + i);
-            h[i] = __float2half_rn(x);
-            if (normalize) codes_n[(size_t)code * d + 8 * j + i] = x;
-        }
+        for (int i = 0; i < 8; ++i) h[i] = __float2half_rn(row[8 * j + i]);
         *reinterpret_cast<uint4*>(tile_base + j * 2048) = *reinterpret_cast<uint4*>(h);
+    }
+    if (normalize) for (int i = lane; i < d; i += 32) codes_n[(size_t)code * d + i] = row[i];
+    if (lane != 0) return;
+    cc[code] = c2;
+    {   // spread of the squared norms around 1 (the unit-norm codebooks of the EMA quantizer): if it is negligible the
+        // kernels drop the bias K-step; two codes then differ by at most 2 x spread, covered by the slack in eps below
+        const float spread = dot_only ? 0.0f : 0.5f * fabsf(c2 - 1.0f);
+        if (spread == spread) atomicMax(reinterpret_cast<int*>(meta + META_SPREAD), __float_as_int(spread));
+        else meta[META_SPREAD] = INFINITY;
     }
     // bias = -||w||^2 / 2 split into three fp16 terms (exact to ~2^-33 relative)
     const float b = dot_only ? 0.0f : -0.5f * c2;
@@ -83,8 +91,9 @@ __global__ void codebook_prep_kernel(const float* __restrict__ w, int k, int kpa
     // |coarse - exact| <= eps for every row with ||zf|| <= 1:
     //   fp16 rounding of both operands: (2^-10 + 2^-22) * ||w||     (Cauchy-Schwarz)
     //   fp16 subnormal flush + fp32 accumulation in the tensor core: 2^-18 * (1 + ||w|| + ||w||^2/2)
+    //   skipped bias step: scores shifted by up to kBiasSkipTol each way
     const float nw = sqrtf(c2) * 1.001f;
-    const float eps = 9.7704e-4f * nw + 3.8147e-6f * (1.0f + nw + 0.5f * c2) + 1e-6f + kBiasSkipTol;
+    const float eps = 9.7704e-4f * nw + 3.8147e-6f * (1.0f + nw + 0.5f * c2) + 1e-6f + 2.0f * kBiasSkipTol;
     if (eps == eps) {   // positive floats order like ints
         atomicMax(reinterpret_cast<int*>(meta + META_EPS), __float_as_int(eps));
         atomicMax(reinterpret_cast<int*>(meta + META_MARGIN), __float_as_int(2.0f * eps));
@@ -403,7 +412,7 @@ cudaError_t launch_codebook_prep(const float* w, int k, int d, int flags, const 
     cudaError_t e = cudaMemsetAsync(ws.meta, 0, sizeof(float) * META_COUNT, stream);
     if (e != cudaSuccess) return e;
     const int kpad = pad_codes(k);
-    codebook_prep_kernel<<<(kpad + 31) / 32, 32, 0, stream>>>(w, k, kpad, d, flags,
+    codebook_prep_kernel<<<(kpad + 7) / 8, 256, 0, stream>>>(w, k, kpad, d, flags,
                                                                   static_cast<unsigned char*>(ws.b_image), ws.cc,
                                                                   ws.codes_n, ws.meta);
     ++g_kernel_launches;

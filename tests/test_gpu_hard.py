@@ -308,3 +308,27 @@ def test_kmeans_init_through_the_module(dev, oracle):
     assert np.max(np.abs(q.embedding.weight.cpu().numpy() - means)) <= 1e-6
     assert np.array_equal(q.embedding.cluster_size.cpu().numpy(), bins.astype(np.float32))
 
+
+@pytest.mark.single_route
+def test_training_forward_is_reproducible_run_to_run(dev):
+    """The per-code sums are accumulated with fp64 atomics (order-dependent at ~1e-16 relative), then rounded to fp32
+    before the EMA: two runs of the same three training steps must give the same indices / cluster sizes bit for bit and
+    codebooks that agree to the last fp32 bit except where an fp64 sum sits within 1e-16 of a rounding boundary --
+    stated tolerance 1 ulp of a unit-norm row (1.2e-7); in practice the runs are bit-equal."""
+    from medtok_b200.norm_ema_quantizer import NormEMAVectorQuantizer
+    n, d, k = 200_000, 64, 4096
+    g = torch.Generator().manual_seed(21)
+    zs = [torch.randn(n, d, 1, 1, generator=g).to(dev) for _ in range(3)]
+    w0 = torch.nn.functional.normalize(torch.randn(k, d, generator=g), dim=-1).to(dev)
+    runs = []
+    for _ in range(2):
+        q = NormEMAVectorQuantizer(k, d, 0.25).to(dev).train()
+        q.embedding.weight.data.copy_(w0)
+        with torch.no_grad():
+            for z in zs:
+                z_q, loss, idx = q(z)
+        runs.append((q.embedding.weight.detach().clone(), q.cluster_size.clone(), idx.clone(), z_q.clone()))
+    assert torch.equal(runs[0][2], runs[1][2]) and torch.equal(runs[0][1], runs[1][1]) and torch.equal(runs[0][3], runs[1][3])
+    assert float((runs[0][0] - runs[1][0]).abs().max()) <= 1.2e-7
+    print("codebooks bit-equal across runs:", bool(torch.equal(runs[0][0], runs[1][0])))
+

@@ -50,7 +50,18 @@ def child(shapes, soft, steps):
             i1, _ = hard_assign(rows, wq)
             i2, _ = hard_assign(rows, wq, exact=True)
             same = bool(torch.equal(i1, i2))
+        kern = None
+        if os.environ.get("AB_KERNELS") == "1":
+            from torch.profiler import profile, ProfilerActivity
+            with torch.no_grad():
+                with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                    for i in range(10):
+                        q(zs[i % len(zs)])
+                    torch.cuda.synchronize()
+            kern = sorted(((e.key[:48], round(getattr(e, "device_time_total", 0) / 10.0, 1)) for e in prof.key_averages()
+                           if getattr(e, "device_time_total", 0) > 0), key=lambda t: -t[1])
         print(json.dumps({"lib": os.path.basename(_lib.SO_PATH), "path": "hard+EMA", "n": n, "d": d, "k": k, "step_ms": sms,
+                          "kernels_us": kern,
                           "coarse_ms": kms, "tflops_step": 2.0 * n * k * d / (sms * 1e-3) / 1e12,
                           "tflops_coarse": 2.0 * n * k * d / (kms * 1e-3) / 1e12, "near_tie": cnt["near_tie_rows"],
                           "idx_equal_exact": same}), flush=True)
