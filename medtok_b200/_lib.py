@@ -112,6 +112,14 @@ def on_tensor_device(fn):
     return wrapped
 
 
+def check_embedding_dim(d: int, who: str) -> None:
+    """The tcgen05 operand layout needs D % 16 == 0 and D <= 256 (include/medtok_vq.h); say so when the module is built,
+    not at the first forward.  MedTok's shipped configuration uses 64; its unused default `codebook_embed_dim=8` does not fit."""
+    if d <= 0 or d % 16 != 0 or d > 256:
+        raise MedTokVQError(f"{who}: embedding dim {d} is not supported by libmedtok_vq (needs a multiple of 16, at most 256); "
+                            "pad the projection to the next multiple of 16")
+
+
 def check(rc: int, what: str) -> None:
     if rc != 0:
         msg = lib().mtvq_last_error().decode(errors="replace")

@@ -20,86 +20,100 @@ __global__ void __launch_bounds__(256) codebook_prep_kernel(const float* __restr
                                                              unsigned char* __restrict__ image, float* __restrict__ cc,
                                                              float* __restrict__ codes_n, float* __restrict__ meta) {
     __shared__ __align__(16) float rows_s[8][kMaxDim];
+    __shared__ float red_s[8][4];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int code = blockIdx.x * 8 + wib;
     const int normalize = flags & 1;
     const bool dot_only = (flags & 2) != 0;      // MTVQ_SCORE_DOT: codes are ranked by z.w alone -> no -||w||^2/2 term
-    if (code >= kpad) return;
     const int nplanes = d >> 3;
-    const int tile = code >> 7, r = code & 127;
-    unsigned char* tile_base = image + (size_t)tile * (nplanes + 2) * 2048 + r * 16;
     const __half hz = __float2half(0.0f);
-
-    if (code >= k) {   // padding code: can never win (bias -60000), contributes nothing
-        for (int j = lane; j < nplanes + 2; j += 32) {
-            uint4 z4 = make_uint4(0, 0, 0, 0);
-            if (j == nplanes) {
-                __half hb[8] = {__float2half(-60000.0f), hz, hz, hz, hz, hz, hz, hz};
-                z4 = *reinterpret_cast<uint4*>(hb);
-            }
-            *reinterpret_cast<uint4*>(tile_base + j * 2048) = z4;
-        }
-        if (lane == 0) cc[code] = 3.0e38f;
-        return;
-    }
     float* row = rows_s[wib];
-    for (int i = lane; i < d; i += 32) row[i] = __ldg(w + (size_t)code * d + i);
-    __syncwarp();
-    auto warp_norm8 = [&](const float* x) {
-        const int v = lane & 7;
-        float a = 0.f;
-        for (int c = 0; c < d; c += 8) { const float e = x[c + v]; a = __fadd_rn(a, __fmul_rn(e, e)); }
-        float sm = __shfl_sync(0xffffffffu, a, 0);
-#pragma unroll
-        for (int t = 1; t < 8; ++t) sm = __fadd_rn(sm, __shfl_sync(0xffffffffu, a, t));
-        const float nrm = __fsqrt_rn(sm);
-        return nrm < kNormEps ? kNormEps : nrm;
-    };
-    if (normalize) {
-        const float den = warp_norm8(row);
+    // running maxima of this warp's codes (lane 0): spread, eps, max norm; NaN anywhere -> everything to the exact path.
+    // One set of atomics per CTA at the end: thousands of atomics on four addresses serialise (they were most of the time).
+    float m_spread = 0.0f, m_eps = 0.0f, m_norm = 0.0f;
+    bool bad = false;
+    for (int code = blockIdx.x * 8 + wib; code < kpad; code += gridDim.x * 8) {
+        const int tile = code >> 7, r = code & 127;
+        unsigned char* tile_base = image + (size_t)tile * (nplanes + 2) * 2048 + r * 16;
+        if (code >= k) {   // padding code: can never win (bias -60000), contributes nothing
+            for (int j = lane; j < nplanes + 2; j += 32) {
+                uint4 z4 = make_uint4(0, 0, 0, 0);
+                if (j == nplanes) {
+                    __half hb[8] = {__float2half(-60000.0f), hz, hz, hz, hz, hz, hz, hz};
+                    z4 = *reinterpret_cast<uint4*>(hb);
+                }
+                *reinterpret_cast<uint4*>(tile_base + j * 2048) = z4;
+            }
+            if (lane == 0) cc[code] = 3.0e38f;
+            continue;
+        }
         __syncwarp();
-        for (int i = lane; i < d; i += 32) row[i] = __fdiv_rn(row[i], den);
+        for (int i = lane; i < d; i += 32) row[i] = __ldg(w + (size_t)code * d + i);
         __syncwarp();
-    }
-    const float c2 = warp_canon_sumsq(row, d, lane);
-    // the fp16 operand image: plane j holds elements [8j, 8j + 8) of the code as one 16-byte unit
-    for (int j = lane; j < nplanes; j += 32) {
-        __half h[8];
+        if (normalize) {
+            // canon_norm8: eight lane-accumulators on lanes 0-7, folded in lane order
+            const int v = lane & 7;
+            float a = 0.f;
+            for (int c = 0; c < d; c += 8) { const float e = row[c + v]; a = __fadd_rn(a, __fmul_rn(e, e)); }
+            float sm = __shfl_sync(0xffffffffu, a, 0);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) h[i] = __float2half_rn(row[8 * j + i]);
-        *reinterpret_cast<uint4*>(tile_base + j * 2048) = *reinterpret_cast<uint4*>(h);
-    }
-    if (normalize) for (int i = lane; i < d; i += 32) codes_n[(size_t)code * d + i] = row[i];
-    if (lane != 0) return;
-    cc[code] = c2;
-    {   // spread of the squared norms around 1 (the unit-norm codebooks of the EMA quantizer): if it is negligible the
+            for (int t = 1; t < 8; ++t) sm = __fadd_rn(sm, __shfl_sync(0xffffffffu, a, t));
+            float den = __fsqrt_rn(sm);
+            den = den < kNormEps ? kNormEps : den;
+            __syncwarp();
+            for (int i = lane; i < d; i += 32) row[i] = __fdiv_rn(row[i], den);
+            __syncwarp();
+        }
+        const float c2 = warp_canon_sumsq(row, d, lane);
+        // the fp16 operand image: plane j holds elements [8j, 8j + 8) of the code as one 16-byte unit
+        for (int j = lane; j < nplanes; j += 32) {
+            __half h[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) h[i] = __float2half_rn(row[8 * j + i]);
+            *reinterpret_cast<uint4*>(tile_base + j * 2048) = *reinterpret_cast<uint4*>(h);
+        }
+        if (normalize) for (int i = lane; i < d; i += 32) codes_n[(size_t)code * d + i] = row[i];
+        if (lane != 0) continue;
+        cc[code] = c2;
+        // spread of the squared norms around 1 (the unit-norm codebooks of the EMA quantizer): if it is negligible the
         // kernels drop the bias K-step; two codes then differ by at most 2 x spread, covered by the slack in eps below
         const float spread = dot_only ? 0.0f : 0.5f * fabsf(c2 - 1.0f);
-        if (spread == spread) atomicMax(reinterpret_cast<int*>(meta + META_SPREAD), __float_as_int(spread));
-        else meta[META_SPREAD] = INFINITY;
+        // bias = -||w||^2 / 2 split into three fp16 terms (exact to ~2^-33 relative)
+        const float b = dot_only ? 0.0f : -0.5f * c2;
+        const __half h0 = __float2half_rn(b);
+        const float r1 = b - __half2float(h0);
+        const __half h1 = __float2half_rn(r1);
+        const __half h2 = __float2half_rn(r1 - __half2float(h1));
+        __half hb[8] = {h0, h1, h2, hz, hz, hz, hz, hz};
+        *reinterpret_cast<uint4*>(tile_base + nplanes * 2048) = *reinterpret_cast<uint4*>(hb);
+        *reinterpret_cast<uint4*>(tile_base + (nplanes + 1) * 2048) = make_uint4(0, 0, 0, 0);
+        // |coarse - exact| <= eps for every row with ||zf|| <= 1:
+        //   fp16 rounding of both operands: (2^-10 + 2^-22) * ||w||     (Cauchy-Schwarz)
+        //   fp16 subnormal flush + fp32 accumulation in the tensor core: 2^-18 * (1 + ||w|| + ||w||^2/2)
+        //   skipped bias step: scores shifted by up to kBiasSkipTol each way
+        const float nw = sqrtf(c2) * 1.001f;
+        const float eps = 9.7704e-4f * nw + 3.8147e-6f * (1.0f + nw + 0.5f * c2) + 1e-6f + 2.0f * kBiasSkipTol;
+        if (eps == eps && spread == spread) {
+            m_spread = fmaxf(m_spread, spread); m_eps = fmaxf(m_eps, eps); m_norm = fmaxf(m_norm, nw);
+        } else {
+            bad = true;
+        }
     }
-    // bias = -||w||^2 / 2 split into three fp16 terms (exact to ~2^-33 relative)
-    const float b = dot_only ? 0.0f : -0.5f * c2;
-    const __half h0 = __float2half_rn(b);
-    const float r1 = b - __half2float(h0);
-    const __half h1 = __float2half_rn(r1);
-    const __half h2 = __float2half_rn(r1 - __half2float(h1));
-    __half hb[8] = {h0, h1, h2, hz, hz, hz, hz, hz};
-    *reinterpret_cast<uint4*>(tile_base + nplanes * 2048) = *reinterpret_cast<uint4*>(hb);
-    *reinterpret_cast<uint4*>(tile_base + (nplanes + 1) * 2048) = make_uint4(0, 0, 0, 0);
-
-    // |coarse - exact| <= eps for every row with ||zf|| <= 1:
-    //   fp16 rounding of both operands: (2^-10 + 2^-22) * ||w||     (Cauchy-Schwarz)
-    //   fp16 subnormal flush + fp32 accumulation in the tensor core: 2^-18 * (1 + ||w|| + ||w||^2/2)
-    //   skipped bias step: scores shifted by up to kBiasSkipTol each way
-    const float nw = sqrtf(c2) * 1.001f;
-    const float eps = 9.7704e-4f * nw + 3.8147e-6f * (1.0f + nw + 0.5f * c2) + 1e-6f + 2.0f * kBiasSkipTol;
-    if (eps == eps) {   // positive floats order like ints
-        atomicMax(reinterpret_cast<int*>(meta + META_EPS), __float_as_int(eps));
-        atomicMax(reinterpret_cast<int*>(meta + META_MARGIN), __float_as_int(2.0f * eps));
-        atomicMax(reinterpret_cast<int*>(meta + META_MAXNORM), __float_as_int(nw));
-    } else {
-        meta[META_MARGIN] = INFINITY;   // NaN in the codebook: send everything to the exact path
+    if (lane == 0) { red_s[wib][0] = m_spread; red_s[wib][1] = m_eps; red_s[wib][2] = m_norm; red_s[wib][3] = bad ? 1.0f : 0.0f; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int t = 1; t < 8; ++t) {
+            red_s[0][0] = fmaxf(red_s[0][0], red_s[t][0]); red_s[0][1] = fmaxf(red_s[0][1], red_s[t][1]);
+            red_s[0][2] = fmaxf(red_s[0][2], red_s[t][2]); red_s[0][3] = fmaxf(red_s[0][3], red_s[t][3]);
+        }
+        // positive floats order like ints
+        atomicMax(reinterpret_cast<int*>(meta + META_SPREAD), __float_as_int(red_s[0][0]));
+        atomicMax(reinterpret_cast<int*>(meta + META_EPS), __float_as_int(red_s[0][1]));
+        atomicMax(reinterpret_cast<int*>(meta + META_MARGIN), __float_as_int(2.0f * red_s[0][1]));
+        atomicMax(reinterpret_cast<int*>(meta + META_MAXNORM), __float_as_int(red_s[0][2]));
+        if (red_s[0][3] != 0.0f) {   // NaN in the codebook: send everything to the exact path, keep the bias step
+            atomicMax(reinterpret_cast<int*>(meta + META_MARGIN), __float_as_int(INFINITY));
+            atomicMax(reinterpret_cast<int*>(meta + META_SPREAD), __float_as_int(INFINITY));
+        }
     }
 }
 
@@ -412,7 +426,9 @@ cudaError_t launch_codebook_prep(const float* w, int k, int d, int flags, const 
     cudaError_t e = cudaMemsetAsync(ws.meta, 0, sizeof(float) * META_COUNT, stream);
     if (e != cudaSuccess) return e;
     const int kpad = pad_codes(k);
-    codebook_prep_kernel<<<(kpad + 7) / 8, 256, 0, stream>>>(w, k, kpad, d, flags,
+    int grid = (kpad + 7) / 8;
+    if (grid > 592) grid = 592;                      // <= 4 CTAs per SM, each walking its share of the codes
+    codebook_prep_kernel<<<grid, 256, 0, stream>>>(w, k, kpad, d, flags,
                                                                   static_cast<unsigned char*>(ws.b_image), ws.cc,
                                                                   ws.codes_n, ws.meta);
     ++g_kernel_launches;

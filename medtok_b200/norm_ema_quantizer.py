@@ -175,6 +175,24 @@ class EmbeddingEMA(nn.Module):
         self.initted.data.copy_(torch.Tensor([True]))
         self._initted_host = True
 
+    @torch.jit.ignore
+    def init_embed_split(self, data, split):
+        """reference :95-106 (unused by MedTok; kept for API parity): one k-means per half of the feature dimension"""
+        if self._is_initted():
+            return
+        print("Performing Kemans init for codebook")
+        embed1, cluster_size1 = kmeans(data[:, :split[0]].contiguous(), self.num_tokens, 10, use_cosine_sim=True)
+        embed2, cluster_size2 = kmeans(data[:, split[0]:].contiguous(), self.num_tokens, 10, use_cosine_sim=True)
+        self.weight.data.copy_(torch.cat([embed1, embed2], dim=-1))
+        self.cluster_size.data.copy_((cluster_size1 + cluster_size2) / 2.)
+        self.initted.data.copy_(torch.Tensor([True]))
+        self._initted_host = True
+
+    @torch.jit.ignore
+    def init_embed_with_ind(self, data, inds):
+        """reference :108-116 (unused by MedTok; `inds` is ignored there too)"""
+        self.init_embed_(data)
+
     def forward(self, embed_id):
         return F.embedding(embed_id, self.weight)
 
@@ -226,6 +244,7 @@ class NormEMAVectorQuantizer(nn.Module):
     def __init__(self, n_embed, embedding_dim, beta, decay=0.99, eps=1e-5,
                  statistic_code_usage=True, kmeans_init=False, codebook_init_path=''):
         super().__init__()
+        _lib.check_embedding_dim(embedding_dim, type(self).__name__)
         self.codebook_dim = embedding_dim
         self.num_tokens = n_embed
         self.beta = beta
@@ -493,8 +512,9 @@ class CVectorQuantiser(NormEMAVectorQuantizer):
     anchor sample with weight exp(-(embed_prob * K * 10) / (1 - decay) - 1e-3) (:379-393).  For anchor='closest' the anchor
     is the sample nearest to the code under the PRE-update codebook, found with the same tensor-core assignment kernel
     with the roles swapped (codes as rows, normalised samples as the codebook) and gathered with mtvq_lookup; the
-    K x D blend itself is plain elementwise PyTorch (not on the hot path).  anchor='probrandom' (a K x N softmax +
-    multinomial) and contras_loss=True (a NameError in the reference, :396-402) are not implemented."""
+    K x D blend itself is plain elementwise PyTorch (not on the hot path).  anchor='random' is the feature pool of
+    :405-460, anchor='probrandom' (:387-390) a K x N softmax + multinomial in PyTorch (a random draw: not bit-comparable);
+    contras_loss=True is a NameError in the reference (:396-402) and raises here too."""
 
     def __init__(self, n_embed, embedding_dim, beta, decay=0.99, eps=1e-5,
                  statistic_code_usage=True, kmeans_init=True, codebook_init_path='',
@@ -504,8 +524,8 @@ class CVectorQuantiser(NormEMAVectorQuantizer):
             raise NotImplementedError("only distance='l2' (on l2-normalised rows 'cos' selects the same codes)")
         if contras_loss:
             raise NotImplementedError("contras_loss=True raises NameError in the reference (:396-402)")
-        if anchor == 'probrandom':
-            raise NotImplementedError("anchor='probrandom' materialises a K x N softmax; use 'closest' or 'random'")
+        if anchor not in ('closest', 'random', 'probrandom'):
+            raise ValueError(f"unknown anchor {anchor!r}")
         self.num_embed = n_embed
         self.n_e = n_embed
         self.embed_dim = embedding_dim
@@ -519,8 +539,8 @@ class CVectorQuantiser(NormEMAVectorQuantizer):
         self._ws_anchor = _lib.Workspace()
 
     def forward(self, z, temp=None, rescale_logits=False, return_logits=False):
-        reinit = self.training and self.anchor in ('closest', 'random') and not self.init
-        w_old = self.embedding.weight.data.clone() if (reinit and self.anchor == 'closest') else None
+        reinit = self.training and self.anchor in ('closest', 'random', 'probrandom') and not self.init
+        w_old = self.embedding.weight.data.clone() if (reinit and self.anchor in ('closest', 'probrandom')) else None
         z_q, loss, idx = super().forward(z)
         if self.training:
             with torch.no_grad():
@@ -537,8 +557,20 @@ class CVectorQuantiser(NormEMAVectorQuantizer):
                         feat = torch.empty(k, d, dtype=torch.float32, device=zf.device)
                         _lib.check(_lib.lib().mtvq_lookup(None, _lib.ptr(zf), _lib.ptr(near), k, d, n, _lib.ptr(feat), None,
                                                           None, None, 0, _lib.stream_ptr(zf.device)), "mtvq_lookup")
-                    else:
+                    elif self.anchor == 'random':
                         feat = self.pool.query(zf)
+                    else:
+                        # 'probrandom' (:387-390): one sample per code drawn from softmax over the samples of
+                        # d = -|z|^2 - |e|^2 + 2 z.e under the pre-update codebook.  A K x N softmax by definition
+                        # (training batches are a few hundred rows); plain PyTorch, in row chunks of the codebook
+                        w_src = self.embedding.weight.data if w_old is None else w_old
+                        pick = torch.empty(k, dtype=torch.int64, device=zf.device)
+                        zz = zf.pow(2).sum(1)
+                        for lo in range(0, k, 4096):
+                            wc = w_src[lo:lo + 4096]
+                            dkn = -(wc.pow(2).sum(1, keepdim=True) + zz[None, :] - 2.0 * wc @ zf.t())
+                            pick[lo:lo + 4096] = torch.multinomial(F.softmax(dkn, dim=1), num_samples=1).view(-1)
+                        feat = zf[pick]
                     dec = torch.exp(-(self.embed_prob * self.num_embed * 10) / (1 - self.decay) - 1e-3).unsqueeze(1)
                     self.embedding.weight.data = self.embedding.weight.data * (1 - dec) + feat * dec
                     if self.first_batch:

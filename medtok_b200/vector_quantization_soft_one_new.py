@@ -135,6 +135,9 @@ class VectorQuantizer(nn.Module):
         self.initted = False
         if not l2_norm:
             raise NotImplementedError("l2_norm=False is a NameError in the reference too (:147-155)")
+        _lib.check_embedding_dim(e_dim, "VectorQuantizer")
+        if not 1 <= k <= 8:
+            raise _lib.MedTokVQError(f"VectorQuantizer: top-k must be in [1, 8], got k={k}")
 
         self.cross_attn = CrossAttention(e_dim, num_head, dropout=0.1, layers=2)
         self.proj_text = nn.Linear(self.split[0], e_dim)

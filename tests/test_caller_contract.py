@@ -58,3 +58,15 @@ def test_hard_quantizer_surface():
     for name in ("l2norm", "ema_inplace", "norm_ema_inplace", "sample_vectors", "kmeans", "EmbeddingEMA",
                  "NormEMAVectorQuantizer", "VectorQuantizer", "CVectorQuantiser", "FeaturePool"):
         assert hasattr(m, name), name
+
+
+def test_unsupported_embedding_dims_are_rejected_at_construction():
+    """D must be a multiple of 16 and <= 256 (tcgen05 operand layout): the constructors say so instead of the first forward"""
+    from medtok_b200 import _lib
+    from medtok_b200.norm_ema_quantizer import NormEMAVectorQuantizer
+    from medtok_b200.vector_quantization_soft_one_new import VectorQuantizer
+    with pytest.raises(_lib.MedTokVQError, match="multiple of 16"):
+        NormEMAVectorQuantizer(64, 8, 0.25)                       # tokenizer.py's unused default codebook_embed_dim=8
+    with pytest.raises(_lib.MedTokVQError, match="multiple of 16"):
+        VectorQuantizer(n_e=96, e_dim=24, beta=0.25, entropy_loss_ratio=0.0, l2_norm=True, show_usage=False, split=[24, 24])
+    NormEMAVectorQuantizer(64, 16, 0.25)

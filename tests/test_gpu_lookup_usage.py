@@ -146,3 +146,37 @@ def test_cvector_quantiser_matches_reference_golden(dev):
         # continue from the reference's own state so that every step is checked on its own
         q.embedding.weight.data.copy_(torch.from_numpy(a[f"weight_{s}"]).to(dev))
         q.embed_prob.copy_(torch.from_numpy(a[f"embed_prob_{s}"]).to(dev))
+
+
+@pytest.mark.parametrize("anchor", ["random", "probrandom"])
+def test_cvector_quantiser_random_anchors(dev, anchor):
+    """anchor='random' (feature pool, norm_ema_quantizer.py:405-460) and 'probrandom' (:387-390) draw samples, so they
+    are checked through what is deterministic: the forward part equals the norm-EMA forward of the same inputs (indices,
+    z_q, loss, cluster_size), embed_prob follows its EMA, and every re-initialised row is the reference's blend
+    w * (1 - dec) + feat * dec of the norm-EMA-updated row with SOME normalised sample of the batch."""
+    from medtok_b200.norm_ema_quantizer import CVectorQuantiser, NormEMAVectorQuantizer
+    g = torch.Generator().manual_seed(8)
+    n, d, k = 700, 32, 96
+    z = torch.randn(n, d, 1, 1, generator=g).to(dev)
+    w0 = torch.nn.functional.normalize(torch.randn(k, d, generator=g), dim=-1).to(dev)
+    q = CVectorQuantiser(n_embed=k, embedding_dim=d, beta=0.25, kmeans_init=False, anchor=anchor).to(dev).train()
+    base = NormEMAVectorQuantizer(k, d, 0.25).to(dev).train()
+    q.embedding.weight.data.copy_(w0)
+    base.embedding.weight.data.copy_(w0)
+    torch.manual_seed(0)
+    with torch.no_grad():
+        z_q, loss, idx = q(z)
+        z_q0, loss0, idx0 = base(z)
+    assert torch.equal(idx, idx0) and torch.equal(z_q, z_q0) and float(loss) == float(loss0)
+    assert torch.equal(q.cluster_size, base.cluster_size)
+    bins = torch.bincount(idx, minlength=k).float()
+    assert torch.allclose(q.embed_prob, 0.01 * bins / n, atol=1e-9)
+    dec = torch.exp(-(q.embed_prob * k * 10) / (1 - 0.99) - 1e-3).unsqueeze(1)
+    zf = torch.nn.functional.normalize(z.view(n, d), dim=-1)
+    w_ema = base.embedding.weight.data
+    feat = (q.embedding.weight.data - w_ema * (1 - dec)) / dec             # the sample each row was pulled towards
+    live = dec.squeeze(1) > 1e-3                                            # rows whose blend weight is not negligible
+    assert live.any()
+    nearest = torch.cdist(feat[live], zf).min(dim=1).values
+    assert float(nearest.max()) <= 1e-3, "a re-initialised row is not a blend with a sample of the batch"
+
