@@ -451,13 +451,8 @@ __global__ void __launch_bounds__(256, 3) sorted_rows_kernel(const float* __rest
 // ------------------------------------------------------------------------------------------------
 constexpr int kEmaCodes = 32;   // codes per CTA
 
-// Cross-GPU exchange fused into the finalize (multi-GPU data parallel, norm_ema_quantizer.py:188,195,203): every
-// rank's packed statistics live in peer-mapped memory; a rank announces "my statistics of step `epoch` are complete" by
-// writing the epoch into its slot of every peer's flag array (one releasing system-scope store per peer over NVLink),
-// waits until all its own slots carry the epoch, and then reads the W partial statistics straight out of the peers'
-// memory, adding them in RANK ORDER in fp64 -- so every rank computes bit-identical sums and the replicas stay
-// identical without a broadcast.  One kernel instead of all-reduce + finalize; the statistics buffers alternate between
-// two copies (epoch parity) so that a rank that runs ahead cannot overwrite what a slower peer is still reading.
+// Cross-GPU exchange (multi-GPU data parallel, norm_ema_quantizer.py:188,195,203): peer-mapped buffers of
+// ema_finalize_peers_kernel below.
 struct PeerTable {
     const double* const* stats;   // [world] peer-mapped statistics buffers of this epoch's parity
     unsigned* const*     flags;   // [world] peer-mapped flag arrays, flags[r][q] = last epoch rank q announced to rank r
@@ -482,9 +477,8 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
     return v;
 }
 
-template <bool PEERS>
 __global__ void __launch_bounds__(256) ema_finalize_kernel(float* __restrict__ weight, float* __restrict__ cluster_size,
-                                                            const double* __restrict__ stats, PeerTable pt, int k, int d,
+                                                            const double* __restrict__ stats, int k, int d,
                                                             float beta, float decay, float alpha, int update_cs,
                                                             int update_w, float* __restrict__ loss) {
     // tile[c][i] (row stride d + 1: conflict-free when 32 threads walk 32 different rows) holds, per code,
@@ -493,34 +487,7 @@ __global__ void __launch_bounds__(256) ema_finalize_kernel(float* __restrict__ w
     float* wold = tile + kEmaCodes * (d + 1);
     __shared__ double bins_s[kEmaCodes];
     const int code0 = blockIdx.x * kEmaCodes;
-    if (PEERS) {
-        if (threadIdx.x < pt.world) {
-            if (blockIdx.x == 0) {
-                __threadfence_system();
-                st_release_sys(pt.flags[threadIdx.x] + pt.rank, pt.epoch);
-            }
-            const unsigned* mine = pt.flags[pt.rank] + threadIdx.x;
-            // bounded wait: a peer that crashed (or never reaches this step) must not park every GPU inside a kernel
-            // where no watchdog can reach it -- after the limit the kernel traps and the host sees a launch failure
-            const unsigned long long t0 = global_timer_ns();
-            while ((int)(ld_acquire_sys(mine) - pt.epoch) < 0) {
-                __nanosleep(200);
-                if (global_timer_ns() - t0 > pt.timeout_ns) {
-                    printf("medtok_vq: rank %d waited more than %llu s for the statistics of rank %d (step %u)\n", pt.rank,
-                           pt.timeout_ns / 1000000000ull, (int)threadIdx.x, pt.epoch);
-                    __trap();
-                }
-            }
-        }
-        __syncthreads();
-    }
-    // one statistic, summed over the ranks in rank order (PEERS) or read from the local / all-reduced buffer
-    auto stat = [&](size_t i) -> double {
-        if (!PEERS) return stats[i];
-        double s = 0.0;
-        for (int r = 0; r < pt.world; ++r) s += __ldcv(pt.stats[r] + i);
-        return s;
-    };
+    auto stat = [&](size_t i) -> double { return stats[i]; };     // the local or all-reduced packed statistics
     if (blockIdx.x == 0 && threadIdx.x == 0 && loss) {
         const double sse = stat((size_t)k + (size_t)k * d), rows = stat((size_t)k + (size_t)k * d + 1);
         const float mse = (float)(sse / (rows * (double)d));
@@ -878,7 +845,7 @@ static cudaError_t ema_finalize_configure() {
     static PerDeviceOnce once;
     bool& configured = once.flag();
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(ema_finalize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(ema_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
         if (e != cudaSuccess) return e;
         configured = true;
     }
@@ -890,8 +857,8 @@ cudaError_t launch_ema_finalize(float* weight, float* cluster_size, const double
     // python: mul_(decay).add_(new, alpha=1-decay): both scalars are doubles cast to fp32
     const size_t smem = sizeof(float) * 2 * kEmaCodes * (d + 1);   // <= 65.8 KB at d = 256
     if (cudaError_t e = ema_finalize_configure()) return e;
-    ema_finalize_kernel<false><<<(k + kEmaCodes - 1) / kEmaCodes, 256, smem, s>>>(
-        weight, cluster_size, stats, PeerTable{}, k, d, (float)beta, (float)decay, (float)(1.0 - decay), update_cs, update_w,
+    ema_finalize_kernel<<<(k + kEmaCodes - 1) / kEmaCodes, 256, smem, s>>>(
+        weight, cluster_size, stats, k, d, (float)beta, (float)decay, (float)(1.0 - decay), update_cs, update_w,
         loss);
     ++g_kernel_launches;
     return cudaGetLastError();
