@@ -233,6 +233,13 @@ MTVQ_API int mtvq_debug_set_trace(void *trace_dev);
  * against every code by the exact CUDA-core scan (cross-check; slow).  All three give bit-identical results. */
 MTVQ_API int mtvq_debug_set_soft_route(int route);
 
+/* route of the hard assignment (mtvq_hard_assign / mtvq_hard_forward) on this host thread: -1 or 0 = automatic (the
+ * MTVQ_HARD_ROUTE environment variable, else by shape), 1 = always the single tensor pass with score records, 2 = the
+ * two-pass route (record-free pass, rows sorted by their best 128-code chunk, per-chunk re-scoring fused with the row
+ * work) whenever the shape allows it (D <= 64, at least two and at most 8192 chunks of 128 codes, enough rows for
+ * four-row-tile blocks).  Both routes give bit-identical indices; the per-code sums differ in summation order only. */
+MTVQ_API int mtvq_debug_set_hard_route(int route);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,7 @@ _SIGNATURES = {
     "mtvq_debug_set_events": (_int, [_vp, _vp]),
     "mtvq_debug_set_trace": (_int, [_vp]),
     "mtvq_debug_set_soft_route": (_int, [_int]),
+    "mtvq_debug_set_hard_route": (_int, [_int]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

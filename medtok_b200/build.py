@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "_build")
 SO_PATH = os.path.join(HERE, "libmedtok_vq.so")
-SOURCES = ["api.cu", "assign_tc.cu", "assign_exact.cu", "rows.cu", "soft.cu", "small.cu"]
+SOURCES = ["api.cu", "assign_tc.cu", "assign_exact.cu", "group.cu", "rows.cu", "soft.cu", "small.cu"]
 PROBE_SOURCES = ["microbench.cu"]          # diagnostics: only in builds made with -DMTVQ_WITH_MICROBENCH
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr"]

@@ -9,6 +9,7 @@
 #include "../../include/medtok_vq.h"
 #include "assign_exact.h"
 #include "assign_tc.h"
+#include "group.h"
 #ifdef MTVQ_WITH_MICROBENCH
 #include "microbench.h"
 #endif
@@ -104,10 +105,36 @@ void fill_coarse(CoarseParams& p, const float* z, int64_t n, int d, int norm_mod
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MTVQ_DBG"); dbg = e ? atoi(e) : 0; } p.debug_flags = dbg; }
 }
 
+// Two-pass route of the hard assignment: record-free tensor pass -> rows sorted by their best
+// 128-code chunk -> REFINE pass over 128-row tiles of one chunk each.  Worth it where the single pass is bound by its
+// epilogue (D <= 64: four row tiles per block) and the batch is large enough to amortise the sort.
+// MTVQ_HARD_ROUTE=1 forces the single-pass route (A/B timing, cross-check tests).
+int hard_route_env() {
+    static int v = -1;
+    if (v < 0) { const char* s = getenv("MTVQ_HARD_ROUTE"); v = s ? atoi(s) : 0; }
+    return v;
+}
+thread_local int g_hard_route = -1;      // mtvq_debug_set_hard_route: -1 = environment / automatic
+bool two_pass_ok(int64_t n, int d, int k, int num_sms) {
+    const int route = g_hard_route >= 0 ? g_hard_route : hard_route_env();
+    if (route == 1) return false;
+    const int nchunks = pad_codes(k) / 128;
+    if (coarse_row_tiles(d, n, num_sms) != 4 || nchunks < 2 || nchunks > kGroupMaxChunks || n >= (1LL << 30)) return false;
+    return route == 2 || n >= 262144;
+}
+
+// fused row outputs of the two-pass route (training forward): z_q, squared error and per-code sums come out of the
+// REFINE pass (decided rows) and finish_flagged (near-tie rows) instead of the sorted-rows pass
+struct FusedRows {
+    float*  z_q;
+    double* stats;
+    bool    done;      // out: the route produced them
+};
+
 // hard assignment: idx[n] (int64, first-index argmin) + ws.bins_i32 (per-code row counts) + denom;
 // `codes` are the rows the distances are taken against
 int assign_rows(const float* z, int64_t n, int d, int norm_mode, const float* codes, int k, float* denom, int64_t* idx,
-                const Workspace& ws, const DeviceInfo& di, bool exact_only, cudaStream_t st) {
+                const Workspace& ws, const DeviceInfo& di, bool exact_only, cudaStream_t st, FusedRows* fused = nullptr) {
     MTVQ_CUDA(cudaMemsetAsync(ws.counters, 0, sizeof(int) * CNT_COUNT, st), "memset counters");
     MTVQ_CUDA(cudaMemsetAsync(ws.bins_i32, 0, sizeof(int) * k, st), "memset bins");
     if (n == 0) return 0;
@@ -128,10 +155,29 @@ int assign_rows(const float* z, int64_t n, int d, int norm_mode, const float* co
     MTVQ_CUDA(cudaMemsetAsync(ws.cand_cnt, 0, sizeof(int) * n, st), "memset cand_cnt");
     CoarseParams p;
     fill_coarse(p, z, n, d, norm_mode, k, ws, denom, 1, false, idx);
-    if (g_ev_before) cudaEventRecord(g_ev_before, st);
-    MTVQ_CUDA(launch_coarse(p, MODE_ARGMAX, coarse_row_tiles(d, n, di.num_sms), di.num_sms, st), "coarse argmax");
-    if (g_ev_after) cudaEventRecord(g_ev_after, st);
-    g_ev_before = g_ev_after = nullptr;
+    const bool two_pass = two_pass_ok(n, d, k, di.num_sms);
+    if (two_pass) {
+        MTVQ_CUDA(cudaMemsetAsync(ws.ghist, 0, sizeof(int) * (pad_codes(k) / 128), st), "memset ghist");
+        p.grp = ws.grp;
+        p.ghist = ws.ghist;
+        if (g_ev_before) cudaEventRecord(g_ev_before, st);
+        MTVQ_CUDA(launch_coarse(p, MODE_GROUP, 4, di.num_sms, st), "coarse group");
+        if (g_ev_after) cudaEventRecord(g_ev_after, st);
+        g_ev_before = g_ev_after = nullptr;
+        MTVQ_CUDA(launch_group_sort(ws, denom, n, k, di.num_sms, st), "group sort");
+        CoarseParams r = p;
+        r.denom = nullptr;
+        r.entries = static_cast<const int4*>(ws.entries);
+        r.tile_tab = static_cast<const int2*>(ws.tile_tab);
+        r.n_tiles_dev = ws.counters + CNT_TILES;
+        if (fused) { r.w = codes; r.z_q = fused->z_q; r.stats = fused->stats; r.fuse_rows = 1; }
+        MTVQ_CUDA(launch_coarse(r, MODE_REFINE, 1, di.num_sms, st), "coarse refine");
+    } else {
+        if (g_ev_before) cudaEventRecord(g_ev_before, st);
+        MTVQ_CUDA(launch_coarse(p, MODE_ARGMAX, coarse_row_tiles(d, n, di.num_sms), di.num_sms, st), "coarse argmax");
+        if (g_ev_after) cudaEventRecord(g_ev_after, st);
+        g_ev_before = g_ev_after = nullptr;
+    }
     // near-tie rows (a few percent) carry a candidate list out of the tensor pass; the few whose list is incomplete
     // (a third granule within the margin) get it from a COLLECT pass -- the row count is only known on the device,
     // the kernel splits the codebook over CTAs to fill the SMs (assign_tc.cu "work items").  Exact fp32 decides.
@@ -143,6 +189,11 @@ int assign_rows(const float* z, int64_t n, int d, int norm_mode, const float* co
     MTVQ_CUDA(launch_resolve(z, d, norm_mode, codes, k, ws, p.cand_cap, idx, di.num_sms, st), "resolve");
     MTVQ_CUDA(launch_exact_scan(z, n, d, norm_mode, codes, k, ws.cc, ws.full_rows, ws.counters + CNT_FULL, idx, ws.bins_i32,
                                 nullptr, di.num_sms, st), "exact_scan(overflow)");
+    if (two_pass && fused) {
+        MTVQ_CUDA(launch_finish_flagged(z, denom, codes, idx, n, d, k, fused->z_q, fused->stats, ws, di.num_sms, st),
+                  "finish_flagged");
+        fused->done = true;
+    }
     return 0;
 }
 
@@ -276,8 +327,9 @@ int mtvq_hard_forward(const float* z, int64_t n, int d, int norm_mode, float* we
 
     if (!(flags & MTVQ_F_ACCUMULATE))
         MTVQ_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * mtvq_stats_len(d, k), st), "memset stats");
-    if (int r = assign_rows(z, n, d, norm_mode, weight, k, ws.denom, idx, ws, di, false, st)) return r;
-    if (n > 0) {
+    FusedRows fused{z_q, stats, false};
+    if (int r = assign_rows(z, n, d, norm_mode, weight, k, ws.denom, idx, ws, di, false, st, upd_w ? &fused : nullptr)) return r;
+    if (n > 0 && !fused.done) {
         if (upd_w) {   // per-code sums wanted: one fused pass over the rows in code-sorted order
             MTVQ_CUDA(launch_sorted_rows(z, ws.denom, weight, idx, n, d, k, z_q, stats, ws, di.num_sms, st), "sorted_rows");
         } else {       // streaming gather/STE/SSE + bins only
@@ -482,6 +534,12 @@ int mtvq_debug_set_soft_route(int route) {
     if (route == 3) { g_no_small = true; return 0; }      // 3: small batches take the tensor route too (A/B, tests)
     if (route == 4) { g_no_small = false; return 0; }     // 4: back to automatic
     g_soft_route = route;
+    return 0;
+}
+
+int mtvq_debug_set_hard_route(int route) {
+    if (route < -1 || route > 2) return fail(MTVQ_ERR_BAD_ARG, "route must be -1 (automatic), 0, 1 (single pass) or 2 (two-pass whenever it applies)%s", "");
+    g_hard_route = route;
     return 0;
 }
 

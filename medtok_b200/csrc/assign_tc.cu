@@ -65,7 +65,7 @@ constexpr int kRecords    = 1024;                    // records per CTA in the T
 // The codebook ring is what hides the L2 latency of the stream: a D = 256 chunk fills four stages, so with a 4-stage
 // ring the tensor pipe waits for every reload (measured 0.60 of peak, 0.67 with six stages).
 // RT = 2 (D = 128) keeps the 4-stage map: six stages measured 2-12 % SLOWER there.
-template <int RT>
+template <int RT, bool REFINE = false>
 struct SmemMap {
     static constexpr int kStages   = (RT == 1) ? 6 : 4;                  // codebook K-block stages of 16 KB
     static constexpr int kRec      = (RT == 1) ? 512 : 1024;             // epilogue threads x state sets
@@ -76,7 +76,34 @@ struct SmemMap {
     static constexpr int kOffSlots = kOffBBias + kBiasStages * kBiasBytes;   // 4 chunks x kRec records x 16 B (fp16 granules)
     static constexpr int kOffState = kOffSlots + 4 * kRec * 16;              // kRec records x 16 B
     static constexpr int kOffBars  = kOffState + kRec * 16;
-    static constexpr int kNumBars  = 2 * kStages + 2 * kBiasStages + 4 + 4 + 4 + 4;
+    static constexpr int kNumBars  = 2 * kStages + 2 * kBiasStages + 4 + 4 + 4 + 4 + 8 + 3 + 4;
+    static constexpr int kOffTmem  = kOffBars + kNumBars * 8;
+    static constexpr int kSmemBytes = kOffTmem + 16;
+    static constexpr int kOffAcc = 0, kOffStage = 0;                      // REFINE only
+    static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
+};
+
+// MODE_REFINE (D <= 64, one 128-code chunk per 128-row tile): ONE fp16 row tile and ONE codebook stage (consecutive tiles
+// mostly share their chunk: it is reloaded only when the chunk changes), and instead of score records the fp64 per-code
+// accumulators of the fused row work (128 codes x d) and THREE staging tiles into which the gathered fp32 rows land by
+// cp.async (row stride 4 d + 16 bytes: the row-per-thread conversion reads are conflict free).  A staging tile is busy
+// from the copy until the finishing warps are done with the rows; three of them keep three such chains interleaved.
+constexpr int kStageTileBytes = kTileRows * (4 * 64 + 16);               // 34816
+constexpr int kStageTiles     = 3;
+template <>
+struct SmemMap<1, true> {
+    static constexpr int kStages   = 1;
+    static constexpr int kRec      = 512;
+    static constexpr int kOffA     = 0;                                  // 1 tile x 16 KB
+    static constexpr int kOffOnes  = 16384;
+    static constexpr int kOffBData = kOffOnes + kBiasBytes;
+    static constexpr int kOffBBias = kOffBData + kStages * kKblkBytes;
+    static constexpr int kOffSlots = kOffBBias + kBiasStages * kBiasBytes;   // 12 KB of epilogue scratch (refine_epilogue)
+    static constexpr int kOffState = kOffSlots + 12288;
+    static constexpr int kOffAcc   = kOffState;                          // double [128][d]
+    static constexpr int kOffStage = kOffAcc + kTileCodes * 64 * 8;
+    static constexpr int kOffBars  = kOffStage + kStageTiles * kStageTileBytes;
+    static constexpr int kNumBars  = 2 * kStages + 2 * kBiasStages + 4 + 4 + 4 + 4 + 8 + 3 + 4;
     static constexpr int kOffTmem  = kOffBars + kNumBars * 8;
     static constexpr int kSmemBytes = kOffTmem + 16;
     static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
@@ -91,20 +118,28 @@ struct Bars {
     uint64_t* a_empty;   // [4]
     uint64_t* acc_full;  // [4]
     uint64_t* acc_empty; // [4]
+    uint64_t* dec_full;  // [4]  REFINE: a tile's decisions are in the ring (deciders -> finishers)
+    uint64_t* dec_empty; // [4]
+    uint64_t* p1_full;   // [4]  REFINE: the ROWS half has left a tile's zf in the staging tile (-> SUMS)
+    uint64_t* stg_empty; // [3]  REFINE: the finishers are done with a staging tile (-> loader)
 };
 
-template <int RT>
+template <class SM>
 __device__ __forceinline__ Bars carve_bars(unsigned char* smem) {
-    uint64_t* b = reinterpret_cast<uint64_t*>(smem + SmemMap<RT>::kOffBars);
+    uint64_t* b = reinterpret_cast<uint64_t*>(smem + SM::kOffBars);
     Bars r;
-    r.bd_full = b;                 b += SmemMap<RT>::kStages;
-    r.bd_empty = b;                b += SmemMap<RT>::kStages;
+    r.bd_full = b;                 b += SM::kStages;
+    r.bd_empty = b;                b += SM::kStages;
     r.bb_full = b;                 b += kBiasStages;
     r.bb_empty = b;                b += kBiasStages;
     r.a_full = b;                  b += 4;
     r.a_empty = b;                 b += 4;
     r.acc_full = b;                b += 4;
-    r.acc_empty = b;
+    r.acc_empty = b;               b += 4;
+    r.dec_full = b;                b += 4;
+    r.dec_empty = b;               b += 4;
+    r.p1_full = b;                 b += 4;
+    r.stg_empty = b;
     return r;
 }
 
@@ -266,6 +301,19 @@ __device__ __forceinline__ void consume_argmax64(const float (&va)[32], const fl
     }
 }
 
+// GROUP (two-pass hard route): branch-free.  The thread only tracks the three largest 64-column maxima of its column
+// half (one per 128-code chunk) and the chunks of the two largest; which COLUMN wins is left to the REFINE pass.
+template <int NTOP>
+__device__ __forceinline__ void consume_group(const float (&va)[32], const float (&vb)[32], int c, RowState<NTOP>& st) {
+    const float x = fmaxf(max32(va), max32(vb));
+    const bool p1 = x > st.m1, p2 = x > st.m2;
+    st.m3 = fmaxf(st.m3, fminf(st.m2, x));
+    st.m2 = fmaxf(st.m2, fminf(st.m1, x));
+    st.chunk2 = p1 ? st.best_chunk : (p2 ? c : st.chunk2);
+    st.m1 = fmaxf(st.m1, x);
+    st.best_chunk = p1 ? c : st.best_chunk;
+}
+
 // TOPK (single-pass soft top-k): a thread keeps its kTopSlots best granules of the row block -- the granule maximum
 // (sorted list `top`, slot id packed into the low 3 mantissa bits: relative error 2^-20, covered by the margin), the
 // granule id (shared memory) and the 32 scores as an fp16 record (global scratch).  A granule can only matter if its
@@ -340,13 +388,456 @@ __device__ __forceinline__ int scan_record(const unsigned char* slots, int rec, 
     return n;
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// REFINE loader: the rows of a tile are scattered over z (the tile is 128 entries of the chunk-sorted order), so a
+// row-per-thread loader would expose a DRAM round trip per tile.  Here the 16 lanes of a group copy whole 4 d-byte rows
+// global -> shared with cp.async (no registers held, two tiles in flight), and only then does thread r turn row r into
+// the fp16 operand planes -- the same values the GROUP pass fed to the tensor cores: x * rcp(norm), norm from the entry.
+// ------------------------------------------------------------------------------------------------
+template <class SM, bool TRACE>
+__device__ __forceinline__ void refine_loader(const CoarseParams& p, unsigned char* smem, const Bars& bars, int r, int lane,
+                                              int item0, int item_end) {
+    // pipeline trace (mtvq_debug_set_trace, CTA 0): per tile [0] copies issued, [1] landed, [2] operand tile published,
+    // [3] deciders saw the accumulator, [4] decisions published, [5] finishers saw them, [6] ownership scan done, [7] tile finished
+    const bool tracing = TRACE && p.trace != nullptr && blockIdx.x == 0 && r == 0;
+    const int d = p.d, vpr = d >> 2, nplanes = d >> 3;
+    const int row_stride = 4 * d + 16;
+    const int g = r >> 4, q = r & 15;
+    unsigned char* stage = smem + SM::kOffStage;
+    // copies of tile `item` into staging buffer `buf`; returns the entry of row r (norm, validity) for the conversion
+    auto issue = [&](int item, int buf) -> int4 {
+        int4 e = make_int4(-1, 0, 0x3f800000, 0);
+        if (item < item_end) {
+            const int2 tt = __ldg(&p.tile_tab[item]);
+            const int cnt = tt.x >> 16;
+            if (r < cnt) e = __ldg(&p.entries[tt.y + r]);
+            unsigned char* st = stage + buf * kStageTileBytes;
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+                const int ex = __shfl_sync(0xffffffffu, e.x, (lane & 16) + i);      // entry of row g * 16 + i
+                const int rr = g * 16 + i;
+                if (ex != -1 && q < vpr)
+                    cp_async16(st + rr * row_stride + q * 16, p.z + (size_t)((unsigned)ex & kEntRowMask) * d + 4 * q);
+            }
+        }
+        cp_async_commit();
+        return e;
+    };
+    const bool fuse = p.fuse_rows != 0;
+    int4 e = issue(item0, 0);
+    if (TRACE && tracing) p.trace[0] = clock64();
+    int4 e1 = issue(item0 + 1, 1);
+    uint32_t bi = 0;
+    int buf = 0;                                         // bi % kStageTiles
+    for (int item = item0; item < item_end; ++item, ++bi) {
+        cp_async_wait<1>();                              // this thread's copies of tile bi have landed ...
+        named_bar_sync(6, kLoadWarps * 32);              // ... and everybody else's
+        if (TRACE && tracing && bi < 512u) p.trace[bi * 8 + 1] = clock64();
+        const bool valid = e.x != -1;
+        const float rden = __frcp_rn(__int_as_float(e.z));
+        const float4* src = reinterpret_cast<const float4*>(stage + buf * kStageTileBytes + r * row_stride);
+        uint4 pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            pk[j] = make_uint4(0, 0, 0, 0);
+            if (valid && j < nplanes) {
+                const float4 x0 = src[2 * j], x1 = src[2 * j + 1];
+                __half2 h0 = __floats2half2_rn(x0.x * rden, x0.y * rden);
+                __half2 h1 = __floats2half2_rn(x0.z * rden, x0.w * rden);
+                __half2 h2 = __floats2half2_rn(x1.x * rden, x1.y * rden);
+                __half2 h3 = __floats2half2_rn(x1.z * rden, x1.w * rden);
+                pk[j].x = *reinterpret_cast<uint32_t*>(&h0);
+                pk[j].y = *reinterpret_cast<uint32_t*>(&h1);
+                pk[j].z = *reinterpret_cast<uint32_t*>(&h2);
+                pk[j].w = *reinterpret_cast<uint32_t*>(&h3);
+            }
+        }
+        unsigned char* tile = smem + SM::kOffA + r * 16;
+        mbar_wait_backoff(&bars.a_empty[0], (bi & 1u) ^ 1u, 100);      // the previous tile's MMAs have read the operand tile
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < nplanes) *reinterpret_cast<uint4*>(tile + j * kPlaneBytes) = pk[j];
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.a_full[0]);
+        if (TRACE && tracing && bi < 512u) p.trace[bi * 8 + 2] = clock64();
+        // Tile bi + 2 goes into the staging tile that held tile bi - 1: every loader thread has converted its row of it
+        // (the barrier above), and with fused rows the finishing warps -- they read the fp32 rows there, so z makes one
+        // trip from HBM -- must be done with it too.  Waiting HERE, after tile bi has been handed to the tensor pipe, keeps
+        // the staging tiles' chains (copy -> convert -> MMA -> decide -> finish) interleaved.
+        const int nbuf = buf == 0 ? kStageTiles - 1 : buf - 1;          // (bi + 2) % 3
+        if (fuse && bi >= 1u) mbar_wait_backoff(&bars.stg_empty[nbuf], (((bi + 2u) / kStageTiles) & 1u) ^ 1u, 100);
+        e = e1;
+        e1 = issue(item + 2, nbuf);
+        if (TRACE && tracing && bi + 2u < 512u) p.trace[(bi + 2u) * 8 + 0] = clock64();
+        buf = buf == kStageTiles - 1 ? 0 : buf + 1;
+    }
+    cp_async_wait<0>();
+}
+
+// REFINE codebook producer / MMA issuers.  Consecutive tiles of the chunk-sorted order mostly share their chunk, so the
+// single codebook stage (and the bias stage) is loaded once per RUN of tiles with the same chunk and handed back by all
+// four issuers with tcgen05.commit -- each may still have MMAs of the run in flight -- after the run's last tile.
+template <class SM>
+__device__ __forceinline__ void refine_producer(const CoarseParams& p, unsigned char* smem, const Bars& bars, int item0,
+                                                int item_end, bool use_bias) {
+    const int nplanes = p.d >> 3;
+    const int tile_b = (nplanes + 2) * kPlaneBytes;
+    const unsigned char* img = static_cast<const unsigned char*>(p.b_image);
+    const uint32_t bytes = (uint32_t)nplanes * kPlaneBytes;
+    int prev = -1;
+    uint32_t run = 0;
+    for (int item = item0; item < item_end; ++item) {
+        const int chunk = __ldg(&p.tile_tab[item]).x & 0xffff;
+        if (chunk == prev) continue;
+        prev = chunk;
+        const unsigned char* tile = img + (size_t)chunk * tile_b;
+        mbar_wait(&bars.bd_empty[0], (run & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&bars.bd_full[0], bytes);
+        bulk_g2s(smem + SM::kOffBData, tile, bytes, &bars.bd_full[0]);
+        if (use_bias) {
+            const uint32_t sb = run % kBiasStages;
+            mbar_wait(&bars.bb_empty[sb], ((run / kBiasStages) & 1u) ^ 1u);
+            mbar_arrive_expect_tx(&bars.bb_full[sb], kBiasBytes);
+            bulk_g2s(smem + SM::kOffBBias + sb * kBiasBytes, tile + (size_t)nplanes * kPlaneBytes, kBiasBytes, &bars.bb_full[sb]);
+        }
+        ++run;
+    }
+}
+
+template <class SM>
+__device__ __forceinline__ void refine_issuer(const CoarseParams& p, unsigned char* smem, const Bars& bars, uint32_t tmem_base,
+                                              int j, int item0, int item_end, bool use_bias) {
+    const int nsteps = p.d >> 4;                     // UMMA K-steps of 16 elements (D <= 64: one K-block)
+    const uint32_t idesc = umma_idesc_f16(kTileRows, kTileCodes);
+    const uint64_t dA = umma_smem_desc(smem_u32(smem + SM::kOffA), p.lbo_bytes, p.sbo_bytes);
+    const uint64_t dOnes = umma_smem_desc(smem_u32(smem + SM::kOffOnes), p.lbo_bytes, p.sbo_bytes);
+    const uint64_t dB = umma_smem_desc(smem_u32(smem + SM::kOffBData), p.lbo_bytes, p.sbo_bytes);
+    const uint64_t dBB0 = umma_smem_desc(smem_u32(smem + SM::kOffBBias), p.lbo_bytes, p.sbo_bytes);
+    const uint32_t tacc = tmem_base + (uint32_t)(j * kTileCodes);
+    int prev = -1;
+    uint32_t run = 0xffffffffu, uses = 0, bi = 0;
+    for (int item = item0; item < item_end; ++item, ++bi) {
+        const int chunk = __ldg(&p.tile_tab[item]).x & 0xffff;
+        if (chunk != prev) {                          // every issuer sees every run (shared barriers: one phase per run)
+            prev = chunk;
+            ++run;
+            mbar_wait(&bars.bd_full[0], run & 1u);
+            if (use_bias) mbar_wait(&bars.bb_full[run % kBiasStages], (run / kBiasStages) & 1u);
+        }
+        const uint32_t sb = run % kBiasStages;
+        // every issuer observes every phase of the shared operand-tile barrier (a parity wait is only meaningful within
+        // one phase) and takes part in handing the tile back, so the loader cannot get a phase ahead of any of them
+        mbar_wait(&bars.a_full[0], bi & 1u);
+        if ((int)(bi & 3u) != j) {
+            mbar_arrive(&bars.a_empty[0]);
+        } else {                                      // tile bi of the CTA lives in accumulator slot bi & 3
+            mbar_wait(&bars.acc_empty[j], (uses & 1u) ^ 1u);
+            ++uses;
+            tc_fence_after();
+            uint64_t da = dA, db = dB;
+            for (int ks = 0; ks < nsteps; ++ks) {
+                umma_f16(tacc, da, db, idesc, ks != 0);
+                da += (2 * kPlaneBytes) >> 4;
+                db += (2 * kPlaneBytes) >> 4;
+            }
+            if (use_bias) umma_f16(tacc, dOnes, dBB0 + (uint64_t)(sb * (kBiasBytes >> 4)), idesc, 1u);
+            umma_commit(&bars.acc_full[j]);
+            umma_commit(&bars.a_empty[0]);
+        }
+        const bool last_of_run = (item + 1 == item_end) || ((__ldg(&p.tile_tab[item + 1]).x & 0xffff) != chunk);
+        if (last_of_run) {
+            umma_commit(&bars.bd_empty[0]);
+            if (use_bias) umma_commit(&bars.bb_empty[sb]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// REFINE epilogue (two-pass hard route).  A tile is 128 entries of ONE chunk; tile bi of the CTA lives in accumulator
+// slot bi & 3.  The 16 epilogue warps split into two groups of eight, each with 16 lanes per row:
+//   warps 0-7  DECIDE tile t: both threads of a row (TMEM lane quarter w & 3, 64-column half w >> 2) locate the columns with
+//     score >= M - margin (M = the row's best coarse score of the GROUP pass, which has shown that no other chunk -- for a
+//     row listed twice: no third chunk -- reaches that bound); the thread of the left half decides: exactly one column
+//     -> final index (+ histogram); several -> the row's candidate list for the exact fp32 re-scoring (a row listed under
+//     two chunks appends to its list from both tiles).  Decisions go to a 4-tile ring in shared memory.  Then, fused rows
+//     only, the same warps do SUMS of tile t - 1: the per-code sums of its decided rows into the fp64 accumulators
+//     (128 codes x d in shared memory; the CTA's tiles are contiguous in the chunk-sorted order, so they are flushed only
+//     when the chunk changes).  The 16-lane group g OWNS the codes with code % 16 == g, so the accumulators are updated
+//     with plain loads and stores: shared-memory fp64 atomics are CAS loops at 2-4 cycles per lane and made the pass
+//     three times slower.
+//   warps 8-15 (fused rows only) ROWS of tile t, what sorted_rows_kernel does: zf = z / norm, z_q = zf + (w - zf), squared
+//     error, on the fp32 rows still sitting in the loader's staging tile (z makes one trip from HBM); zf is left in the
+//     staging tile for the sums.
+// Both halves are bound by the latency of their own instruction streams (no pipe is more than a quarter busy), which is
+// why the work is spread over all 16 warps and why the float -> double widening of the sums is done with integer
+// instructions (F2F.F64.F32 runs on the quarter-rate conversion unit that the divisions already keep busy).
+// ------------------------------------------------------------------------------------------------
+constexpr int kRefHitOff = 0;        // uint2  [half][128]      columns within the margin (bit masks)
+constexpr int kRefDecOff = 4096;     // int4   [4 tiles][128]   {code or -1, row, norm bits, 0}
+
+// exact float -> double without the conversion unit (normal numbers and zero; anything else takes the instruction)
+__device__ __forceinline__ double widen_exact(float f) {
+    const uint32_t b = __float_as_uint(f);
+    const uint32_t ex = b & 0x7f800000u;
+    if (ex == 0u || ex == 0x7f800000u) return (b << 1) == 0u ? __hiloint2double((int)b, 0) : (double)f;
+    return __hiloint2double((int)((b & 0x80000000u) | (((b & 0x7fffffffu) >> 3) + 0x38000000u)), (int)(b << 29));
+}
+
+template <int OFF_SCRATCH, int OFF_ACC, int OFF_STAGE, bool TRACE>
+__device__ __forceinline__ void refine_epilogue(const CoarseParams& p, unsigned char* smem, const Bars& bars, uint32_t tmem_base,
+                                                int warp, int lane, int item0, int item_end) {
+    const int d = p.d, vpr = d >> 2;
+    const int row_stride = 4 * d + 16;
+    const bool fuse = p.fuse_rows != 0;
+    int4* dec_ring = reinterpret_cast<int4*>(smem + OFF_SCRATCH + kRefDecOff);
+    const int tid_h = (warp & 7) * 32 + lane;         // within the half (0..255)
+    const int g16 = tid_h >> 4, q = tid_h & 15;       // 16 groups of 16 lanes
+    const bool lane_on = q < vpr;
+    if (warp < 8) {
+        // ---------------------------------- DECIDE (+ SUMS of the previous tile) ----------------------------------
+        const int quarter = warp & 3, half = warp >> 2;
+        const int rq = quarter * 32 + lane;
+        const int gsh = lane & 16;                    // position of this group's 16 lanes in the warp's ballots
+        const float margin = p.meta[META_MARGIN];
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 64);
+        uint2* hit_s = reinterpret_cast<uint2*>(smem + OFF_SCRATCH + kRefHitOff);
+        double* acc = reinterpret_cast<double*>(smem + OFF_ACC);
+        const int nacc = kTileCodes * d;
+        if (fuse) {
+            for (int i = tid_h; i < nacc; i += 256) acc[i] = 0.0;
+            named_bar_sync(1, 256);
+        }
+        auto flush = [&](int ch) {       // accumulators of chunk `ch` -> embed_sum (fp64 REDs), then zero
+            double* dst = p.stats + p.k + (size_t)ch * kTileCodes * d;
+            const int lim = min(kTileCodes, p.k - ch * kTileCodes) * d;
+            for (int i = tid_h; i < nacc; i += 256) {
+                const double v = acc[i];
+                if (v != 0.0 && i < lim) atomicAdd(dst + i, v);
+                acc[i] = 0.0;
+            }
+        };
+        // SUMS of tile number `t` (chunk `ch`): rows are taken by code ownership; the next owned row's data is fetched
+        // before the current accumulator update, so only updates of the same code wait for one another
+        int acc_chunk = -1;
+        auto sums = [&](uint32_t t, int ch, int sbuf) {
+            if (acc_chunk >= 0 && ch != acc_chunk) {
+                named_bar_sync(1, 256);               // every group is done with the previous chunk's tiles
+                flush(acc_chunk);
+                named_bar_sync(1, 256);
+            }
+            acc_chunk = ch;
+            const int slot = (int)(t & 3u);
+            mbar_wait(&bars.p1_full[slot], (t >> 2) & 1u);           // the ROWS half has left zf in the staging tile
+            const int4* dec = dec_ring + slot * 128;
+            const unsigned char* stg = smem + OFF_STAGE + sbuf * kStageTileBytes;
+            unsigned long long own_lo = 0ull, own_hi = 0ull;        // rows 0-63 / 64-127 (lane q looks at rows q, q + 16, ...)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int code = dec[j * 16 + q].x;
+                const unsigned b = __ballot_sync(0xffffffffu, code >= 0 && (code & 15) == g16);
+                const unsigned long long m16 = (unsigned long long)((b >> gsh) & 0xffffu);
+                if (j < 4) own_lo |= m16 << (16 * j); else own_hi |= m16 << (16 * (j - 4));
+            }
+            auto next_row = [&]() -> int {
+                if (own_lo) { const int r = __ffsll((long long)own_lo) - 1; own_lo &= own_lo - 1; return r; }
+                if (own_hi) { const int r = 63 + __ffsll((long long)own_hi); own_hi &= own_hi - 1; return r; }
+                return -1;
+            };
+            int rr = next_row();
+            int code = rr >= 0 ? dec[rr].x : 0;
+            float4 zf = (rr >= 0 && lane_on) ? *reinterpret_cast<const float4*>(stg + rr * row_stride + q * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
+            while (rr >= 0) {
+                const int rn = next_row();
+                const int code_n = rn >= 0 ? dec[rn].x : 0;
+                const float4 zn = (rn >= 0 && lane_on) ? *reinterpret_cast<const float4*>(stg + rn * row_stride + q * 16)
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (lane_on) {
+                    double2* a = reinterpret_cast<double2*>(acc + (code & (kTileCodes - 1)) * d + 4 * q);
+                    double2 a0 = a[0], a1 = a[1];
+                    a0.x += widen_exact(zf.x); a0.y += widen_exact(zf.y); a1.x += widen_exact(zf.z); a1.y += widen_exact(zf.w);
+                    a[0] = a0; a[1] = a1;
+                }
+                rr = rn; code = code_n; zf = zn;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars.stg_empty[sbuf]);      // the staging tile may be refilled
+        };
+        uint32_t bi = 0;
+        int sbuf = 0, sbuf_prev = 0, chunk_prev = -1;
+        for (int item = item0; item < item_end; ++item, ++bi) {
+            const int2 tt = __ldg(&p.tile_tab[item]);
+            const int chunk = tt.x & 0xffff, cnt = tt.x >> 16, start = tt.y;
+            const int slot = (int)(bi & 3u);
+            const uint32_t use_par = (bi >> 2) & 1u;
+            const bool valid = rq < cnt;
+            int4 e = make_int4(0, 0, 0, 0);                 // {row | flags, best coarse score, norm, -}
+            if (valid) e = __ldg(&p.entries[start + rq]);
+            const float thrF = __int_as_float(e.y) - margin;
+            mbar_wait(&bars.acc_full[slot], use_par);
+            if (TRACE && p.trace != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0 && bi < 512u) p.trace[bi * 8 + 3] = clock64();
+            tc_fence_after();
+            uint32_t ha = 0, hb = 0;
+            {
+                float va[32], vb[32];
+                tmem_ld32x2_wait(t_lane + (uint32_t)(slot * kTileCodes), va, vb);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_relaxed_addr(smem_u32(&bars.acc_empty[slot]));
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    ha |= (va[i] >= thrF) ? (1u << i) : 0u;
+                    hb |= (vb[i] >= thrF) ? (1u << i) : 0u;
+                }
+            }
+            if (!valid) ha = hb = 0u;
+            hit_s[half * 128 + rq] = make_uint2(ha, hb);
+            named_bar_sync(1, 256);
+            if (half == 0) {
+                const uint2 o = hit_s[128 + rq];
+                const uint32_t msk[4] = {ha, hb, o.x, o.y};          // columns [0,32) [32,64) [64,96) [96,128) of the chunk
+                const int nhit = __popc(ha) + __popc(hb) + __popc(o.x) + __popc(o.y);
+                const int first = ha ? __ffs(ha) - 1 : (hb ? 31 + __ffs(hb) : (o.x ? 63 + __ffs(o.x) : (o.y ? 95 + __ffs(o.y) : -1)));
+                const int row = (int)((unsigned)e.x & kEntRowMask);
+                const bool cross = ((unsigned)e.x & kEntCross) != 0u, second = ((unsigned)e.x & kEntSecond) != 0u;
+                const int col0 = chunk * kTileCodes;
+                const bool decided = valid && !cross && nhit == 1 && col0 + first < p.k;
+                const int code = decided ? col0 + first : -1;
+                if (fuse) {       // the other warps only need the decided rows: publish them before the near-tie bookkeeping
+                    mbar_wait(&bars.dec_empty[slot], use_par ^ 1u);
+                    dec_ring[slot * 128 + rq] = make_int4(code, row, e.z, 0);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars.dec_full[slot]);
+                    if (TRACE && p.trace != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0 && bi < 512u) p.trace[bi * 8 + 4] = clock64();
+                }
+                bool flagged = false, over = false;
+                auto list_to = [&](int* dst, int at) {                // append the hit columns at dst[at...] (capacity cand_cap)
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) {
+                        uint32_t m = msk[qq];
+                        while (m) {
+                            const int i = __ffs(m) - 1;
+                            m &= m - 1;
+                            if (at < p.cand_cap) dst[at] = col0 + 32 * qq + i;
+                            ++at;
+                        }
+                    }
+                };
+                if (valid && !decided) {
+                    int* dst = p.cand + (size_t)row * p.cand_cap;
+                    if (!cross) {
+                        if (nhit >= 2 && nhit <= p.cand_cap) {
+                            list_to(dst, 0);
+                            p.cand_cnt[row] = nhit;
+                            flagged = true;
+                        } else {                                      // too many near-ties: the COLLECT pass / exact scan decides
+                            flagged = true;                           // (best_val[row] still holds M from the GROUP pass)
+                            over = true;
+                        }
+                    } else {
+                        list_to(dst, atomicAdd(&p.cand_cnt[row], nhit));    // an overflowing list sends the row to the exact scan
+                        flagged = !second;
+                    }
+                }
+                const unsigned dall = __ballot_sync(0xffffffffu, decided);
+                if (decided) {
+                    p.idx_out[row] = (int64_t)code;
+                    const unsigned same = __match_any_sync(dall, code);
+                    if (lane == __ffs(same) - 1) atomicAdd(&p.bins[code], __popc(same));
+                }
+                const unsigned ball = __ballot_sync(0xffffffffu, flagged);
+                if (ball) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&p.counters[CNT_FLAGGED], __popc(ball));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (flagged) p.flag_rows[base + __popc(ball & ((1u << lane) - 1))] = row;
+                }
+                const unsigned oall = __ballot_sync(0xffffffffu, over);
+                if (oall) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&p.counters[CNT_OVER], __popc(oall));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (over) p.over_rows[base + __popc(oall & ((1u << lane) - 1))] = row;
+                }
+            }
+            named_bar_sync(1, 256);                                   // hit_s is rewritten by the next tile
+            if (fuse && bi >= 1u) sums(bi - 1u, chunk_prev, sbuf_prev);
+            chunk_prev = chunk;
+            sbuf_prev = sbuf;
+            sbuf = sbuf == kStageTiles - 1 ? 0 : sbuf + 1;
+        }
+        if (fuse) {
+            if (bi >= 1u) sums(bi - 1u, chunk_prev, sbuf_prev);
+            named_bar_sync(1, 256);
+            if (acc_chunk >= 0) flush(acc_chunk);
+        }
+    } else if (fuse) {
+        // ---------------------------------- ROWS ----------------------------------
+        double sse = 0.0;
+        uint32_t bi = 0;
+        int sbuf = 0;                                     // bi % kStageTiles
+        for (int item = item0; item < item_end; ++item, ++bi, sbuf = (sbuf == kStageTiles - 1 ? 0 : sbuf + 1)) {
+            const int slot = (int)(bi & 3u);
+            mbar_wait(&bars.dec_full[slot], (bi >> 2) & 1u);
+            const bool tr_f = TRACE && p.trace != nullptr && blockIdx.x == 0 && warp == 8 && lane == 0 && bi < 512u;
+            if (TRACE && tr_f) p.trace[bi * 8 + 5] = clock64();
+            const int4* dec = dec_ring + slot * 128;
+            unsigned char* stg_w = smem + OFF_STAGE + sbuf * kStageTileBytes;
+            // group g takes rows g, g + 16, ...; four codebook rows in flight at a time
+#pragma unroll 1
+            for (int t0 = 0; t0 < 8; t0 += 4) {
+                int4 de[4];
+                float4 c[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    de[u] = dec[g16 + 16 * (t0 + u)];
+                    c[u] = (lane_on && de[u].x >= 0) ? __ldg(reinterpret_cast<const float4*>(p.w + (size_t)de[u].x * d) + q)
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (lane_on && de[u].x >= 0) {
+                        float4* xp = reinterpret_cast<float4*>(stg_w + (g16 + 16 * (t0 + u)) * row_stride + q * 16);
+                        const float4 x = *xp;
+                        const float dn = __int_as_float(de[u].z);
+                        float4 zf;
+                        zf.x = __fdiv_rn(x.x, dn); zf.y = __fdiv_rn(x.y, dn); zf.z = __fdiv_rn(x.z, dn); zf.w = __fdiv_rn(x.w, dn);
+                        *xp = zf;
+                        const float d0 = __fsub_rn(c[u].x, zf.x), d1 = __fsub_rn(c[u].y, zf.y), d2 = __fsub_rn(c[u].z, zf.z),
+                                    d3 = __fsub_rn(c[u].w, zf.w);
+                        // the four squares of a lane are added in fp32 first (one widening per row and lane instead of four)
+                        sse += (double)__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)),
+                                                 __fadd_rn(__fmul_rn(d2, d2), __fmul_rn(d3, d3)));
+                        float4 o;
+                        o.x = __fadd_rn(zf.x, d0); o.y = __fadd_rn(zf.y, d1); o.z = __fadd_rn(zf.z, d2); o.w = __fadd_rn(zf.w, d3);
+                        __stcs(reinterpret_cast<float4*>(p.z_q + (size_t)de[u].y * d) + q, o);
+                    }
+                }
+            }
+            __syncwarp();
+            if (TRACE && tr_f) p.trace[bi * 8 + 6] = clock64();
+            if (lane == 0) { mbar_arrive(&bars.p1_full[slot]); mbar_arrive(&bars.dec_empty[slot]); }
+        }
+        sse = warp_sum(sse);
+        if (lane == 0 && sse != 0.0) atomicAdd(&p.stats[(size_t)p.k + (size_t)p.k * d], sse);
+    }
+}
+
 }  // namespace
 
 template <int RT, int MODE, int NTOP, bool DBG>
 __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    using SM = SmemMap<RT>;
+    using SM = SmemMap<RT, MODE == MODE_REFINE>;
     constexpr int kDataStages = SM::kStages;
+    constexpr int kRing = SM::kStages;
     constexpr int kOffA = SM::kOffA, kOffOnes = SM::kOffOnes, kOffBData = SM::kOffBData, kOffBBias = SM::kOffBBias;
     constexpr int kOffSlots = SM::kOffSlots, kOffState = SM::kOffState, kOffTmem = SM::kOffTmem;
     // thread id through a volatile read: ptxas otherwise re-derives warp/lane (S2R + shifts) inside the hot loops
@@ -387,13 +878,23 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
     }
     const int cps    = (nchunks + ksplit - 1) / ksplit;          // chunks per item (the last range may be shorter)
     const int nitems = nblocks * ksplit;
+    // REFINE walks the 128-entry tiles of the chunk-sorted entries.  A CTA takes a CONTIGUOUS range of tiles: it meets few
+    // different chunks, so its shared-memory per-code accumulators are flushed rarely.
+    int item0 = blockIdx.x, item_end = nitems, item_step = gridDim.x;
+    if (MODE == MODE_REFINE) {
+        const int nt = *p.n_tiles_dev;
+        const int per = (nt + (int)gridDim.x - 1) / (int)gridDim.x;
+        item0 = (int)blockIdx.x * per;
+        item_end = min(nt, item0 + per);
+        item_step = 1;
+    }
 
     // bias K-step (-||w||^2/2): needed unless every code has the same squared norm (then it is a constant
     // shift of all scores); padding codes rely on it to lose, so it stays on when K is not a tile multiple
     const bool use_bias = !(DBG && (p.debug_flags & 2)) &&
                           (MODE == MODE_DUMP || p.k != p.kpad || !(p.meta[META_SPREAD] <= kBiasSkipTol));
 
-    Bars bars = carve_bars<RT>(smem);
+    Bars bars = carve_bars<SM>(smem);
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kOffTmem);
 
     // ---- one-time setup ------------------------------------------------------------------------
@@ -406,6 +907,10 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
             mbar_init(&bars.a_empty[i], 4 / RT);     // one commit from each issuer that reads the tile
             mbar_init(&bars.acc_full[i], 1);
             mbar_init(&bars.acc_empty[i], 8);        // one elected lane per epilogue warp serving the slot
+            mbar_init(&bars.dec_full[i], 4);         // REFINE: the four deciding warps of the left column half
+            mbar_init(&bars.dec_empty[i], 8);        //         the eight finishing warps
+            mbar_init(&bars.p1_full[i], 8);
+            if (i < kStageTiles) mbar_init(&bars.stg_empty[i], 8);
         }
         fence_mbar_init();
     }
@@ -444,6 +949,9 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
 
     // ============================================================================================
     if (warp < kEpiWarps) {
+      if constexpr (MODE == MODE_REFINE) {
+        refine_epilogue<SM::kOffSlots, SM::kOffAcc, SM::kOffStage, DBG>(p, smem, bars, tmem_base, warp, lane, item0, item_end);
+      } else {
         // ---------------------------------- EPILOGUE --------------------------------------------
         constexpr int NS = (RT == 4) ? 2 : 1;       // row tiles (state sets) per thread
         constexpr int NLIST = (MODE == MODE_TOPK) ? kTopSlots : NTOP;   // TOPK: NTOP is the static k (5) or 8 = runtime k
@@ -483,7 +991,12 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                                                              : make_float4(-INFINITY, 0.f, 0.f, 0.f);
             named_bar_sync((RT == 1) ? 1 : 1 + pair, (RT == 1) ? 512 : 256);
         }
-        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        int* hist_s = reinterpret_cast<int*>(smem + kOffSlots);   // GROUP: this CTA's sorted entries per chunk
+        if (MODE == MODE_GROUP) {
+            for (int i = (int)tid_x; i < nchunks; i += kEpiWarps * 32) hist_s[i] = 0;
+            named_bar_sync(5, kEpiWarps * 32);
+        }
+        for (int item = item0; item < item_end; item += item_step) {
             const int blk = (MODE == MODE_COLLECT) ? item / ksplit : item;
             const int cbeg = (MODE == MODE_COLLECT) ? (item - blk * ksplit) * cps : 0;
             const int cend = min(nchunks, cbeg + cps);
@@ -533,6 +1046,8 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                     if (MODE == MODE_ARGMAX) {
                         consume_argmax64<NLIST, SM::kRec>(va, vb, c * 4 + half2, st[ss], margin, slots, ss * 512 + rec0,
                                                 &state[ss * 512 + rec0].x, &state[ss * 512 + (rec0 ^ 128)].x);
+                    } else if (MODE == MODE_GROUP) {
+                        consume_group<NLIST>(va, vb, c, st[ss]);
                     } else if (MODE == MODE_TOPK) {
                         if constexpr (NLIST == kTopSlots) {
                             constexpr int KS = (NTOP == 5) ? 5 : 0;
@@ -651,6 +1166,67 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                     }
                 }
                 named_bar_sync(bar_id, bar_n);
+            } else if (MODE == MODE_GROUP) {
+#pragma unroll
+                for (int ss = 0; ss < NS; ++ss)
+                    state[ss * 512 + rec0] = make_float4(st[ss].m1, st[ss].m2,
+                                                         __int_as_float(st[ss].best_chunk | (st[ss].chunk2 << 16)), st[ss].m3);
+                named_bar_sync(bar_id, bar_n);
+                if (leader) {
+#pragma unroll
+                    for (int ss = 0; ss < NS; ++ss) {
+                        // the row's best chunk, and every OTHER chunk holding a 64-column group within the margin of the best
+                        float M = -INFINITY;
+                        int cb = 0;
+#pragma unroll
+                        for (int pp = 0; pp < NP; ++pp)
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh) {
+                                const int w2 = quarter + 4 * hh + 8 * ((RT == 1) ? pp : pair);
+                                const float4 sv = state[ss * 512 + w2 * 32 + lane];
+                                if (sv.x > M) { M = sv.x; cb = __float_as_int(sv.z) & 0xffff; }
+                            }
+                        const float thrF = M - margin;
+                        int other = -1;
+                        bool unknown = !(M > -INFINITY);          // no finite score (NaN row): the exact scan decides
+#pragma unroll
+                        for (int pp = 0; pp < NP; ++pp)
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh) {
+                                const int w2 = quarter + 4 * hh + 8 * ((RT == 1) ? pp : pair);
+                                const float4 sv = state[ss * 512 + w2 * 32 + lane];
+                                const int c1 = __float_as_int(sv.z) & 0xffff, c2 = (int)((unsigned)__float_as_int(sv.z) >> 16);
+                                if (sv.w >= thrF) unknown = true;            // a group known only by its maximum
+                                if (sv.x >= thrF && c1 != cb) { if (other < 0 || other == c1) other = c1; else unknown = true; }
+                                if (sv.y >= thrF && c2 != cb) { if (other < 0 || other == c2) other = c2; else unknown = true; }
+                            }
+                        const bool valid = st[ss].valid;
+                        if (valid) {
+                            p.best_val[st[ss].row] = M;
+                            p.grp[st[ss].row] = cb | ((other < 0 ? 0 : other) << kGrpOtherShift) |
+                                                ((other >= 0 && !unknown) ? kGrpCrossBit : 0) | (unknown ? kGrpOverBit : 0);
+                            if (!unknown) {
+                                atomicAdd(&hist_s[cb], 1);
+                                if (other >= 0) atomicAdd(&hist_s[other], 1);
+                            }
+                        }
+                        // three or more chunks within the margin (or nothing finite): flagged + COLLECT, like ARGMAX's overflow
+                        const bool over = valid && unknown;
+                        const unsigned oall = __ballot_sync(0xffffffffu, over);
+                        if (oall) {
+                            int base = 0, base2 = 0;
+                            if (lane == 0) {
+                                base = atomicAdd(&p.counters[CNT_FLAGGED], __popc(oall));
+                                base2 = atomicAdd(&p.counters[CNT_OVER], __popc(oall));
+                            }
+                            base = __shfl_sync(0xffffffffu, base, 0);
+                            base2 = __shfl_sync(0xffffffffu, base2, 0);
+                            const int at = __popc(oall & ((1u << lane) - 1));
+                            if (over) { p.flag_rows[base + at] = (int)st[ss].row; p.over_rows[base2 + at] = (int)st[ss].row; }
+                        }
+                    }
+                }
+                named_bar_sync(bar_id, bar_n);
             } else if (MODE == MODE_TOPK) {
                 if constexpr (NLIST == kTopSlots) {
                 float* tl = reinterpret_cast<float*>(smem + SM::kOffSlots + 2 * kTopSlots * SM::kRec);   // [record][8], after the ids
@@ -758,6 +1334,16 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                 named_bar_sync(bar_id, bar_n);
             }
         }
+        if (MODE == MODE_GROUP) {      // the CTA's histogram goes to the global one (every row block has been counted)
+            named_bar_sync(5, kEpiWarps * 32);
+            for (int i = (int)tid_x; i < nchunks; i += kEpiWarps * 32) {
+                const int h = hist_s[i];
+                if (h) atomicAdd(&p.ghist[i], h);
+            }
+        }
+      }
+    } else if (MODE == MODE_REFINE && warp < kLoadWarp0 + kLoadWarps) {
+        if constexpr (MODE == MODE_REFINE) refine_loader<SM, DBG>(p, smem, bars, (int)tid_x - kLoadWarp0 * 32, lane, item0, item_end);
     } else if (warp < kLoadWarp0 + kLoadWarps) {
         // ---------------------------------- A LOADER --------------------------------------------
         // one thread per row.  The exact reference-order norm goes to `denom` (later kernels divide by
@@ -765,7 +1351,7 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
         // produced with one reciprocal and a multiply per element instead of an IEEE division.
         const int r = (int)tid_x - kLoadWarp0 * 32;
         uint32_t bi = 0;
-        for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++bi) {
+        for (int item = item0; item < item_end; item += item_step, ++bi) {
             const int blk = (MODE == MODE_COLLECT) ? item / ksplit : item;
             const bool skip = DBG && (p.debug_flags & 4) && bi > 0;   // timing experiment only
             for (int g = 0; g < RT; ++g) {
@@ -839,15 +1425,19 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                 if (lane == 0) mbar_arrive(&bars.a_full[areg]);
             }
         }
+    } else if (MODE == MODE_REFINE && warp == kProdWarp) {
+        if constexpr (MODE == MODE_REFINE) { if (elect_one()) refine_producer<SM>(p, smem, bars, item0, item_end, use_bias); }
+    } else if (MODE == MODE_REFINE && warp >= kMmaWarp) {
+        if constexpr (MODE == MODE_REFINE) { if (elect_one()) refine_issuer<SM>(p, smem, bars, tmem_base, warp - kMmaWarp, item0, item_end, use_bias); }
     } else if (warp == kProdWarp) {
         // ---------------------------------- B PRODUCER ------------------------------------------
         if (elect_one()) {
             const unsigned char* img = static_cast<const unsigned char*>(p.b_image);
             uint32_t itB = 0;
             uint32_t st = 0, ph = 0;      // ring position and phase, advanced per K-block (the ring need not be a power of 2)
-            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-                const int cbeg = (MODE == MODE_COLLECT) ? (item % ksplit) * cps : 0;
-                const int cend = min(nchunks, cbeg + cps);
+            for (int item = item0; item < item_end; item += item_step) {
+                int cbeg = (MODE == MODE_COLLECT) ? (item % ksplit) * cps : 0;
+                int cend = min(nchunks, cbeg + cps);
                 for (int c = cbeg; c < cend; ++c) {
                     const unsigned char* tile = img + (size_t)c * tile_b;
                     for (int kb = 0; kb < nkblk; ++kb) {
@@ -856,7 +1446,7 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                         mbar_arrive_expect_tx(&bars.bd_full[st], bytes);
                         bulk_g2s(smem + kOffBData + st * kKblkBytes, tile + (size_t)kb * kKblkBytes, bytes,
                                  &bars.bd_full[st]);
-                        if (++st == (uint32_t)kDataStages) { st = 0; ph ^= 1; }
+                        if (++st == (uint32_t)kRing) { st = 0; ph ^= 1; }
                     }
                     if (use_bias) {
                         const int sb = itB % kBiasStages;
@@ -890,7 +1480,7 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
             uint32_t chunk0 = 0;                     // chunks issued by the CTA before this block
             const bool tracing = DBG && (p.trace != nullptr) && blockIdx.x == 0 && j == 0;
             int cbeg = 0, cend = nchunks;
-            for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++bi, chunk0 += (uint32_t)(cend - cbeg)) {
+            for (int item = item0; item < item_end; item += item_step, ++bi, chunk0 += (uint32_t)(cend - cbeg)) {
                 if (MODE == MODE_COLLECT) { cbeg = (item % ksplit) * cps; cend = min(nchunks, cbeg + cps); }
                 // Every issuer walks EVERY chunk so that each shared barrier sees all four issuers once per
                 // phase (an mbarrier parity wait is only meaningful within one phase of the barrier);
@@ -904,7 +1494,7 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                     const uint32_t sb = gc % kBiasStages;
                     // this chunk's K-blocks occupy ring positions dst0, dst0 + 1, ... (wrapping, phase flips at the wrap)
                     const uint32_t cst = dst0, cph = dph0;
-                    auto next_stage = [&](uint32_t& st_, uint32_t& ph_) { if (++st_ == (uint32_t)kDataStages) { st_ = 0; ph_ ^= 1; } };
+                    auto next_stage = [&](uint32_t& st_, uint32_t& ph_) { if (++st_ == (uint32_t)kRing) { st_ = 0; ph_ ^= 1; } };
                     // operands first, accumulator last: when the epilogue hands the slot back, every MMA of
                     // the tile is issued back to back
                     {
@@ -968,14 +1558,15 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
 template <int RT, int MODE, int NTOP, bool DBG>
 static cudaError_t launch_one(const CoarseParams& p, int grid, cudaStream_t stream) {
     auto kern = coarse_kernel<RT, MODE, NTOP, DBG>;
+    using SM = SmemMap<RT, MODE == MODE_REFINE>;
     static PerDeviceOnce once;         // one per instantiation and device
     bool& configured = once.flag();
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemMap<RT>::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kSmemBytes);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    kern<<<grid, kThreads, SmemMap<RT>::kSmemBytes, stream>>>(p);
+    kern<<<grid, kThreads, SM::kSmemBytes, stream>>>(p);
     ++g_kernel_launches;
     return cudaGetLastError();
 }
@@ -999,6 +1590,10 @@ cudaError_t launch_coarse(const CoarseParams& p, int mode, int row_tiles, int nu
     if (mode == MODE_TOPK && (num_sms > kTopkMaxCtas || p.topk_scratch == nullptr)) return cudaErrorInvalidValue;
     // timing knobs / pipeline trace live in a separate instantiation so that the production kernels carry none of it
     const bool dbg = (mode == MODE_ARGMAX) && (p.trace != nullptr || p.debug_flags != 0);
+    if (mode == MODE_GROUP) return row_tiles == 4 ? launch_one<4, MODE_GROUP, 5, false>(p, num_sms, stream) : cudaErrorInvalidValue;
+    if (mode == MODE_REFINE)
+        return p.trace != nullptr ? launch_one<1, MODE_REFINE, 5, true>(p, num_sms, stream)
+                                  : launch_one<1, MODE_REFINE, 5, false>(p, num_sms, stream);
 #define MTVQ_CASE(RT_, MODE_, NTOP_)                                                                   \
     if (row_tiles == RT_ && mode == MODE_ && ntop == NTOP_) {                                           \
         if (MODE_ == MODE_ARGMAX && dbg) return launch_one<RT_, MODE_ARGMAX, 5, true>(p, num_sms, stream); \
@@ -1020,6 +1615,9 @@ cudaError_t launch_coarse(const CoarseParams& p, int mode, int row_tiles, int nu
     return cudaErrorInvalidValue;
 }
 
-int coarse_smem_bytes() { return SmemMap<4>::kSmemBytes > SmemMap<1>::kSmemBytes ? SmemMap<4>::kSmemBytes : SmemMap<1>::kSmemBytes; }
+int coarse_smem_bytes() {
+    int m = SmemMap<4>::kSmemBytes > SmemMap<1>::kSmemBytes ? SmemMap<4>::kSmemBytes : SmemMap<1>::kSmemBytes;
+    return m > SmemMap<1, true>::kSmemBytes ? m : SmemMap<1, true>::kSmemBytes;
+}
 
 }  // namespace mtvq

@@ -7,7 +7,20 @@
 
 namespace mtvq {
 
-enum CoarseMode { MODE_ARGMAX = 0, MODE_THRESH = 1, MODE_COLLECT = 2, MODE_DUMP = 3, MODE_TOPK = 4 };
+enum CoarseMode { MODE_ARGMAX = 0, MODE_THRESH = 1, MODE_COLLECT = 2, MODE_DUMP = 3, MODE_TOPK = 4, MODE_GROUP = 5, MODE_REFINE = 6 };
+
+// Two-pass hard route (D <= 64, large batches).  MODE_GROUP is the tensor pass with a
+// branch-free epilogue: per row only the best 128-code chunk (its maximum, and whether another chunk comes within the
+// margin) -- no score records.  The rows are then counting-sorted by chunk (group.cu) and MODE_REFINE re-scores every
+// 128-row tile of the sorted order against its ONE chunk: it decides the column, lists near-ties for the exact
+// re-scoring, and -- fused -- writes z_q, the squared error and the per-code sums of the decided rows.
+constexpr int kGroupMaxChunks = 8192;      // chunk ids are packed into 14 bits; the per-CTA histogram lives in 32 KB
+constexpr int kGrpOtherShift  = 14;
+constexpr int kGrpCrossBit    = 1 << 28;   // a second chunk is within the margin (the row is listed under both)
+constexpr int kGrpOverBit     = 1 << 29;   // three or more chunks (or no finite score): COLLECT pass decides
+constexpr unsigned kEntCross  = 1u << 31;  // sorted entry {row | flags, best coarse score, row norm, 0} (16 bytes)
+constexpr unsigned kEntSecond = 1u << 30;
+constexpr unsigned kEntRowMask = (1u << 30) - 1;
 
 // MODE_TOPK keeps the fp16 scores of every thread's best granules in an L2-resident scratch: per CTA 8 slots x 4 x
 // 1024 records x 16 B
@@ -46,6 +59,16 @@ struct CoarseParams {
     // shared-memory descriptor strides (kept as parameters so tests can probe the encoding)
     uint32_t     lbo_bytes;  // 2048
     uint32_t     sbo_bytes;  // 128
+    // two-pass hard route
+    int*         grp;         // GROUP out [n]: best chunk | other chunk << 14 | kGrpCrossBit | kGrpOverBit
+    int*         ghist;       // GROUP out [kpad / 128]: sorted entries per chunk (zeroed by the caller)
+    const int4*  entries;     // REFINE in: entries sorted by chunk {row | flags, best coarse score, row norm, 0}
+    const int2*  tile_tab;    // REFINE in: per 128-entry tile {chunk | count << 16, first entry}
+    const int*   n_tiles_dev; // REFINE in: number of tiles
+    const float* w;           // REFINE, fused rows: fp32 codebook [k, d]
+    float*       z_q;         //         straight-through output rows [n, d]
+    double*      stats;       //         packed statistics (bins [k] | embed_sum [k, d] | sse | rows)
+    int          fuse_rows;   //         0 = decide only, 1 = also gather / STE / SSE / per-code sums of the decided rows
     long long*   trace;       // optional clock64 trace of slot 0 of CTA 0 (mtvq_debug_set_trace), 8 x int64 per tile
     int          debug_flags; // timing experiments only (MTVQ_DBG): 1 = epilogue does no work, 2 = no bias K-step,
                               // 4 = A tiles loaded once per CTA; results are wrong when set

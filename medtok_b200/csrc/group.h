@@ -1,0 +1,19 @@
+// group.h -- glue kernels of the two-pass hard route (group.cu)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "workspace.h"
+
+namespace mtvq {
+
+// ws.ghist (entries per chunk, from the GROUP pass) -> ws.goff / ws.gcur / ws.gtile, the tile table and
+// counters[CNT_TILES]; then ws.grp / ws.best_val / denom (the row norms the GROUP pass wrote) -> ws.entries sorted by chunk
+cudaError_t launch_group_sort(const Workspace& ws, const float* denom, int64_t n, int k, int num_sms, cudaStream_t s);
+
+// z_q / squared error / per-code sums of the near-tie rows (ws.flag_rows, decided by the exact re-scoring), and the
+// counts of the packed statistics (stats[c] += bins[c], rows += n)
+cudaError_t launch_finish_flagged(const float* z, const float* denom, const float* w, const int64_t* idx, int64_t n, int d,
+                                  int k, float* z_q, double* stats, const Workspace& ws, int num_sms, cudaStream_t s);
+
+}  // namespace mtvq

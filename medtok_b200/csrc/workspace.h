@@ -13,7 +13,7 @@ enum MetaSlot { META_MARGIN = 0, META_EPS = 1, META_MAXNORM = 2, META_SPREAD = 3
 // the -||w||^2/2 K-step is skipped when max_k | ||w_k||^2 - ||w_0||^2 | / 2 <= kBiasSkipTol (eps carries the slack)
 constexpr float kBiasSkipTol = 1.0e-6f;
 // counters (ints), zeroed at the start of every assign
-enum Counter { CNT_FLAGGED = 0, CNT_FULL = 1, CNT_CANDS = 2, CNT_LAUNCHES = 3, CNT_OVER = 4, CNT_COUNT = 8 };
+enum Counter { CNT_FLAGGED = 0, CNT_FULL = 1, CNT_CANDS = 2, CNT_LAUNCHES = 3, CNT_OVER = 4, CNT_TILES = 5, CNT_COUNT = 8 };
 
 // cudaFuncSetAttribute applies to the current device only: "configured once" flags are kept per device (a host may
 // drive several GPUs from one process, even though the module layer uses one process per GPU)
@@ -50,6 +50,14 @@ struct Workspace {
     int*     offsets;      // [k+1]
     int*     cursor;       // [k]
     int*     perm;         // [n]
+    // two-pass hard route (assign_tc.h MODE_GROUP / MODE_REFINE, group.cu)
+    int*     grp;          // [n]            per-row chunk word of the GROUP pass
+    int*     ghist;        // [kpad / 128]   entries per chunk | first entry | scatter cursor | first tile
+    int*     goff;
+    int*     gcur;
+    int*     gtile;
+    void*    entries;      // [2 n] int4     rows sorted by chunk (a near-tie row spanning two chunks is listed twice)
+    void*    tile_tab;     // [group_tile_capacity] int2
     size_t   total_bytes;
 };
 
@@ -57,6 +65,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline int    pad_codes(int k) { return (int)align_up((size_t)k, 128); }
 // near-tie candidates kept per row before the row falls back to the full exact scan
 inline int    cand_capacity(bool soft) { return soft ? 24 : 16; }
+inline size_t group_tile_capacity(int64_t n, int k) { return (size_t)(2 * n / 128) + (size_t)(pad_codes(k) / 128) + 2; }
 inline size_t image_bytes(int d, int k) { return (size_t)(pad_codes(k) / 128) * (size_t)(d / 8 + 2) * 2048; }
 
 // Small-batch route (small.cu): work bound below which scoring every (row, code) pair exactly on the CUDA cores beats the
@@ -107,6 +116,14 @@ inline Workspace carve(void* base, int64_t n, int d, int k, int topk) {
     w.codes_n   = (float*)take(soft ? sizeof(float) * (size_t)k * d : 0);
     w.topk_scratch = take(soft ? (size_t)160 * (8 * 4 * 1024 * 16) : 0);   // kTopkMaxCtas x kTopkScratchPerCta
     w.small_part = take(small_route_fits(n, d, k) ? small_scratch_bytes(n, d, k, soft ? topk : 1) : 0);
+    const size_t nchunks = (size_t)kpad / 128;
+    w.grp       = (int*)take(sizeof(int) * n);
+    w.ghist     = (int*)take(sizeof(int) * nchunks);
+    w.goff      = (int*)take(sizeof(int) * nchunks);
+    w.gcur      = (int*)take(sizeof(int) * nchunks);
+    w.gtile     = (int*)take(sizeof(int) * (nchunks + 1));
+    w.entries   = take(16 * (size_t)(2 * n));
+    w.tile_tab  = take(8 * group_tile_capacity(n, k));
     w.total_bytes = off;
     return w;
 }
