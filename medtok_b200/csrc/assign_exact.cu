@@ -6,6 +6,7 @@
 // Every distance here is fl(fl(zz + cc) - 2*dot) with dot a sequential fmaf chain over d, i.e. bit-for-bit
 // what the reference's CPU path computes (norm_ema_quantizer.py:175-179).
 #include "assign_exact.h"
+#include "assign_tc.h"
 #include "common.cuh"
 
 namespace mtvq {
@@ -152,7 +153,11 @@ __global__ void __launch_bounds__(kResWarps * 32, 4) resolve_kernel(
     int ncands = 0;
     for (int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < nflag; p += nwarps) {
         const int row = flag_rows[p];
-        const int cnt = cand_cnt[row];            // candidate lists are indexed by row
+        // candidate lists are indexed by row; the count word has two fields (assign_tc.h kCandBackShift): columns listed
+        // from the front of the list and -- second tile of a row listed under two chunks by the REFINE pass -- from its back
+        const unsigned cw = (unsigned)cand_cnt[row];
+        const int nfront = (int)(cw & ((1u << kCandBackShift) - 1u)), nback = (int)(cw >> kCandBackShift);
+        const int cnt = nfront + nback;
         if (cnt <= 0 || cnt > cand_cap) {
             if (lane == 0) full_rows[atomicAdd(&counters[CNT_FULL], 1)] = row;
             continue;
@@ -201,7 +206,8 @@ __global__ void __launch_bounds__(kResWarps * 32, 4) resolve_kernel(
         if (dots) zz = 0.0f;
         float best = 0.0f;
         int bcol = 0x7fffffff;
-        const int mine = lane < cnt ? cand[(size_t)row * cand_cap + lane] : 0x7fffffff;   // cand_cap <= 32
+        const int mine = lane < cnt ? cand[(size_t)row * cand_cap + (lane < nfront ? lane : cand_cap - 1 - (lane - nfront))]
+                                    : 0x7fffffff;                                          // cand_cap <= 32
         // single columns: lane j scores entry j
         if (lane < cnt && mine >= 0 && mine < k) {
             const float4* wr = reinterpret_cast<const float4*>(w + (size_t)mine * d);

@@ -76,7 +76,7 @@ struct SmemMap {
     static constexpr int kOffSlots = kOffBBias + kBiasStages * kBiasBytes;   // 4 chunks x kRec records x 16 B (fp16 granules)
     static constexpr int kOffState = kOffSlots + 4 * kRec * 16;              // kRec records x 16 B
     static constexpr int kOffBars  = kOffState + kRec * 16;
-    static constexpr int kNumBars  = 2 * kStages + 2 * kBiasStages + 4 + 4 + 4 + 4 + 8 + 3 + 4;
+    static constexpr int kNumBars  = 2 * kStages + 2 * kBiasStages + 4 + 4 + 4 + 4 + 8 + 3 + 4 + 3 + 4;
     static constexpr int kOffTmem  = kOffBars + kNumBars * 8;
     static constexpr int kSmemBytes = kOffTmem + 16;
     static constexpr int kOffAcc = 0, kOffStage = 0;                      // REFINE only
@@ -103,7 +103,7 @@ struct SmemMap<1, true> {
     static constexpr int kOffAcc   = kOffState;                          // double [128][d]
     static constexpr int kOffStage = kOffAcc + kTileCodes * 64 * 8;
     static constexpr int kOffBars  = kOffStage + kStageTiles * kStageTileBytes;
-    static constexpr int kNumBars  = 2 * kStages + 2 * kBiasStages + 4 + 4 + 4 + 4 + 8 + 3 + 4;
+    static constexpr int kNumBars  = 2 * kStages + 2 * kBiasStages + 4 + 4 + 4 + 4 + 8 + 3 + 4 + 3 + 4;
     static constexpr int kOffTmem  = kOffBars + kNumBars * 8;
     static constexpr int kSmemBytes = kOffTmem + 16;
     static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
@@ -121,6 +121,8 @@ struct Bars {
     uint64_t* dec_full;  // [4]  REFINE: a tile's decisions are in the ring (deciders -> finishers)
     uint64_t* dec_empty; // [4]
     uint64_t* p1_full;   // [4]  REFINE: the ROWS half has left a tile's zf in the staging tile (-> SUMS)
+    uint64_t* sort_full; // [4]  REFINE: a tile's decided rows are listed in code order (-> SUMS)
+    uint64_t* landed;    // [3]  REFINE: a staging tile's cp.async copies have landed (copy warps -> convert warps)
     uint64_t* stg_empty; // [3]  REFINE: the finishers are done with a staging tile (-> loader)
 };
 
@@ -139,6 +141,8 @@ __device__ __forceinline__ Bars carve_bars(unsigned char* smem) {
     r.dec_full = b;                b += 4;
     r.dec_empty = b;               b += 4;
     r.p1_full = b;                 b += 4;
+    r.sort_full = b;               b += 4;
+    r.landed = b;                  b += 3;
     r.stg_empty = b;
     return r;
 }
@@ -397,89 +401,112 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 // ------------------------------------------------------------------------------------------------
 // REFINE loader: the rows of a tile are scattered over z (the tile is 128 entries of the chunk-sorted order), so a
-// row-per-thread loader would expose a DRAM round trip per tile.  Here the 16 lanes of a group copy whole 4 d-byte rows
-// global -> shared with cp.async (no registers held, two tiles in flight), and only then does thread r turn row r into
-// the fp16 operand planes -- the same values the GROUP pass fed to the tensor cores: x * rcp(norm), norm from the entry.
+// row-per-thread loader would expose a DRAM round trip per tile.  Two of the four loader warps COPY: the 16 lanes of a
+// group move whole 4 d-byte rows global -> shared with cp.async (no registers held; up to three tiles in flight, a
+// staging tile being refilled as soon as the epilogue is done with its rows) and signal the tile's mbarrier when their
+// copies have landed.  The other two CONVERT: thread c turns rows c and c + 64 into the fp16 operand planes -- the same
+// values the GROUP pass fed to the tensor cores: x * rcp(norm), norm from the entry.  The copies never wait for the
+// conversion and the conversion never waits for a staging tile to be released.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 template <class SM, bool TRACE>
 __device__ __forceinline__ void refine_loader(const CoarseParams& p, unsigned char* smem, const Bars& bars, int r, int lane,
                                               int item0, int item_end) {
     // pipeline trace (mtvq_debug_set_trace, CTA 0): per tile [0] copies issued, [1] landed, [2] operand tile published,
-    // [3] deciders saw the accumulator, [4] decisions published, [5] finishers saw them, [6] ownership scan done, [7] tile finished
-    const bool tracing = TRACE && p.trace != nullptr && blockIdx.x == 0 && r == 0;
+    // [3] deciders saw the accumulator, [4] decisions published, [5] ROWS saw them, [6] ROWS done, [7] SUMS done
     const int d = p.d, vpr = d >> 2, nplanes = d >> 3;
     const int row_stride = 4 * d + 16;
-    const int g = r >> 4, q = r & 15;
     unsigned char* stage = smem + SM::kOffStage;
-    // copies of tile `item` into staging buffer `buf`; returns the entry of row r (norm, validity) for the conversion
-    auto issue = [&](int item, int buf) -> int4 {
-        int4 e = make_int4(-1, 0, 0x3f800000, 0);
-        if (item < item_end) {
+    const bool fuse = p.fuse_rows != 0;
+    if (r < 64) {
+        // ---------------------------------- COPY ----------------------------------
+        const bool tracing = TRACE && p.trace != nullptr && blockIdx.x == 0 && r == 0;
+        const int g = r >> 4, q = r & 15;                // group g copies rows g, g + 4, ... (32 rows per tile)
+        uint32_t bi = 0;
+        int buf = 0;                                     // bi % kStageTiles
+        for (int item = item0; item < item_end; ++item, ++bi, buf = (buf == kStageTiles - 1 ? 0 : buf + 1)) {
             const int2 tt = __ldg(&p.tile_tab[item]);
             const int cnt = tt.x >> 16;
-            if (r < cnt) e = __ldg(&p.entries[tt.y + r]);
+            // lane q knows the rows g + 4 q and g + 4 (q + 16) of the tile
+            const int ra = g + 4 * q, rb = ra + 64;
+            const int ea = ra < cnt ? __ldg(&p.entries[tt.y + ra]).x : -1;
+            const int eb = rb < cnt ? __ldg(&p.entries[tt.y + rb]).x : -1;
+            // the staging tile held tile bi - 3: with fused rows the epilogue reads the fp32 rows there (z makes one trip
+            // from HBM), so it is refilled only once the SUMS step is done with it
+            if (fuse && bi >= (uint32_t)kStageTiles) mbar_wait_backoff(&bars.stg_empty[buf], (((bi / kStageTiles) & 1u) ^ 1u), 100);
+            // without fused rows: once the conversion of tile bi - 3 has been published (its MMAs need tile bi - 2's turn)
+            if (!fuse && bi >= (uint32_t)kStageTiles) mbar_wait_backoff(&bars.a_empty[0], ((bi - kStageTiles) & 1u), 100);
             unsigned char* st = stage + buf * kStageTileBytes;
 #pragma unroll 4
-            for (int i = 0; i < 16; ++i) {
-                const int ex = __shfl_sync(0xffffffffu, e.x, (lane & 16) + i);      // entry of row g * 16 + i
-                const int rr = g * 16 + i;
+            for (int i = 0; i < 32; ++i) {
+                const int ex = __shfl_sync(0xffffffffu, i < 16 ? ea : eb, (lane & 16) + (i & 15));
+                const int rr = g + 4 * i;
                 if (ex != -1 && q < vpr)
                     cp_async16(st + rr * row_stride + q * 16, p.z + (size_t)((unsigned)ex & kEntRowMask) * d + 4 * q);
             }
+            cp_async_mbar_arrive_noinc(&bars.landed[buf]);
+            if (TRACE && tracing && bi < 256u) p.trace[bi * 8 + 0] = clock64();
         }
-        cp_async_commit();
-        return e;
-    };
-    const bool fuse = p.fuse_rows != 0;
-    int4 e = issue(item0, 0);
-    if (TRACE && tracing) p.trace[0] = clock64();
-    int4 e1 = issue(item0 + 1, 1);
-    uint32_t bi = 0;
-    int buf = 0;                                         // bi % kStageTiles
-    for (int item = item0; item < item_end; ++item, ++bi) {
-        cp_async_wait<1>();                              // this thread's copies of tile bi have landed ...
-        named_bar_sync(6, kLoadWarps * 32);              // ... and everybody else's
-        if (TRACE && tracing && bi < 512u) p.trace[bi * 8 + 1] = clock64();
-        const bool valid = e.x != -1;
-        const float rden = __frcp_rn(__int_as_float(e.z));
-        const float4* src = reinterpret_cast<const float4*>(stage + buf * kStageTileBytes + r * row_stride);
-        uint4 pk[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            pk[j] = make_uint4(0, 0, 0, 0);
-            if (valid && j < nplanes) {
-                const float4 x0 = src[2 * j], x1 = src[2 * j + 1];
-                __half2 h0 = __floats2half2_rn(x0.x * rden, x0.y * rden);
-                __half2 h1 = __floats2half2_rn(x0.z * rden, x0.w * rden);
-                __half2 h2 = __floats2half2_rn(x1.x * rden, x1.y * rden);
-                __half2 h3 = __floats2half2_rn(x1.z * rden, x1.w * rden);
-                pk[j].x = *reinterpret_cast<uint32_t*>(&h0);
-                pk[j].y = *reinterpret_cast<uint32_t*>(&h1);
-                pk[j].z = *reinterpret_cast<uint32_t*>(&h2);
-                pk[j].w = *reinterpret_cast<uint32_t*>(&h3);
+        cp_async_wait<0>();
+    } else {
+        // ---------------------------------- CONVERT ----------------------------------
+        const int c = r - 64;
+        const bool tracing = TRACE && p.trace != nullptr && blockIdx.x == 0 && c == 0;
+        auto fetch = [&](int item, int4& e0, int4& e1) {
+            e0 = e1 = make_int4(-1, 0, 0x3f800000, 0);
+            if (item < item_end) {
+                const int2 tt = __ldg(&p.tile_tab[item]);
+                const int cnt = tt.x >> 16;
+                if (c < cnt) e0 = __ldg(&p.entries[tt.y + c]);
+                if (c + 64 < cnt) e1 = __ldg(&p.entries[tt.y + c + 64]);
             }
-        }
-        unsigned char* tile = smem + SM::kOffA + r * 16;
-        mbar_wait_backoff(&bars.a_empty[0], (bi & 1u) ^ 1u, 100);      // the previous tile's MMAs have read the operand tile
+        };
+        int4 e0, e1;
+        fetch(item0, e0, e1);
+        uint32_t bi = 0;
+        int buf = 0;
+        for (int item = item0; item < item_end; ++item, ++bi, buf = (buf == kStageTiles - 1 ? 0 : buf + 1)) {
+            const int4 c0 = e0, c1 = e1;
+            fetch(item + 1, e0, e1);                      // the next tile's norms arrive while this one is converted
+            mbar_wait(&bars.landed[buf], (bi / kStageTiles) & 1u);
+            if (TRACE && tracing && bi < 256u) p.trace[bi * 8 + 1] = clock64();
+            mbar_wait_backoff(&bars.a_empty[0], (bi & 1u) ^ 1u, 100);      // the previous tile's MMAs have read the operand tile
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                const int4 e = h ? c1 : c0;
+                const int row = c + 64 * h;
+                const bool valid = e.x != -1;
+                const float rden = __frcp_rn(__int_as_float(e.z));
+                const float4* src = reinterpret_cast<const float4*>(stage + buf * kStageTileBytes + row * row_stride);
+                unsigned char* tile = smem + SM::kOffA + row * 16;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (j < nplanes) *reinterpret_cast<uint4*>(tile + j * kPlaneBytes) = pk[j];
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars.a_full[0]);
-        if (TRACE && tracing && bi < 512u) p.trace[bi * 8 + 2] = clock64();
-        // Tile bi + 2 goes into the staging tile that held tile bi - 1: every loader thread has converted its row of it
-        // (the barrier above), and with fused rows the finishing warps -- they read the fp32 rows there, so z makes one
-        // trip from HBM -- must be done with it too.  Waiting HERE, after tile bi has been handed to the tensor pipe, keeps
-        // the staging tiles' chains (copy -> convert -> MMA -> decide -> finish) interleaved.
-        const int nbuf = buf == 0 ? kStageTiles - 1 : buf - 1;          // (bi + 2) % 3
-        if (fuse && bi >= 1u) mbar_wait_backoff(&bars.stg_empty[nbuf], (((bi + 2u) / kStageTiles) & 1u) ^ 1u, 100);
-        e = e1;
-        e1 = issue(item + 2, nbuf);
-        if (TRACE && tracing && bi + 2u < 512u) p.trace[(bi + 2u) * 8 + 0] = clock64();
-        buf = buf == kStageTiles - 1 ? 0 : buf + 1;
+                for (int j = 0; j < 8; ++j) {
+                    if (j < nplanes) {
+                        uint4 pk = make_uint4(0, 0, 0, 0);
+                        if (valid) {
+                            const float4 x0 = src[2 * j], x1 = src[2 * j + 1];
+                            __half2 h0 = __floats2half2_rn(x0.x * rden, x0.y * rden);
+                            __half2 h1 = __floats2half2_rn(x0.z * rden, x0.w * rden);
+                            __half2 h2 = __floats2half2_rn(x1.x * rden, x1.y * rden);
+                            __half2 h3 = __floats2half2_rn(x1.z * rden, x1.w * rden);
+                            pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                            pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                            pk.z = *reinterpret_cast<uint32_t*>(&h2);
+                            pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                        }
+                        *reinterpret_cast<uint4*>(tile + j * kPlaneBytes) = pk;
+                    }
+                }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars.a_full[0]);
+            if (TRACE && tracing && bi < 256u) p.trace[bi * 8 + 2] = clock64();
+        }
     }
-    cp_async_wait<0>();
 }
 
 // REFINE codebook producer / MMA issuers.  Consecutive tiles of the chunk-sorted order mostly share their chunk, so the
@@ -580,16 +607,13 @@ __device__ __forceinline__ void refine_issuer(const CoarseParams& p, unsigned ch
 // why the work is spread over all 16 warps and why the float -> double widening of the sums is done with integer
 // instructions (F2F.F64.F32 runs on the quarter-rate conversion unit that the divisions already keep busy).
 // ------------------------------------------------------------------------------------------------
-constexpr int kRefHitOff = 0;        // uint2  [half][128]      columns within the margin (bit masks)
-constexpr int kRefDecOff = 4096;     // int4   [4 tiles][128]   {code or -1, row, norm bits, 0}
-
-// exact float -> double without the conversion unit (normal numbers and zero; anything else takes the instruction)
-__device__ __forceinline__ double widen_exact(float f) {
-    const uint32_t b = __float_as_uint(f);
-    const uint32_t ex = b & 0x7f800000u;
-    if (ex == 0u || ex == 0x7f800000u) return (b << 1) == 0u ? __hiloint2double((int)b, 0) : (double)f;
-    return __hiloint2double((int)((b & 0x80000000u) | (((b & 0x7fffffffu) >> 3) + 0x38000000u)), (int)(b << 29));
-}
+constexpr int kRefHitOff  = 0;       // uint2  [half][128]      columns within the margin (bit masks)
+constexpr int kRefSortOff = 2048;    // uint8  [4 tiles][168]   decided rows in code order [128] | first entry of each group [33]
+constexpr int kRefSortSlot = 168;
+constexpr int kRefCntOff  = 2720;    // int    [128]            counting-sort counters / offsets of the tile being decided
+constexpr int kRefFlagOff = 3232;    // int    [1 + 210 + 1]    the CTA's near-tie rows (count first), flushed to flag_rows in batches
+constexpr int kRefFlagCap = 210;
+constexpr int kRefDecOff  = 4096;    // int4   [4 tiles][128]   {code or -1, row, norm bits, 0}
 
 template <int OFF_SCRATCH, int OFF_ACC, int OFF_STAGE, bool TRACE>
 __device__ __forceinline__ void refine_epilogue(const CoarseParams& p, unsigned char* smem, const Bars& bars, uint32_t tmem_base,
@@ -599,76 +623,107 @@ __device__ __forceinline__ void refine_epilogue(const CoarseParams& p, unsigned 
     const bool fuse = p.fuse_rows != 0;
     int4* dec_ring = reinterpret_cast<int4*>(smem + OFF_SCRATCH + kRefDecOff);
     const int tid_h = (warp & 7) * 32 + lane;         // within the half (0..255)
-    const int g16 = tid_h >> 4, q = tid_h & 15;       // 16 groups of 16 lanes
+    const int g16 = tid_h >> 4, q = tid_h & 15;       // 16 groups of 16 lanes per half
     const bool lane_on = q < vpr;
+    // SUMS (fused rows): the per-code sums of a tile's decided rows go into fp64 accumulators in shared memory (128 codes
+    // x d; the CTA's tiles are contiguous in the chunk-sorted order, so they are flushed only when the chunk changes).
+    // Each of the 32 sixteen-lane groups of the epilogue OWNS four consecutive codes of the chunk, and lane q of the group
+    // the dimensions 4 q .. 4 q + 3 of them: every accumulator cell belongs to one thread -- no atomics (shared-memory fp64
+    // atomics are CAS loops at 2-4 cycles per lane and made the pass three times slower), no barriers.  The tile's decided
+    // rows arrive sorted by code, so a group adds up each code's rows in registers and touches a cell once per code and tile.
+    const int G = (warp >> 3) * 16 + g16;
+    double* acc = reinterpret_cast<double*>(smem + OFF_ACC);
+    unsigned char* sort_s = smem + OFF_SCRATCH + kRefSortOff;         // per ring slot: order[128] | group offsets [33]
+    const bool tr_d = TRACE && p.trace != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0;
+    int acc_chunk = -1;
+    if (fuse && lane_on)
+        for (int c4 = 0; c4 < 4; ++c4) {
+            double2* a = reinterpret_cast<double2*>(acc + (4 * G + c4) * d + 4 * q);
+            a[0] = make_double2(0.0, 0.0); a[1] = make_double2(0.0, 0.0);
+        }
+    auto flush_own = [&](int ch) {       // this thread's cells of chunk `ch` -> embed_sum (fp64 REDs), then zero
+        if (!lane_on) return;
+        for (int c4 = 0; c4 < 4; ++c4) {
+            const int code = ch * kTileCodes + 4 * G + c4;
+            double2* a = reinterpret_cast<double2*>(acc + (4 * G + c4) * d + 4 * q);
+            const double2 x0 = a[0], x1 = a[1];
+            if (code < p.k) {
+                double* dst = p.stats + p.k + (size_t)code * d + 4 * q;
+                if (x0.x != 0.0) atomicAdd(dst + 0, x0.x);
+                if (x0.y != 0.0) atomicAdd(dst + 1, x0.y);
+                if (x1.x != 0.0) atomicAdd(dst + 2, x1.x);
+                if (x1.y != 0.0) atomicAdd(dst + 3, x1.y);
+            }
+            a[0] = make_double2(0.0, 0.0); a[1] = make_double2(0.0, 0.0);
+        }
+    };
+    // SUMS of tile number `t` (chunk `ch`, staging tile `sbuf`); `release_dec`: also hand the decision ring slot back
+    auto sums = [&](uint32_t t, int ch, int sbuf, bool release_dec) {
+        if (acc_chunk >= 0 && ch != acc_chunk) flush_own(acc_chunk);
+        acc_chunk = ch;
+        const int slot = (int)(t & 3u);
+        mbar_wait(&bars.p1_full[slot], (t >> 2) & 1u);            // the ROWS half has left zf in the staging tile
+        mbar_wait(&bars.sort_full[slot], (t >> 2) & 1u);          // the tile's decided rows are listed in code order
+        if (TRACE && tr_d && t + 1u < 256u) p.trace[(256 + t + 1u) * 8 + 6] = clock64();
+        const int4* dec = dec_ring + slot * 128;
+        const unsigned char* stg = smem + OFF_STAGE + sbuf * kStageTileBytes;
+        const unsigned char* order = sort_s + slot * kRefSortSlot;
+        const int lo = order[128 + G], hi = order[128 + G + 1];   // this group's codes: 4 G .. 4 G + 3
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int cur = -1;
+        auto put = [&]() {
+            if (cur >= 0 && lane_on) {
+                double2* a = reinterpret_cast<double2*>(acc + (cur & (kTileCodes - 1)) * d + 4 * q);
+                double2 x0 = a[0], x1 = a[1];
+                x0.x += a0; x0.y += a1; x1.x += a2; x1.y += a3;
+                a[0] = x0; a[1] = x1;
+            }
+        };
+        // one row ahead: the next row's code and zf are fetched before the current row is added
+        int r_n = lo < hi ? (int)order[lo] : 0;
+        int code_n = lo < hi ? dec[r_n].x : -1;
+        float4 z_n = (lo < hi && lane_on) ? *reinterpret_cast<const float4*>(stg + r_n * row_stride + q * 16)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = lo; i < hi; ++i) {
+            const int code = code_n;
+            const float4 zf = z_n;
+            if (i + 1 < hi) {
+                r_n = (int)order[i + 1];
+                code_n = dec[r_n].x;
+                if (lane_on) z_n = *reinterpret_cast<const float4*>(stg + r_n * row_stride + q * 16);
+            }
+            if (code != cur) { put(); cur = code; a0 = a1 = a2 = a3 = 0.0; }
+            a0 += (double)zf.x; a1 += (double)zf.y; a2 += (double)zf.z; a3 += (double)zf.w;
+        }
+        put();
+        __syncwarp();
+        if (TRACE && tr_d && t < 256u) p.trace[t * 8 + 7] = clock64();
+        if (lane == 0) {
+            mbar_arrive(&bars.stg_empty[sbuf]);                    // the staging tile may be refilled
+            if (release_dec) mbar_arrive(&bars.dec_empty[slot]);
+        }
+    };
     if (warp < 8) {
         // ---------------------------------- DECIDE (+ SUMS of the previous tile) ----------------------------------
         const int quarter = warp & 3, half = warp >> 2;
         const int rq = quarter * 32 + lane;
-        const int gsh = lane & 16;                    // position of this group's 16 lanes in the warp's ballots
         const float margin = p.meta[META_MARGIN];
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 64);
         uint2* hit_s = reinterpret_cast<uint2*>(smem + OFF_SCRATCH + kRefHitOff);
-        double* acc = reinterpret_cast<double*>(smem + OFF_ACC);
-        const int nacc = kTileCodes * d;
-        if (fuse) {
-            for (int i = tid_h; i < nacc; i += 256) acc[i] = 0.0;
-            named_bar_sync(1, 256);
-        }
-        auto flush = [&](int ch) {       // accumulators of chunk `ch` -> embed_sum (fp64 REDs), then zero
-            double* dst = p.stats + p.k + (size_t)ch * kTileCodes * d;
-            const int lim = min(kTileCodes, p.k - ch * kTileCodes) * d;
-            for (int i = tid_h; i < nacc; i += 256) {
-                const double v = acc[i];
-                if (v != 0.0 && i < lim) atomicAdd(dst + i, v);
-                acc[i] = 0.0;
-            }
-        };
-        // SUMS of tile number `t` (chunk `ch`): rows are taken by code ownership; the next owned row's data is fetched
-        // before the current accumulator update, so only updates of the same code wait for one another
-        int acc_chunk = -1;
-        auto sums = [&](uint32_t t, int ch, int sbuf) {
-            if (acc_chunk >= 0 && ch != acc_chunk) {
-                named_bar_sync(1, 256);               // every group is done with the previous chunk's tiles
-                flush(acc_chunk);
-                named_bar_sync(1, 256);
-            }
-            acc_chunk = ch;
-            const int slot = (int)(t & 3u);
-            mbar_wait(&bars.p1_full[slot], (t >> 2) & 1u);           // the ROWS half has left zf in the staging tile
-            const int4* dec = dec_ring + slot * 128;
-            const unsigned char* stg = smem + OFF_STAGE + sbuf * kStageTileBytes;
-            unsigned long long own_lo = 0ull, own_hi = 0ull;        // rows 0-63 / 64-127 (lane q looks at rows q, q + 16, ...)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int code = dec[j * 16 + q].x;
-                const unsigned b = __ballot_sync(0xffffffffu, code >= 0 && (code & 15) == g16);
-                const unsigned long long m16 = (unsigned long long)((b >> gsh) & 0xffffu);
-                if (j < 4) own_lo |= m16 << (16 * j); else own_hi |= m16 << (16 * (j - 4));
-            }
-            auto next_row = [&]() -> int {
-                if (own_lo) { const int r = __ffsll((long long)own_lo) - 1; own_lo &= own_lo - 1; return r; }
-                if (own_hi) { const int r = 63 + __ffsll((long long)own_hi); own_hi &= own_hi - 1; return r; }
-                return -1;
-            };
-            int rr = next_row();
-            int code = rr >= 0 ? dec[rr].x : 0;
-            float4 zf = (rr >= 0 && lane_on) ? *reinterpret_cast<const float4*>(stg + rr * row_stride + q * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
-            while (rr >= 0) {
-                const int rn = next_row();
-                const int code_n = rn >= 0 ? dec[rn].x : 0;
-                const float4 zn = (rn >= 0 && lane_on) ? *reinterpret_cast<const float4*>(stg + rn * row_stride + q * 16)
-                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
-                if (lane_on) {
-                    double2* a = reinterpret_cast<double2*>(acc + (code & (kTileCodes - 1)) * d + 4 * q);
-                    double2 a0 = a[0], a1 = a[1];
-                    a0.x += widen_exact(zf.x); a0.y += widen_exact(zf.y); a1.x += widen_exact(zf.z); a1.y += widen_exact(zf.w);
-                    a[0] = a0; a[1] = a1;
-                }
-                rr = rn; code = code_n; zf = zn;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars.stg_empty[sbuf]);      // the staging tile may be refilled
+        int* cnt_s = reinterpret_cast<int*>(smem + OFF_SCRATCH + kRefCntOff);
+        int* fl_s = reinterpret_cast<int*>(smem + OFF_SCRATCH + kRefFlagOff);    // [0] count, [1...] the CTA's near-tie rows
+        if (warp == 0 && lane == 0) fl_s[0] = 0;
+        // the CTA's flag list -> the global one (`nthr` threads with ids `tid` that meet at named barrier `bar`)
+        auto flush_flags = [&](int tid, int nthr, int bar) {
+            int* base_s = fl_s + 1 + kRefFlagCap;
+            const int nfl = fl_s[0];
+            if (tid == 0) *base_s = atomicAdd(&p.counters[CNT_FLAGGED], nfl);
+            named_bar_sync(bar, nthr);
+            const int base = *base_s;
+            for (int i = tid; i < nfl; i += nthr) p.flag_rows[base + i] = fl_s[1 + i];
+            named_bar_sync(bar, nthr);
+            if (tid == 0) fl_s[0] = 0;
+            named_bar_sync(bar, nthr);
         };
         uint32_t bi = 0;
         int sbuf = 0, sbuf_prev = 0, chunk_prev = -1;
@@ -682,7 +737,7 @@ __device__ __forceinline__ void refine_epilogue(const CoarseParams& p, unsigned 
             if (valid) e = __ldg(&p.entries[start + rq]);
             const float thrF = __int_as_float(e.y) - margin;
             mbar_wait(&bars.acc_full[slot], use_par);
-            if (TRACE && p.trace != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0 && bi < 512u) p.trace[bi * 8 + 3] = clock64();
+            if (TRACE && tr_d && bi < 256u) { p.trace[bi * 8 + 3] = clock64(); p.trace[(256 + bi) * 8 + 0] = clock64(); }
             tc_fence_after();
             uint32_t ha = 0, hb = 0;
             {
@@ -700,6 +755,7 @@ __device__ __forceinline__ void refine_epilogue(const CoarseParams& p, unsigned 
             if (!valid) ha = hb = 0u;
             hit_s[half * 128 + rq] = make_uint2(ha, hb);
             named_bar_sync(1, 256);
+            if (TRACE && tr_d && bi < 256u) p.trace[(256 + bi) * 8 + 1] = clock64();
             if (half == 0) {
                 const uint2 o = hit_s[128 + rq];
                 const uint32_t msk[4] = {ha, hb, o.x, o.y};          // columns [0,32) [32,64) [64,96) [96,128) of the chunk
@@ -715,26 +771,24 @@ __device__ __forceinline__ void refine_epilogue(const CoarseParams& p, unsigned 
                     dec_ring[slot * 128 + rq] = make_int4(code, row, e.z, 0);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars.dec_full[slot]);
-                    if (TRACE && p.trace != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0 && bi < 512u) p.trace[bi * 8 + 4] = clock64();
+                    named_bar_sync(3, 256);                           // ... and the warps of the right half sort them by code
+                    if (TRACE && tr_d && bi < 256u) { p.trace[bi * 8 + 4] = clock64(); p.trace[(256 + bi) * 8 + 3] = clock64(); }
                 }
+                // Near-tie bookkeeping.  Nothing here waits for a global atomic: the flag list is collected per CTA in
+                // shared memory (flushed with one reservation per ~100 rows), a row listed under two chunks gets its first
+                // tile's columns from the front of its candidate list and the second tile's from the back, counted in
+                // separate bit fields of cand_cnt by fire-and-forget reductions.
                 bool flagged = false, over = false;
-                auto list_to = [&](int* dst, int at) {                // append the hit columns at dst[at...] (capacity cand_cap)
-#pragma unroll
-                    for (int qq = 0; qq < 4; ++qq) {
-                        uint32_t m = msk[qq];
-                        while (m) {
-                            const int i = __ffs(m) - 1;
-                            m &= m - 1;
-                            if (at < p.cand_cap) dst[at] = col0 + 32 * qq + i;
-                            ++at;
-                        }
-                    }
-                };
                 if (valid && !decided) {
                     int* dst = p.cand + (size_t)row * p.cand_cap;
                     if (!cross) {
                         if (nhit >= 2 && nhit <= p.cand_cap) {
-                            list_to(dst, 0);
+                            int at = 0;
+#pragma unroll
+                            for (int qq = 0; qq < 4; ++qq) {
+                                uint32_t m = msk[qq];
+                                while (m) { const int i = __ffs(m) - 1; m &= m - 1; dst[at++] = col0 + 32 * qq + i; }
+                            }
                             p.cand_cnt[row] = nhit;
                             flagged = true;
                         } else {                                      // too many near-ties: the COLLECT pass / exact scan decides
@@ -742,7 +796,18 @@ __device__ __forceinline__ void refine_epilogue(const CoarseParams& p, unsigned 
                             over = true;
                         }
                     } else {
-                        list_to(dst, atomicAdd(&p.cand_cnt[row], nhit));    // an overflowing list sends the row to the exact scan
+                        int at = 0;
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq) {
+                            uint32_t m = msk[qq];
+                            while (m) {
+                                const int i = __ffs(m) - 1;
+                                m &= m - 1;
+                                if (at < p.cand_cap) dst[second ? p.cand_cap - 1 - at : at] = col0 + 32 * qq + i;
+                                ++at;
+                            }
+                        }
+                        atomicAdd(&p.cand_cnt[row], second ? (min(nhit, 255) << kCandBackShift) : nhit);   // result unused: RED
                         flagged = !second;
                     }
                 }
@@ -755,38 +820,76 @@ __device__ __forceinline__ void refine_epilogue(const CoarseParams& p, unsigned 
                 const unsigned ball = __ballot_sync(0xffffffffu, flagged);
                 if (ball) {
                     int base = 0;
-                    if (lane == 0) base = atomicAdd(&p.counters[CNT_FLAGGED], __popc(ball));
+                    if (lane == 0) base = atomicAdd(&fl_s[0], __popc(ball));            // shared-memory counter
                     base = __shfl_sync(0xffffffffu, base, 0);
-                    if (flagged) p.flag_rows[base + __popc(ball & ((1u << lane) - 1))] = row;
+                    if (flagged) fl_s[1 + base + __popc(ball & ((1u << lane) - 1))] = row;
                 }
                 const unsigned oall = __ballot_sync(0xffffffffu, over);
-                if (oall) {
+                if (oall) {                                           // rare
                     int base = 0;
                     if (lane == 0) base = atomicAdd(&p.counters[CNT_OVER], __popc(oall));
                     base = __shfl_sync(0xffffffffu, base, 0);
                     if (over) p.over_rows[base + __popc(oall & ((1u << lane) - 1))] = row;
                 }
+                // flush the CTA's flag list before it can overflow (128 more rows fit after this point)
+                named_bar_sync(2, 128);
+                if (fl_s[0] > kRefFlagCap - 128) flush_flags(warp * 32 + lane, 128, 2);
+            } else if (fuse) {
+                // right half: counting sort of the tile's decided rows by code (128 threads = 128 rows, 128 possible codes):
+                // the SUMS step then adds up each code's rows in registers and touches an accumulator once per code and tile
+                named_bar_sync(3, 256);                               // the left half has published the decisions
+                unsigned char* order = sort_s + slot * kRefSortSlot;
+                const int code = dec_ring[slot * 128 + rq].x;
+                const bool decided = code >= 0;
+                cnt_s[rq] = 0;
+                named_bar_sync(4, 128);
+                const int lc = code & (kTileCodes - 1);
+                const int rank = decided ? atomicAdd(&cnt_s[lc], 1) : 0;
+                named_bar_sync(4, 128);
+                if (warp == 4) {
+                    const int4 c4 = *reinterpret_cast<const int4*>(&cnt_s[4 * lane]);
+                    const int tot4 = c4.x + c4.y + c4.z + c4.w;
+                    int incl = tot4;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += v;
+                    }
+                    const int ex0 = incl - tot4;
+                    *reinterpret_cast<int4*>(&cnt_s[4 * lane]) = make_int4(ex0, ex0 + c4.x, ex0 + c4.x + c4.y, ex0 + c4.x + c4.y + c4.z);
+                    order[128 + lane] = (unsigned char)ex0;               // first entry of group `lane` (codes 4 lane ...)
+                    if (lane == 31) order[128 + 32] = (unsigned char)incl;
+                }
+                named_bar_sync(4, 128);
+                if (decided) order[cnt_s[lc] + rank] = (unsigned char)rq;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars.sort_full[slot]);
             }
+            if (TRACE && tr_d && bi < 256u) p.trace[(256 + bi) * 8 + 4] = clock64();
             named_bar_sync(1, 256);                                   // hit_s is rewritten by the next tile
-            if (fuse && bi >= 1u) sums(bi - 1u, chunk_prev, sbuf_prev);
+            if (TRACE && tr_d && bi < 256u) p.trace[(256 + bi) * 8 + 5] = clock64();
+            if (fuse && bi >= 1u) sums(bi - 1u, chunk_prev, sbuf_prev, false);
+            if (TRACE && tr_d && bi < 256u) p.trace[(256 + bi) * 8 + 7] = clock64();
             chunk_prev = chunk;
             sbuf_prev = sbuf;
             sbuf = sbuf == kStageTiles - 1 ? 0 : sbuf + 1;
         }
+        named_bar_sync(1, 256);
+        flush_flags(tid_h, 256, 1);
         if (fuse) {
-            if (bi >= 1u) sums(bi - 1u, chunk_prev, sbuf_prev);
-            named_bar_sync(1, 256);
-            if (acc_chunk >= 0) flush(acc_chunk);
+            if (bi >= 1u) sums(bi - 1u, chunk_prev, sbuf_prev, false);
+            if (acc_chunk >= 0) flush_own(acc_chunk);
         }
     } else if (fuse) {
         // ---------------------------------- ROWS ----------------------------------
         double sse = 0.0;
         uint32_t bi = 0;
-        int sbuf = 0;                                     // bi % kStageTiles
+        int sbuf = 0, sbuf_prev = 0, chunk_prev = -1;     // bi % kStageTiles
         for (int item = item0; item < item_end; ++item, ++bi, sbuf = (sbuf == kStageTiles - 1 ? 0 : sbuf + 1)) {
+            const int chunk = __ldg(&p.tile_tab[item]).x & 0xffff;
             const int slot = (int)(bi & 3u);
             mbar_wait(&bars.dec_full[slot], (bi >> 2) & 1u);
-            const bool tr_f = TRACE && p.trace != nullptr && blockIdx.x == 0 && warp == 8 && lane == 0 && bi < 512u;
+            const bool tr_f = TRACE && p.trace != nullptr && blockIdx.x == 0 && warp == 8 && lane == 0 && bi < 256u;
             if (TRACE && tr_f) p.trace[bi * 8 + 5] = clock64();
             const int4* dec = dec_ring + slot * 128;
             unsigned char* stg_w = smem + OFF_STAGE + sbuf * kStageTileBytes;
@@ -823,8 +926,13 @@ __device__ __forceinline__ void refine_epilogue(const CoarseParams& p, unsigned 
             }
             __syncwarp();
             if (TRACE && tr_f) p.trace[bi * 8 + 6] = clock64();
-            if (lane == 0) { mbar_arrive(&bars.p1_full[slot]); mbar_arrive(&bars.dec_empty[slot]); }
+            if (lane == 0) mbar_arrive(&bars.p1_full[slot]);
+            if (bi >= 1u) sums(bi - 1u, chunk_prev, sbuf_prev, true);     // this half's share of the previous tile's sums
+            chunk_prev = chunk;
+            sbuf_prev = sbuf;
         }
+        if (bi >= 1u) sums(bi - 1u, chunk_prev, sbuf_prev, true);
+        if (acc_chunk >= 0) flush_own(acc_chunk);
         sse = warp_sum(sse);
         if (lane == 0 && sse != 0.0) atomicAdd(&p.stats[(size_t)p.k + (size_t)p.k * d], sse);
     }
@@ -903,14 +1011,15 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
         for (int i = 0; i < kDataStages; ++i) { mbar_init(&bars.bd_full[i], 1); mbar_init(&bars.bd_empty[i], 4); }
         for (int i = 0; i < kBiasStages; ++i) { mbar_init(&bars.bb_full[i], 1); mbar_init(&bars.bb_empty[i], 4); }
         for (int i = 0; i < 4; ++i) {
-            mbar_init(&bars.a_full[i], kLoadWarps);  // one elected lane per loader warp
+            mbar_init(&bars.a_full[i], (MODE == MODE_REFINE) ? 2 : kLoadWarps);  // one elected lane per loader (REFINE: converting) warp
             mbar_init(&bars.a_empty[i], 4 / RT);     // one commit from each issuer that reads the tile
             mbar_init(&bars.acc_full[i], 1);
             mbar_init(&bars.acc_empty[i], 8);        // one elected lane per epilogue warp serving the slot
             mbar_init(&bars.dec_full[i], 4);         // REFINE: the four deciding warps of the left column half
             mbar_init(&bars.dec_empty[i], 8);        //         the eight finishing warps
             mbar_init(&bars.p1_full[i], 8);
-            if (i < kStageTiles) mbar_init(&bars.stg_empty[i], 8);
+            mbar_init(&bars.sort_full[i], 4);
+            if (i < kStageTiles) { mbar_init(&bars.stg_empty[i], 16); mbar_init(&bars.landed[i], 64); }
         }
         fence_mbar_init();
     }

@@ -21,6 +21,9 @@ constexpr int kGrpOverBit     = 1 << 29;   // three or more chunks (or no finite
 constexpr unsigned kEntCross  = 1u << 31;  // sorted entry {row | flags, best coarse score, row norm, 0} (16 bytes)
 constexpr unsigned kEntSecond = 1u << 30;
 constexpr unsigned kEntRowMask = (1u << 30) - 1;
+// cand_cnt[row]: bits 0-23 = columns listed from the front of the row's candidate list, bits 24-31 = columns listed from
+// its back (the second tile of a row listed under two chunks, REFINE only)
+constexpr int kCandBackShift = 24;
 
 // MODE_TOPK keeps the fp16 scores of every thread's best granules in an L2-resident scratch: per CTA 8 slots x 4 x
 // 1024 records x 16 B

@@ -77,8 +77,8 @@ def run_route(route, zs, w, n, d, k, steps):
         torch.cuda.synchronize()
         _lib.check(_lib.lib().mtvq_debug_set_trace(None), "set_trace")
         t = tr.view(512, 8).cpu().numpy()[4:44].astype(np.int64)
-        names = ["issue->landed", "landed->a_full", "a_full->acc_seen", "acc_seen->dec_pub", "dec_pub->fin_seen",
-                 "fin_seen->scan", "scan->done"]
+        names = ["issue->landed", "landed->a_full", "a_full->acc_seen", "acc_seen->dec_pub", "dec_pub->rows_seen",
+                 "rows_seen->rows_done", "rows_done->sums_done"]
         med = {nm: float(np.median(t[:, i + 1] - t[:, i])) for i, nm in enumerate(names)}
         med["tile_period(done)"] = float(np.median(np.diff(t[:, 7])))
         med["tile_period(issue)"] = float(np.median(np.diff(t[:, 0])))
@@ -87,6 +87,10 @@ def run_route(route, zs, w, n, d, k, steps):
         base = full[0, 2]
         print("TRACE rows0-7", (full[:8] - base).tolist(), flush=True)
         print("TRACE rows40-44", (full[40:45] - base).tolist(), flush=True)
+        dd = full[256 + 20:256 + 44]
+        dn = ["acc->hits", "hits->sorted", "sorted->pub", "pub->bookkept", "bookkept->joined", "joined->sums_start", "sums_start->sums_done"]
+        print("TRACE decider", json.dumps({nm: float(np.median(dd[:, i + 1] - dd[:, i])) for i, nm in enumerate(dn)}),
+              "period", float(np.median(np.diff(dd[:, 0]))), flush=True)
     if "--kernels" in sys.argv:
         from torch.profiler import profile, ProfilerActivity
         with torch.no_grad():
