@@ -489,6 +489,7 @@ def extra_workloads(ctx, peaks, cpu):
 def run_ours(args):
     ctx = Ctx()
     dev, world, rank = ctx.dev, ctx.world, ctx.rank
+    from medtok_b200 import _lib
     from medtok_b200.host_pipeline import HostStream
     from medtok_b200.norm_ema_quantizer import NormEMAVectorQuantizer
 
@@ -575,7 +576,11 @@ def run_ours(args):
                          "frac_burst": achieved / peaks["burst"], "frac_sustained": achieved / peaks["sustained"],
                          "step_frac": step_tf / peak, "step_frac_burst": step_tf / peaks["burst"],
                          "step_frac_sustained": step_tf / peaks["sustained"], "step_achieved": step_tf,
-                         "kernel": "mtvq::coarse_kernel<RT=4, ARGMAX> (tcgen05 coarse-score pass)",
+                         "kernel": ("mtvq::coarse_kernel<RT=4, GROUP> (record-free tcgen05 coarse-score pass of the two-pass route; "
+                                    "the per-chunk REFINE pass, 1/64 of its FLOPs, is part of the step, not of this figure)"
+                                    if _lib.lib().mtvq_hard_route(n, d, k) == 2 else
+                                    "mtvq::coarse_kernel<RT=4, ARGMAX> (tcgen05 coarse-score pass)"),
+                         "route": "two-pass" if _lib.lib().mtvq_hard_route(n, d, k) == 2 else "single-pass",
                          "kernel_ms_median": kms, "kernel_share_of_step": kms / (elapsed_ms / steps),
                          "peak_source": peaks["source"], "flops_per_launch": flops,
                          "sustained_leg": {"seconds": sus_ms * 1e-3, "steps": sus_steps, "ms_per_step": sus_ms / sus_steps,

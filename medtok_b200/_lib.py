@@ -58,6 +58,7 @@ _SIGNATURES = {
     "mtvq_debug_set_trace": (_int, [_vp]),
     "mtvq_debug_set_soft_route": (_int, [_int]),
     "mtvq_debug_set_hard_route": (_int, [_int]),
+    "mtvq_hard_route": (_int, [_i64, _int, _int]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -537,6 +537,13 @@ int mtvq_debug_set_soft_route(int route) {
     return 0;
 }
 
+int mtvq_hard_route(int64_t n, int d, int k) {
+    if (check_dims(n, d, k)) return 0;
+    DeviceInfo di;
+    if (device_info(&di)) return 0;
+    return two_pass_ok(n, d, k, di.num_sms) ? 2 : 1;
+}
+
 int mtvq_debug_set_hard_route(int route) {
     if (route < -1 || route > 2) return fail(MTVQ_ERR_BAD_ARG, "route must be -1 (automatic), 0, 1 (single pass) or 2 (two-pass whenever it applies)%s", "");
     g_hard_route = route;

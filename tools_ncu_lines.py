@@ -16,7 +16,7 @@ txt = subprocess.run(cmd, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
 fname, hdr, lines = "", None, []
 for r in rows:
-    if len(r) >= 2 and r[0] == "File Name":
+    if len(r) >= 2 and r[0] in ("File Name", "File Path"):
         fname = r[1].split("/")[-1]
     elif len(r) > 8 and r[0] == "Line No":
         hdr = r
