@@ -392,6 +392,13 @@ __device__ __forceinline__ int scan_record(const unsigned char* slots, int rec, 
     return n;
 }
 
+// bar.sync is warp-aligned: after divergent code (a lane-0 arrive, per-lane list writes) the warp is re-converged
+// explicitly before it meets a named barrier (synccheck flags the barrier otherwise)
+__device__ __forceinline__ void conv_bar_sync(int id, int nthreads) {
+    __syncwarp();
+    named_bar_sync(id, nthreads);
+}
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
@@ -718,12 +725,12 @@ __device__ __forceinline__ void refine_epilogue(const CoarseParams& p, unsigned 
             int* base_s = fl_s + 1 + kRefFlagCap;
             const int nfl = fl_s[0];
             if (tid == 0) *base_s = atomicAdd(&p.counters[CNT_FLAGGED], nfl);
-            named_bar_sync(bar, nthr);
+            conv_bar_sync(bar, nthr);
             const int base = *base_s;
             for (int i = tid; i < nfl; i += nthr) p.flag_rows[base + i] = fl_s[1 + i];
-            named_bar_sync(bar, nthr);
+            conv_bar_sync(bar, nthr);
             if (tid == 0) fl_s[0] = 0;
-            named_bar_sync(bar, nthr);
+            conv_bar_sync(bar, nthr);
         };
         uint32_t bi = 0;
         int sbuf = 0, sbuf_prev = 0, chunk_prev = -1;
@@ -754,26 +761,33 @@ __device__ __forceinline__ void refine_epilogue(const CoarseParams& p, unsigned 
             }
             if (!valid) ha = hb = 0u;
             hit_s[half * 128 + rq] = make_uint2(ha, hb);
-            named_bar_sync(1, 256);
+            conv_bar_sync(1, 256);
             if (TRACE && tr_d && bi < 256u) p.trace[(256 + bi) * 8 + 1] = clock64();
+            // left half: merge the two column halves of every row and decide
+            uint32_t msk[4] = {0u, 0u, 0u, 0u};                      // columns [0,32) [32,64) [64,96) [96,128) of the chunk
+            int nhit = 0, row = 0, code = -1;
+            bool cross = false, second = false, decided = false;
+            const int col0 = chunk * kTileCodes;
             if (half == 0) {
                 const uint2 o = hit_s[128 + rq];
-                const uint32_t msk[4] = {ha, hb, o.x, o.y};          // columns [0,32) [32,64) [64,96) [96,128) of the chunk
-                const int nhit = __popc(ha) + __popc(hb) + __popc(o.x) + __popc(o.y);
+                msk[0] = ha; msk[1] = hb; msk[2] = o.x; msk[3] = o.y;
+                nhit = __popc(ha) + __popc(hb) + __popc(o.x) + __popc(o.y);
                 const int first = ha ? __ffs(ha) - 1 : (hb ? 31 + __ffs(hb) : (o.x ? 63 + __ffs(o.x) : (o.y ? 95 + __ffs(o.y) : -1)));
-                const int row = (int)((unsigned)e.x & kEntRowMask);
-                const bool cross = ((unsigned)e.x & kEntCross) != 0u, second = ((unsigned)e.x & kEntSecond) != 0u;
-                const int col0 = chunk * kTileCodes;
-                const bool decided = valid && !cross && nhit == 1 && col0 + first < p.k;
-                const int code = decided ? col0 + first : -1;
+                row = (int)((unsigned)e.x & kEntRowMask);
+                cross = ((unsigned)e.x & kEntCross) != 0u;
+                second = ((unsigned)e.x & kEntSecond) != 0u;
+                decided = valid && !cross && nhit == 1 && col0 + first < p.k;
+                code = decided ? col0 + first : -1;
                 if (fuse) {       // the other warps only need the decided rows: publish them before the near-tie bookkeeping
                     mbar_wait(&bars.dec_empty[slot], use_par ^ 1u);
                     dec_ring[slot * 128 + rq] = make_int4(code, row, e.z, 0);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars.dec_full[slot]);
-                    named_bar_sync(3, 256);                           // ... and the warps of the right half sort them by code
-                    if (TRACE && tr_d && bi < 256u) { p.trace[bi * 8 + 4] = clock64(); p.trace[(256 + bi) * 8 + 3] = clock64(); }
                 }
+            }
+            if (fuse) conv_bar_sync(3, 256);                          // the decisions are in the ring: the right half sorts them
+            if (TRACE && tr_d && bi < 256u) { p.trace[bi * 8 + 4] = clock64(); p.trace[(256 + bi) * 8 + 3] = clock64(); }
+            if (half == 0) {
                 // Near-tie bookkeeping.  Nothing here waits for a global atomic: the flag list is collected per CTA in
                 // shared memory (flushed with one reservation per ~100 rows), a row listed under two chunks gets its first
                 // tile's columns from the front of its candidate list and the second tile's from the back, counted in
@@ -832,20 +846,19 @@ __device__ __forceinline__ void refine_epilogue(const CoarseParams& p, unsigned 
                     if (over) p.over_rows[base + __popc(oall & ((1u << lane) - 1))] = row;
                 }
                 // flush the CTA's flag list before it can overflow (128 more rows fit after this point)
-                named_bar_sync(2, 128);
+                conv_bar_sync(2, 128);
                 if (fl_s[0] > kRefFlagCap - 128) flush_flags(warp * 32 + lane, 128, 2);
             } else if (fuse) {
                 // right half: counting sort of the tile's decided rows by code (128 threads = 128 rows, 128 possible codes):
                 // the SUMS step then adds up each code's rows in registers and touches an accumulator once per code and tile
-                named_bar_sync(3, 256);                               // the left half has published the decisions
                 unsigned char* order = sort_s + slot * kRefSortSlot;
-                const int code = dec_ring[slot * 128 + rq].x;
-                const bool decided = code >= 0;
+                code = dec_ring[slot * 128 + rq].x;
+                decided = code >= 0;
                 cnt_s[rq] = 0;
-                named_bar_sync(4, 128);
+                conv_bar_sync(4, 128);
                 const int lc = code & (kTileCodes - 1);
                 const int rank = decided ? atomicAdd(&cnt_s[lc], 1) : 0;
-                named_bar_sync(4, 128);
+                conv_bar_sync(4, 128);
                 if (warp == 4) {
                     const int4 c4 = *reinterpret_cast<const int4*>(&cnt_s[4 * lane]);
                     const int tot4 = c4.x + c4.y + c4.z + c4.w;
@@ -860,13 +873,13 @@ __device__ __forceinline__ void refine_epilogue(const CoarseParams& p, unsigned 
                     order[128 + lane] = (unsigned char)ex0;               // first entry of group `lane` (codes 4 lane ...)
                     if (lane == 31) order[128 + 32] = (unsigned char)incl;
                 }
-                named_bar_sync(4, 128);
+                conv_bar_sync(4, 128);
                 if (decided) order[cnt_s[lc] + rank] = (unsigned char)rq;
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars.sort_full[slot]);
             }
             if (TRACE && tr_d && bi < 256u) p.trace[(256 + bi) * 8 + 4] = clock64();
-            named_bar_sync(1, 256);                                   // hit_s is rewritten by the next tile
+            conv_bar_sync(1, 256);                                   // hit_s is rewritten by the next tile
             if (TRACE && tr_d && bi < 256u) p.trace[(256 + bi) * 8 + 5] = clock64();
             if (fuse && bi >= 1u) sums(bi - 1u, chunk_prev, sbuf_prev, false);
             if (TRACE && tr_d && bi < 256u) p.trace[(256 + bi) * 8 + 7] = clock64();
@@ -874,7 +887,7 @@ __device__ __forceinline__ void refine_epilogue(const CoarseParams& p, unsigned 
             sbuf_prev = sbuf;
             sbuf = sbuf == kStageTiles - 1 ? 0 : sbuf + 1;
         }
-        named_bar_sync(1, 256);
+        conv_bar_sync(1, 256);
         flush_flags(tid_h, 256, 1);
         if (fuse) {
             if (bi >= 1u) sums(bi - 1u, chunk_prev, sbuf_prev, false);

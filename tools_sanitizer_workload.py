@@ -35,5 +35,21 @@ with torch.no_grad():
     for kk, nn_, kc in ((1, 257, 333), (8, 130, 1000)):
         _SoftQuantizeFn.apply(torch.randn(nn_, 64, device=dev), torch.randn(kc, 64, device=dev), 0, kc, kk, 0.25, True,
                               _lib.Workspace())
+# two-pass hard route (GROUP -> group sort -> REFINE with fused rows -> finish_flagged): forced, at the smallest size that
+# gives four-row-tile blocks; ragged tail (n % 128 != 0), padding codes (k % 128 != 0), duplicated codes (near-ties
+# across chunks, rows listed twice, COLLECT fallback), training and eval
+if os.environ.get("SANITIZE_TWO_PASS", "1") == "1":
+    _lib.check(_lib.lib().mtvq_debug_set_hard_route(2), "route")
+    n2, k2 = 151700, 300
+    q2 = NormEMAVectorQuantizer(k2, 32, 0.25).to(dev).train()
+    w2 = torch.nn.functional.normalize(torch.randn(k2, 32, device=dev), dim=-1)
+    w2[200:230] = w2[3]
+    q2.embedding.weight.data.copy_(w2)
+    z2 = torch.randn(n2, 32, 1, 1, device=dev)
+    z2[:2000, :, 0, 0] = w2[3] + 1e-3 * torch.randn(2000, 32, device=dev)
+    with torch.no_grad():
+        q2(z2)
+        q2.eval(); q2(z2)
+    _lib.check(_lib.lib().mtvq_debug_set_hard_route(-1), "route")
 torch.cuda.synchronize()
 print("sanitizer workload done", "(tensor route forced)" if force_tensor else "(automatic route)")
