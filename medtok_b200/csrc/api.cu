@@ -120,7 +120,9 @@ bool two_pass_ok(int64_t n, int d, int k, int num_sms) {
     if (route == 1) return false;
     const int nchunks = pad_codes(k) / 128;
     if (coarse_row_tiles(d, n, num_sms) != 4 || nchunks < 2 || nchunks > kGroupMaxChunks || n >= (1LL << 30)) return false;
-    return route == 2 || n >= 262144;
+    // measured on B200 (tools_route_check.py): the record-free tensor pass saves ~16 % of the single pass, the sort + REFINE
+    // tail costs ~0.16 us per 1000 rows more than the single pass's tail -- a net win from about K x D = 8192 x 64 upwards
+    return route == 2 || (n >= 262144 && (int64_t)pad_codes(k) * d >= (1 << 19));
 }
 
 // fused row outputs of the two-pass route (training forward): z_q, squared error and per-code sums come out of the
@@ -152,10 +154,10 @@ int assign_rows(const float* z, int64_t n, int d, int norm_mode, const float* co
                                     di.num_sms, st), "exact_scan");
         return 0;
     }
-    MTVQ_CUDA(cudaMemsetAsync(ws.cand_cnt, 0, sizeof(int) * n, st), "memset cand_cnt");
     CoarseParams p;
     fill_coarse(p, z, n, d, norm_mode, k, ws, denom, 1, false, idx);
     const bool two_pass = two_pass_ok(n, d, k, di.num_sms);
+    if (!two_pass) MTVQ_CUDA(cudaMemsetAsync(ws.cand_cnt, 0, sizeof(int) * n, st), "memset cand_cnt");   // GROUP zeroes it per row
     if (two_pass) {
         MTVQ_CUDA(cudaMemsetAsync(ws.ghist, 0, sizeof(int) * (pad_codes(k) / 128), st), "memset ghist");
         p.grp = ws.grp;
@@ -186,7 +188,8 @@ int assign_rows(const float* z, int64_t n, int d, int norm_mode, const float* co
     c.n_rows_dev = ws.counters + CNT_OVER;
     c.denom = nullptr;
     MTVQ_CUDA(launch_coarse(c, MODE_COLLECT, 1, di.num_sms, st), "coarse collect");   // few rows: 128-row items
-    MTVQ_CUDA(launch_resolve(z, d, norm_mode, codes, k, ws, p.cand_cap, idx, di.num_sms, st), "resolve");
+    MTVQ_CUDA(launch_resolve(z, d, norm_mode, codes, k, ws, p.cand_cap, idx, di.num_sms, st,
+                             (two_pass && fused) ? fused->z_q : nullptr, (two_pass && fused) ? fused->stats : nullptr), "resolve");
     MTVQ_CUDA(launch_exact_scan(z, n, d, norm_mode, codes, k, ws.cc, ws.full_rows, ws.counters + CNT_FULL, idx, ws.bins_i32,
                                 nullptr, di.num_sms, st), "exact_scan(overflow)");
     if (two_pass && fused) {

@@ -142,7 +142,8 @@ __device__ __forceinline__ bool better(float v, int i, float bv, int bi) {
 __global__ void __launch_bounds__(kResWarps * 32, 4) resolve_kernel(
     const float* __restrict__ z, int d, int norm_mode, const float* __restrict__ w, int k, const float* __restrict__ cc,
     const int* __restrict__ flag_rows, const int* __restrict__ cand, const int* __restrict__ cand_cnt, int cand_cap,
-    int64_t* __restrict__ idx, int* __restrict__ bins, int* __restrict__ full_rows, int* __restrict__ counters) {
+    int64_t* __restrict__ idx, int* __restrict__ bins, int* __restrict__ full_rows, int* __restrict__ counters,
+    float* __restrict__ z_q, double* __restrict__ stats) {
     __shared__ __align__(16) float xs[kResWarps][kMaxDim];                  // normalised row per warp
     // granule slab per warp; row stride 36 floats keeps 16-byte accesses aligned and conflict free: within a
     // quarter-warp phase the 8 lanes' rows (or 8 consecutive float4 of a row) fall into 8 different bank quads
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(kResWarps * 32, 4) resolve_kernel(
     const int nflag = counters[CNT_FLAGGED];
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     int ncands = 0;
+    double sse = 0.0;
     for (int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < nflag; p += nwarps) {
         const int row = flag_rows[p];
         // candidate lists are indexed by row; the count word has two fields (assign_tc.h kCandBackShift): columns listed
@@ -287,10 +289,27 @@ __global__ void __launch_bounds__(kResWarps * 32, 4) resolve_kernel(
                 full_rows[atomicAdd(&counters[CNT_FULL], 1)] = row;
             }
         }
+        // two-pass route, fused rows: the row's share of :181,202,212-214 right here -- the normalised row is in shared
+        // memory and the winner is known (the REFINE pass did this for the rows it decided itself)
+        if (z_q != nullptr && bcol != 0x7fffffff) {
+            double* esum = stats + k + (size_t)bcol * d;
+            const float* wr = w + (size_t)bcol * d;
+            for (int i = lane; i < d; i += 32) {
+                const float zf = xs[wib][i];
+                const float dd = __fsub_rn(__ldg(wr + i), zf);
+                sse += (double)__fmul_rn(dd, dd);
+                z_q[(size_t)row * d + i] = __fadd_rn(zf, dd);
+                atomicAdd(esum + i, (double)zf);
+            }
+        }
     }
     __syncwarp();
     ncands = __reduce_add_sync(0xffffffffu, ncands);
     if (lane == 0 && ncands) atomicAdd(&counters[CNT_CANDS], ncands);
+    if (z_q != nullptr) {
+        sse = warp_sum(sse);
+        if (lane == 0 && sse != 0.0) atomicAdd(&stats[(size_t)k + (size_t)k * d], sse);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -442,10 +461,10 @@ cudaError_t launch_codebook_prep(const float* w, int k, int d, int flags, const 
 }
 
 cudaError_t launch_resolve(const float* z, int d, int norm_mode, const float* w, int k, const Workspace& ws,
-                           int cand_cap, int64_t* idx, int num_sms, cudaStream_t stream) {
+                           int cand_cap, int64_t* idx, int num_sms, cudaStream_t stream, float* z_q, double* stats) {
     resolve_kernel<<<num_sms * 4, kResWarps * 32, 0, stream>>>(z, d, norm_mode, w, k, ws.cc, ws.flag_rows, ws.cand,
                                                                 ws.cand_cnt, cand_cap, idx, ws.bins_i32, ws.full_rows,
-                                                                ws.counters);
+                                                                ws.counters, z_q, stats);
     ++g_kernel_launches;
     return cudaGetLastError();
 }

@@ -1506,6 +1506,7 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                     }
                     den = den < kNormEps ? kNormEps : den;
                     if (p.denom) p.denom[row] = den;
+                    if (MODE == MODE_GROUP) p.cand_cnt[row] = 0;      // candidate lists start empty (REFINE / COLLECT append)
                     rden = __frcp_rn(den);
                 }
                 auto pack8 = [&](int j) {

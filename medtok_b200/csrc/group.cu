@@ -137,24 +137,24 @@ __global__ void __launch_bounds__(256) group_scatter_direct_kernel(const int* __
     }
 }
 
-// After the exact re-scoring: the near-tie rows' share of the fused row work (z_q, squared error, per-code sums -- the
-// REFINE pass only did the rows it decided itself), 16 lanes per row; and the packed statistics' counts (bins as doubles,
-// rows), which need the histogram to be complete.
+// After the exact scan: the row work (z_q, squared error, per-code sums) of the few rows only the full scan could decide
+// (ws.full_rows; every other near-tie row was finished by resolve_kernel, every decided row by the REFINE pass), 16 lanes
+// per row; and the packed statistics' counts (bins as doubles, rows), which need the histogram to be complete.
 __global__ void __launch_bounds__(256) finish_flagged_kernel(const float* __restrict__ z, const float* __restrict__ denom,
                                                               const float* __restrict__ w, const int64_t* __restrict__ idx,
-                                                              const int* __restrict__ flag_rows, const int* __restrict__ counters,
+                                                              const int* __restrict__ rows, const int* __restrict__ n_rows_dev,
                                                               const int* __restrict__ bins, int64_t n, int d, int k,
                                                               float* __restrict__ z_q, double* __restrict__ stats) {
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < k; c += (int64_t)gridDim.x * blockDim.x)
         stats[c] += (double)bins[c];
     if (blockIdx.x == 0 && threadIdx.x == 0) stats[(size_t)k + (size_t)k * d + 1] += (double)n;
-    const int nflag = counters[CNT_FLAGGED];
+    const int nflag = *n_rows_dev;
     const int vpr = d >> 2, q = threadIdx.x & 15;
     const int ngroups = (gridDim.x * blockDim.x) >> 4;
     double* embed_sum = stats + k;
     double sse = 0.0;
     for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 4; i < nflag; i += ngroups) {
-        const int row = flag_rows[i];
+        const int row = rows[i];
         const int code = (int)idx[row];
         if (q >= vpr || code < 0 || code >= k) continue;
         const float dn = denom[row];
@@ -197,8 +197,8 @@ cudaError_t launch_group_sort(const Workspace& ws, const float* denom, int64_t n
 
 cudaError_t launch_finish_flagged(const float* z, const float* denom, const float* w, const int64_t* idx, int64_t n, int d,
                                   int k, float* z_q, double* stats, const Workspace& ws, int num_sms, cudaStream_t s) {
-    finish_flagged_kernel<<<num_sms * 4, 256, 0, s>>>(z, denom, w, idx, ws.flag_rows, ws.counters, ws.bins_i32, n, d, k, z_q,
-                                                      stats);
+    finish_flagged_kernel<<<num_sms, 256, 0, s>>>(z, denom, w, idx, ws.full_rows, ws.counters + CNT_FULL, ws.bins_i32, n, d, k,
+                                                  z_q, stats);
     ++g_kernel_launches;
     return cudaGetLastError();
 }

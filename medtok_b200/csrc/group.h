@@ -11,8 +11,8 @@ namespace mtvq {
 // counters[CNT_TILES]; then ws.grp / ws.best_val / denom (the row norms the GROUP pass wrote) -> ws.entries sorted by chunk
 cudaError_t launch_group_sort(const Workspace& ws, const float* denom, int64_t n, int k, int num_sms, cudaStream_t s);
 
-// z_q / squared error / per-code sums of the near-tie rows (ws.flag_rows, decided by the exact re-scoring), and the
-// counts of the packed statistics (stats[c] += bins[c], rows += n)
+// z_q / squared error / per-code sums of the rows only the exact full scan could decide (ws.full_rows; resolve_kernel
+// finishes the other near-tie rows itself), and the counts of the packed statistics (stats[c] += bins[c], rows += n)
 cudaError_t launch_finish_flagged(const float* z, const float* denom, const float* w, const int64_t* idx, int64_t n, int d,
                                   int k, float* z_q, double* stats, const Workspace& ws, int num_sms, cudaStream_t s);
 
