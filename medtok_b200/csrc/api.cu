@@ -162,6 +162,9 @@ int assign_rows(const float* z, int64_t n, int d, int norm_mode, const float* co
         MTVQ_CUDA(cudaMemsetAsync(ws.ghist, 0, sizeof(int) * (pad_codes(k) / 128), st), "memset ghist");
         p.grp = ws.grp;
         p.ghist = ws.ghist;
+        static int trace_group = -1;
+        if (trace_group < 0) { const char* e = getenv("MTVQ_TRACE_GROUP"); trace_group = (e && e[0] == '1') ? 1 : 0; }
+        if (trace_group) p.debug_flags |= 0x100;         // the pipeline trace (if set) records the GROUP pass, not REFINE
         if (g_ev_before) cudaEventRecord(g_ev_before, st);
         MTVQ_CUDA(launch_coarse(p, MODE_GROUP, 4, di.num_sms, st), "coarse group");
         if (g_ev_after) cudaEventRecord(g_ev_after, st);
@@ -169,6 +172,8 @@ int assign_rows(const float* z, int64_t n, int d, int norm_mode, const float* co
         MTVQ_CUDA(launch_group_sort(ws, denom, n, k, di.num_sms, st), "group sort");
         CoarseParams r = p;
         r.denom = nullptr;
+        if (trace_group) r.trace = nullptr;
+        r.debug_flags = 0;
         r.entries = static_cast<const int4*>(ws.entries);
         r.tile_tab = static_cast<const int2*>(ws.tile_tab);
         r.n_tiles_dev = ws.counters + CNT_TILES;

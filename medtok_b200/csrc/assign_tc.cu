@@ -897,7 +897,7 @@ __device__ __forceinline__ void refine_epilogue(const CoarseParams& p, unsigned 
         // ---------------------------------- ROWS ----------------------------------
         double sse = 0.0;
         uint32_t bi = 0;
-        int sbuf = 0, sbuf_prev = 0, chunk_prev = -1;     // bi % kStageTiles
+        int sbuf = 0;                                     // bi % kStageTiles
         for (int item = item0; item < item_end; ++item, ++bi, sbuf = (sbuf == kStageTiles - 1 ? 0 : sbuf + 1)) {
             const int chunk = __ldg(&p.tile_tab[item]).x & 0xffff;
             const int slot = (int)(bi & 3u);
@@ -940,11 +940,11 @@ __device__ __forceinline__ void refine_epilogue(const CoarseParams& p, unsigned 
             __syncwarp();
             if (TRACE && tr_f) p.trace[bi * 8 + 6] = clock64();
             if (lane == 0) mbar_arrive(&bars.p1_full[slot]);
-            if (bi >= 1u) sums(bi - 1u, chunk_prev, sbuf_prev, true);     // this half's share of the previous tile's sums
-            chunk_prev = chunk;
-            sbuf_prev = sbuf;
+            // this half's share of the tile's sums right away (the deciders do theirs one tile later, after the next
+            // decision): the staging tile is handed back a whole tile period earlier, and with three staging tiles that
+            // period is what bounds the pass (copy -> convert -> MMA -> decide -> rows -> sums must fit into two periods)
+            sums(bi, chunk, sbuf, true);
         }
-        if (bi >= 1u) sums(bi - 1u, chunk_prev, sbuf_prev, true);
         if (acc_chunk >= 0) flush_own(acc_chunk);
         sse = warp_sum(sse);
         if (lane == 0 && sse != 0.0) atomicAdd(&p.stats[(size_t)p.k + (size_t)p.k * d], sse);
@@ -1713,7 +1713,13 @@ cudaError_t launch_coarse(const CoarseParams& p, int mode, int row_tiles, int nu
     if (mode == MODE_TOPK && (num_sms > kTopkMaxCtas || p.topk_scratch == nullptr)) return cudaErrorInvalidValue;
     // timing knobs / pipeline trace live in a separate instantiation so that the production kernels carry none of it
     const bool dbg = (mode == MODE_ARGMAX) && (p.trace != nullptr || p.debug_flags != 0);
-    if (mode == MODE_GROUP) return row_tiles == 4 ? launch_one<4, MODE_GROUP, 5, false>(p, num_sms, stream) : cudaErrorInvalidValue;
+    if (mode == MODE_GROUP) {
+        if (row_tiles != 4) return cudaErrorInvalidValue;
+        // slot-loop trace of the GROUP pass (mtvq_debug_set_trace + MTVQ_TRACE_GROUP=1; the REFINE pass leaves the buffer alone then)
+        // (MTVQ_DBG timing experiments 1 / 2 / 4 apply to this pass too; results are wrong when set)
+        const bool dbg_g = (p.trace != nullptr && (p.debug_flags & 0x100)) || (p.debug_flags & 7);
+        return dbg_g ? launch_one<4, MODE_GROUP, 5, true>(p, num_sms, stream) : launch_one<4, MODE_GROUP, 5, false>(p, num_sms, stream);
+    }
     if (mode == MODE_REFINE)
         return p.trace != nullptr ? launch_one<1, MODE_REFINE, 5, true>(p, num_sms, stream)
                                   : launch_one<1, MODE_REFINE, 5, false>(p, num_sms, stream);
