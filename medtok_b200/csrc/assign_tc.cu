@@ -76,7 +76,7 @@ struct SmemMap {
     static constexpr int kOffSlots = kOffBBias + kBiasStages * kBiasBytes;   // 4 chunks x kRec records x 16 B (fp16 granules)
     static constexpr int kOffState = kOffSlots + 4 * kRec * 16;              // kRec records x 16 B
     static constexpr int kOffBars  = kOffState + kRec * 16;
-    static constexpr int kNumBars  = 2 * kStages + 2 * kBiasStages + 4 + 4 + 4 + 4 + 8 + 3 + 4 + 3 + 4;
+    static constexpr int kNumBars  = 2 * kStages + 2 * kBiasStages + 4 + 4 + 4 + 4 + 8 + 4 + 4 + 4 + 4;
     static constexpr int kOffTmem  = kOffBars + kNumBars * 8;
     static constexpr int kSmemBytes = kOffTmem + 16;
     static constexpr int kOffAcc = 0, kOffStage = 0;                      // REFINE only
@@ -88,8 +88,14 @@ struct SmemMap {
 // accumulators of the fused row work (128 codes x d) and THREE staging tiles into which the gathered fp32 rows land by
 // cp.async (row stride 4 d + 16 bytes: the row-per-thread conversion reads are conflict free).  A staging tile is busy
 // from the copy until the finishing warps are done with the rows; three of them keep three such chains interleaved.
-constexpr int kStageTileBytes = kTileRows * (4 * 64 + 16);               // 34816
-constexpr int kStageTiles     = 3;
+#ifndef MTVQ_STAGE_DIM          // experiments only: staging tiles sized for a smaller D leave room for a deeper ring
+#define MTVQ_STAGE_DIM 64
+#endif
+#ifndef MTVQ_STAGE_TILES
+#define MTVQ_STAGE_TILES 3
+#endif
+constexpr int kStageTileBytes = kTileRows * (4 * MTVQ_STAGE_DIM + 16);   // 34816
+constexpr int kStageTiles     = MTVQ_STAGE_TILES;                        // <= 4
 template <>
 struct SmemMap<1, true> {
     static constexpr int kStages   = 1;
@@ -103,7 +109,7 @@ struct SmemMap<1, true> {
     static constexpr int kOffAcc   = kOffState;                          // double [128][d]
     static constexpr int kOffStage = kOffAcc + kTileCodes * 64 * 8;
     static constexpr int kOffBars  = kOffStage + kStageTiles * kStageTileBytes;
-    static constexpr int kNumBars  = 2 * kStages + 2 * kBiasStages + 4 + 4 + 4 + 4 + 8 + 3 + 4 + 3 + 4;
+    static constexpr int kNumBars  = 2 * kStages + 2 * kBiasStages + 4 + 4 + 4 + 4 + 8 + 4 + 4 + 4 + 4;
     static constexpr int kOffTmem  = kOffBars + kNumBars * 8;
     static constexpr int kSmemBytes = kOffTmem + 16;
     static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
@@ -142,7 +148,7 @@ __device__ __forceinline__ Bars carve_bars(unsigned char* smem) {
     r.dec_empty = b;               b += 4;
     r.p1_full = b;                 b += 4;
     r.sort_full = b;               b += 4;
-    r.landed = b;                  b += 3;
+    r.landed = b;                  b += 4;
     r.stg_empty = b;
     return r;
 }
