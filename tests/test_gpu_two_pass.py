@@ -158,3 +158,49 @@ def test_two_pass_accumulates_like_single_pass(dev, route):
     assert np.allclose(s1[k:k + k * d], s2[k:k + k * d], rtol=0, atol=1e-10)
     assert abs(s1[k + k * d] - s2[k + k * d]) <= 1e-7 * s1[k + k * d]
     assert abs(out[1][3] - out[2][3]) <= 1e-6 * out[1][3]
+
+
+def test_two_pass_strided_input_layout(oracle, dev, route):
+    """'b c h w' input with h * w > 1 (reference :169-171: the rows are a permuted view and torch normalises the strided
+    view with a sequential sum): the GROUP loader's strided norm, the norm carried in the sorted entries and the row work
+    of the REFINE pass must reproduce the oracle's strided-norm results bit for bit."""
+    from medtok_b200.norm_ema_quantizer import NormEMAVectorQuantizer
+    b, c, h, w_ = 600, 32, 16, 16                      # 153600 rows
+    k = 520
+    g = torch.Generator().manual_seed(31)
+    z = torch.randn(b, c, h, w_, generator=g)
+    w = torch.nn.functional.normalize(torch.randn(k, c, generator=g), dim=-1)
+    rows = z.permute(0, 2, 3, 1).reshape(-1, c).contiguous()
+    r = oracle.hard_forward(rows.numpy(), w.numpy(), np.zeros(k, np.float32), 0.25, 0.99, strided_norm=True)
+    route(2)
+    q = NormEMAVectorQuantizer(k, c, 0.25).to(dev).train()
+    q.embedding.weight.data.copy_(w.to(dev))
+    with torch.no_grad():
+        z_q, loss, idx = q(z.to(dev))
+    assert z_q.shape == z.shape
+    assert np.array_equal(idx.cpu().numpy(), r.idx)
+    assert np.array_equal(z_q.permute(0, 2, 3, 1).reshape(-1, c).cpu().numpy(), r.z_q)
+    assert np.array_equal(q.cluster_size.cpu().numpy(), r.cluster_size)
+    assert abs(float(loss) - r.loss) <= 1e-6 * r.loss
+    assert np.max(np.abs(q.embedding.weight.cpu().numpy() - r.weight)) <= 1.2e-7
+
+
+def test_route_choice_is_reported(dev):
+    """mtvq_hard_route: the automatic rule (D <= 64, N >= 2^18, K x D >= 2^19) and the overrides."""
+    from medtok_b200 import _lib
+    L = _lib.lib()
+    assert L.mtvq_hard_route(1 << 20, 64, 8192) == 2
+    assert L.mtvq_hard_route(1 << 20, 64, 4096) == 1          # tensor pass too short for the longer tail to pay
+    assert L.mtvq_hard_route(1 << 20, 128, 8192) == 1         # D > 64: two row tiles per block, single pass
+    assert L.mtvq_hard_route(100000, 64, 8192) == 1
+    _lib.check(L.mtvq_debug_set_hard_route(2), "route")
+    try:
+        assert L.mtvq_hard_route(160000, 32, 600) == 2
+        assert L.mtvq_hard_route(1000, 32, 600) == 1          # not enough rows for four-row-tile blocks
+    finally:
+        L.mtvq_debug_set_hard_route(-1)
+    _lib.check(L.mtvq_debug_set_hard_route(1), "route")
+    try:
+        assert L.mtvq_hard_route(1 << 20, 64, 8192) == 1
+    finally:
+        L.mtvq_debug_set_hard_route(-1)
