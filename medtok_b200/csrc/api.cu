@@ -119,7 +119,9 @@ bool two_pass_ok(int64_t n, int d, int k, int num_sms) {
     const int route = g_hard_route >= 0 ? g_hard_route : hard_route_env();
     if (route == 1) return false;
     const int nchunks = pad_codes(k) / 128;
-    if (coarse_row_tiles(d, n, num_sms) != 4 || nchunks < 2 || nchunks > kGroupMaxChunks || n >= (1LL << 30)) return false;
+    if (coarse_row_tiles(d, n, num_sms) != 4 || nchunks < 2 || nchunks > kGroupMaxChunks || n >= (1LL << 30) ||
+        num_sms > kGroupMaxCtas)
+        return false;
     // measured on B200 (tools_route_check.py): the record-free tensor pass saves ~16 % of the single pass, the sort + REFINE
     // tail costs ~0.16 us per 1000 rows more than the single pass's tail -- a net win from about K x D = 8192 x 64 upwards
     return route == 2 || (n >= 262144 && (int64_t)pad_codes(k) * d >= (1 << 19));
@@ -159,9 +161,13 @@ int assign_rows(const float* z, int64_t n, int d, int norm_mode, const float* co
     const bool two_pass = two_pass_ok(n, d, k, di.num_sms);
     if (!two_pass) MTVQ_CUDA(cudaMemsetAsync(ws.cand_cnt, 0, sizeof(int) * n, st), "memset cand_cnt");   // GROUP zeroes it per row
     if (two_pass) {
-        MTVQ_CUDA(cudaMemsetAsync(ws.ghist, 0, sizeof(int) * (pad_codes(k) / 128), st), "memset ghist");
+        if (di.num_sms > kGroupMaxCtas) return fail(MTVQ_ERR_UNSUPPORTED, "more SMs than the group tables hold%s", "");
         p.grp = ws.grp;
+        MTVQ_CUDA(cudaMemsetAsync(ws.gtot, 0, sizeof(int) * (pad_codes(k) / 128), st), "memset gtot");
         p.ghist = ws.ghist;
+        p.gtot = ws.gtot;
+        p.grank = ws.grank;
+        p.grank2 = ws.grank2;
         static int trace_group = -1;
         if (trace_group < 0) { const char* e = getenv("MTVQ_TRACE_GROUP"); trace_group = (e && e[0] == '1') ? 1 : 0; }
         if (trace_group) p.debug_flags |= 0x100;         // the pipeline trace (if set) records the GROUP pass, not REFINE

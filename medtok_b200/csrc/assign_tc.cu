@@ -1334,8 +1334,10 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                             p.grp[st[ss].row] = cb | ((other < 0 ? 0 : other) << kGrpOtherShift) |
                                                 ((other >= 0 && !unknown) ? kGrpCrossBit : 0) | (unknown ? kGrpOverBit : 0);
                             if (!unknown) {
-                                atomicAdd(&hist_s[cb], 1);
-                                if (other >= 0) atomicAdd(&hist_s[other], 1);
+                                // rank of the entry within this CTA's share of its chunk: the group sort then places every
+                                // entry without a single global atomic (base of (CTA, chunk) + rank)
+                                p.grank[st[ss].row] = atomicAdd(&hist_s[cb], 1);
+                                if (other >= 0) p.grank2[st[ss].row] = atomicAdd(&hist_s[other], 1);
                             }
                         }
                         // three or more chunks within the margin (or nothing finite): flagged + COLLECT, like ARGMAX's overflow
@@ -1462,11 +1464,12 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                 named_bar_sync(bar_id, bar_n);
             }
         }
-        if (MODE == MODE_GROUP) {      // the CTA's histogram goes to the global one (every row block has been counted)
+        if (MODE == MODE_GROUP) {      // the CTA's histogram (every row block has been counted) goes to its row of the table
             named_bar_sync(5, kEpiWarps * 32);
             for (int i = (int)tid_x; i < nchunks; i += kEpiWarps * 32) {
+                // reserve this CTA's share of the chunk: offset within the chunk's range, table [CTA][chunk]
                 const int h = hist_s[i];
-                if (h) atomicAdd(&p.ghist[i], h);
+                if (h) p.ghist[(size_t)blockIdx.x * nchunks + i] = atomicAdd(&p.gtot[i], h);
             }
         }
       }

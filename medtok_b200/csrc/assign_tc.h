@@ -64,7 +64,10 @@ struct CoarseParams {
     uint32_t     sbo_bytes;  // 128
     // two-pass hard route
     int*         grp;         // GROUP out [n]: best chunk | other chunk << 14 | kGrpCrossBit | kGrpOverBit
-    int*         ghist;       // GROUP out [kpad / 128]: sorted entries per chunk (zeroed by the caller)
+    int*         ghist;       // GROUP out [CTAs][kpad / 128]: offset of the CTA's share within the chunk's range of entries
+    int*         gtot;        // GROUP out [kpad / 128]: entries per chunk (zeroed by the caller)
+    int*         grank;       // GROUP out [n]: rank of the row's entry within its (CTA, chunk) share
+    int*         grank2;      //           [n]: the same for the second entry of a row listed under two chunks
     const int4*  entries;     // REFINE in: entries sorted by chunk {row | flags, best coarse score, row norm, 0}
     const int2*  tile_tab;    // REFINE in: per 128-entry tile {chunk | count << 16, first entry}
     const int*   n_tiles_dev; // REFINE in: number of tiles

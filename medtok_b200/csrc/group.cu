@@ -1,8 +1,8 @@
 // group.cu -- glue kernels of the two-pass hard route (assign_tc.h: MODE_GROUP -> here -> MODE_REFINE -> here).
 //
 // The GROUP tensor pass leaves, per row, the 128-code chunk holding its best coarse score (`grp`, plus a second chunk
-// for the few rows with a near-tie across chunks) and that score (`best_val`), and per chunk the number of entries
-// (`ghist`).  Here the rows are counting-sorted by chunk into 128-entry tiles for the REFINE pass (norm_ema_quantizer.py
+// for the few rows with a near-tie across chunks), that score (`best_val`), the rank of every entry within its (CTA,
+// chunk) share and the table of share sizes (`ghist`).  Here the rows are counting-sorted by chunk into 128-entry tiles for the REFINE pass (norm_ema_quantizer.py
 // :175-179 is still what is being computed: the argmin; the sort only makes the second look at a row a 128-code GEMM tile
 // instead of a scan), and after the exact re-scoring of the near-tie rows their share of :181,202,212-214 is added.
 #include "group.h"
@@ -13,15 +13,15 @@
 namespace mtvq {
 
 // one CTA: exclusive prefix sums of the entries and of the 128-entry tiles per chunk, then the tile table
-__global__ void __launch_bounds__(1024) group_scan_kernel(const int* __restrict__ ghist, int nchunks, int* __restrict__ goff,
-                                                           int* __restrict__ gcur, int* __restrict__ gtile,
-                                                           int2* __restrict__ tile_tab, int* __restrict__ counters) {
+__global__ void __launch_bounds__(1024) group_scan_kernel(const int* __restrict__ gtot, int nchunks, int* __restrict__ goff,
+                                                           int* __restrict__ gtile, int2* __restrict__ tile_tab,
+                                                           int* __restrict__ counters) {
     __shared__ int wtot_e[32], wtot_t[32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int per = (nchunks + 1023) / 1024;
     const int lo = min(nchunks, (int)threadIdx.x * per), hi = min(nchunks, lo + per);
     int se = 0, stl = 0;
-    for (int c = lo; c < hi; ++c) { const int h = ghist[c]; se += h; stl += (h + kTileRows - 1) / kTileRows; }
+    for (int c = lo; c < hi; ++c) { const int h = gtot[c]; se += h; stl += (h + kTileRows - 1) / kTileRows; }
     int ie = se, it = stl;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -43,96 +43,42 @@ __global__ void __launch_bounds__(1024) group_scan_kernel(const int* __restrict_
     int re = ie - se + (wid > 0 ? wtot_e[wid - 1] : 0);
     int rt = it - stl + (wid > 0 ? wtot_t[wid - 1] : 0);
     for (int c = lo; c < hi; ++c) {
-        const int h = ghist[c];
-        goff[c] = re; gcur[c] = re; gtile[c] = rt;
+        const int h = gtot[c];
+        goff[c] = re; gtile[c] = rt;
         re += h; rt += (h + kTileRows - 1) / kTileRows;
     }
     if (threadIdx.x == 1023) { gtile[nchunks] = wtot_t[31]; counters[CNT_TILES] = wtot_t[31]; }
     __syncthreads();
     // tile table: warp w takes chunks w, w + 32, ...; its lanes write the chunk's tiles side by side
     for (int c = wid; c < nchunks; c += 32) {
-        const int h = ghist[c], e0 = goff[c], t0 = gtile[c];
+        const int h = gtot[c], e0 = goff[c], t0 = gtile[c];
         const int nt = (h + kTileRows - 1) / kTileRows;
         for (int t = lane; t < nt; t += 32)
             tile_tab[t0 + t] = make_int2(c | (min(kTileRows, h - t * kTileRows) << 16), e0 + t * kTileRows);
     }
 }
 
-// rows -> 16-byte entries {row | flags, best coarse score, row norm, 0} at the next free position of their chunk.
-// Two levels, so that the few hot cursors (64 chunks at K = 8192) are not hammered by a million returning atomics: a CTA
-// ranks a segment of kSegRowsPerCta rows per chunk in shared memory, reserves one range per (segment, chunk) with a single
-// global atomic, and writes.  The second entry of a row listed under two chunks (a few percent) bumps the cursor directly.
-constexpr int kScatterThreads = 256;
-constexpr int kScatterPerThread = 16;
-constexpr int kSegRowsPerCta = kScatterThreads * kScatterPerThread;
-constexpr int kScatterSmemChunks = 2048;
-
-__global__ void __launch_bounds__(kScatterThreads) group_scatter_kernel(const int* __restrict__ grp, const float* __restrict__ best_val,
-                                                                        const float* __restrict__ denom, int64_t n, int nchunks,
-                                                                        int* __restrict__ gcur, int4* __restrict__ entries) {
-    extern __shared__ int sm_i[];
-    int* cnt_s = sm_i;                  // [nchunks] entries of this segment per chunk, then the reserved base
-    const int64_t nseg = (n + kSegRowsPerCta - 1) / kSegRowsPerCta;
-    for (int64_t seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
-        for (int c = threadIdx.x; c < nchunks; c += kScatterThreads) cnt_s[c] = 0;
-        __syncthreads();
-        const int64_t row0 = seg * kSegRowsPerCta + threadIdx.x;
-        int g[kScatterPerThread], rank[kScatterPerThread];
-#pragma unroll
-        for (int i = 0; i < kScatterPerThread; ++i) {
-            const int64_t row = row0 + (int64_t)i * kScatterThreads;
-            g[i] = row < n ? grp[row] : kGrpOverBit;
-        }
-#pragma unroll
-        for (int i = 0; i < kScatterPerThread; ++i)
-            rank[i] = (g[i] & kGrpOverBit) ? 0 : atomicAdd(&cnt_s[g[i] & ((1 << kGrpOtherShift) - 1)], 1);
-        __syncthreads();
-        for (int c = threadIdx.x; c < nchunks; c += kScatterThreads) {
-            const int h = cnt_s[c];
-            if (h) cnt_s[c] = atomicAdd(&gcur[c], h);
-        }
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < kScatterPerThread; ++i) {
-            if (g[i] & kGrpOverBit) continue;
-            const int64_t row = row0 + (int64_t)i * kScatterThreads;
-            const int mbits = __float_as_int(best_val[row]), dbits = __float_as_int(denom[row]);
-            const unsigned cross = (g[i] & kGrpCrossBit) ? kEntCross : 0u;
-            entries[cnt_s[g[i] & ((1 << kGrpOtherShift) - 1)] + rank[i]] = make_int4((int)((unsigned)row | cross), mbits, dbits, 0);
-            if (cross) {
-                const int other = (g[i] >> kGrpOtherShift) & ((1 << kGrpOtherShift) - 1);
-                entries[atomicAdd(&gcur[other], 1)] = make_int4((int)((unsigned)row | kEntCross | kEntSecond), mbits, dbits, 0);
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// the same for codebooks with many chunks (cursors are spread out: warp-aggregated bumps straight on the global cursors)
-__global__ void __launch_bounds__(256) group_scatter_direct_kernel(const int* __restrict__ grp, const float* __restrict__ best_val,
-                                                                    const float* __restrict__ denom, int64_t n,
-                                                                    int* __restrict__ gcur, int4* __restrict__ entries) {
-    const int lane = threadIdx.x & 31;
-    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x - lane; base < n; base += nthreads) {
-        const int64_t row = base + lane;
-        const int g = row < n ? grp[row] : kGrpOverBit;
-        const bool valid = !(g & kGrpOverBit);
-        const unsigned act = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
-            const int cb = g & ((1 << kGrpOtherShift) - 1);
-            const int mbits = __float_as_int(best_val[row]), dbits = __float_as_int(denom[row]);
-            const unsigned cross = (g & kGrpCrossBit) ? kEntCross : 0u;
-            const unsigned same = __match_any_sync(act, cb);
-            const int leader = __ffs(same) - 1;
-            int startp = 0;
-            if (lane == leader) startp = atomicAdd(&gcur[cb], __popc(same));
-            startp = __shfl_sync(same, startp, leader);
-            entries[startp + __popc(same & ((1u << lane) - 1))] = make_int4((int)((unsigned)row | cross), mbits, dbits, 0);
-            if (cross) {
-                const int other = (g >> kGrpOtherShift) & ((1 << kGrpOtherShift) - 1);
-                entries[atomicAdd(&gcur[other], 1)] = make_int4((int)((unsigned)row | kEntCross | kEntSecond), mbits, dbits, 0);
-            }
+// rows -> 16-byte entries {row | flags, best coarse score, row norm, 0} at (first entry of the chunk) + (offset of the
+// (CTA, chunk) share) + (rank within the share): the GROUP pass ranked every entry in shared memory and reserved its
+// shares with one atomic per (CTA, chunk), so placing the entries needs no atomics at all
+__global__ void __launch_bounds__(256) group_place_kernel(const int* __restrict__ grp, const int* __restrict__ grank,
+                                                           const int* __restrict__ grank2, const float* __restrict__ best_val,
+                                                           const float* __restrict__ denom, int64_t n, int nchunks, int nctas,
+                                                           int rows_per_block, const int* __restrict__ share0,
+                                                           const int* __restrict__ goff,
+                                                           int4* __restrict__ entries) {
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
+        const int g = grp[row];
+        if (g & kGrpOverBit) continue;
+        const int cta = (int)((row / rows_per_block) % nctas);       // the GROUP pass hands row block b to CTA b % nctas
+        const int cb = g & ((1 << kGrpOtherShift) - 1);
+        const int mbits = __float_as_int(best_val[row]), dbits = __float_as_int(denom[row]);
+        const unsigned cross = (g & kGrpCrossBit) ? kEntCross : 0u;
+        entries[goff[cb] + share0[(size_t)cta * nchunks + cb] + grank[row]] = make_int4((int)((unsigned)row | cross), mbits, dbits, 0);
+        if (cross) {
+            const int other = (g >> kGrpOtherShift) & ((1 << kGrpOtherShift) - 1);
+            entries[goff[other] + share0[(size_t)cta * nchunks + other] + grank2[row]] =
+                make_int4((int)((unsigned)row | kEntCross | kEntSecond), mbits, dbits, 0);
         }
     }
 }
@@ -175,22 +121,14 @@ __global__ void __launch_bounds__(256) finish_flagged_kernel(const float* __rest
 
 cudaError_t launch_group_sort(const Workspace& ws, const float* denom, int64_t n, int k, int num_sms, cudaStream_t s) {
     const int nchunks = pad_codes(k) / kTileCodes;
-    group_scan_kernel<<<1, 1024, 0, s>>>(ws.ghist, nchunks, ws.goff, ws.gcur, ws.gtile, static_cast<int2*>(ws.tile_tab),
-                                         ws.counters);
+    group_scan_kernel<<<1, 1024, 0, s>>>(ws.gtot, nchunks, ws.goff, ws.gtile, static_cast<int2*>(ws.tile_tab), ws.counters);
     ++g_kernel_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    int4* entries = static_cast<int4*>(ws.entries);
-    if (nchunks <= kScatterSmemChunks) {
-        const int64_t nseg = (n + kSegRowsPerCta - 1) / kSegRowsPerCta;
-        const int blocks = (int)(nseg < (int64_t)num_sms * 8 ? nseg : (int64_t)num_sms * 8);
-        group_scatter_kernel<<<blocks, kScatterThreads, sizeof(int) * nchunks, s>>>(ws.grp, ws.best_val, denom, n, nchunks,
-                                                                                   ws.gcur, entries);
-    } else {
-        const int64_t want = (n + 255) / 256;
-        const int blocks = (int)(want < (int64_t)num_sms * 8 ? want : (int64_t)num_sms * 8);
-        group_scatter_direct_kernel<<<blocks, 256, 0, s>>>(ws.grp, ws.best_val, denom, n, ws.gcur, entries);
-    }
+    const int64_t want = (n + 255) / 256;
+    const int blocks = (int)(want < (int64_t)num_sms * 16 ? want : (int64_t)num_sms * 16);
+    group_place_kernel<<<blocks, 256, 0, s>>>(ws.grp, ws.grank, ws.grank2, ws.best_val, denom, n, nchunks, num_sms, 4 * kTileRows,
+                                              ws.ghist, ws.goff, static_cast<int4*>(ws.entries));
     ++g_kernel_launches;
     return cudaGetLastError();
 }

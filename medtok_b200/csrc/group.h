@@ -7,8 +7,8 @@
 
 namespace mtvq {
 
-// ws.ghist (entries per chunk, from the GROUP pass) -> ws.goff / ws.gcur / ws.gtile, the tile table and
-// counters[CNT_TILES]; then ws.grp / ws.best_val / denom (the row norms the GROUP pass wrote) -> ws.entries sorted by chunk
+// ws.gtot (entries per chunk, from the GROUP pass) -> ws.goff / ws.gtile, the tile table and counters[CNT_TILES]; then ws.grp / ws.grank / ws.best_val / denom (the row norms the GROUP pass wrote) ->
+// ws.entries sorted by chunk, placed without atomics
 cudaError_t launch_group_sort(const Workspace& ws, const float* denom, int64_t n, int k, int num_sms, cudaStream_t s);
 
 // z_q / squared error / per-code sums of the rows only the exact full scan could decide (ws.full_rows; resolve_kernel

@@ -52,10 +52,12 @@ struct Workspace {
     int*     perm;         // [n]
     // two-pass hard route (assign_tc.h MODE_GROUP / MODE_REFINE, group.cu)
     int*     grp;          // [n]            per-row chunk word of the GROUP pass
-    int*     ghist;        // [kpad / 128]   entries per chunk | first entry | scatter cursor | first tile
-    int*     goff;
-    int*     gcur;
+    int*     ghist;        // [160][kpad / 128]  entries per (CTA of the GROUP pass, chunk), then the first entry of each share
+    int*     goff;         // [kpad / 128]   first entry | first tile of each chunk
     int*     gtile;
+    int*     gtot;         // [kpad / 128]   entries per chunk
+    int*     grank;        // [n]            rank of a row's entry within its (CTA, chunk) share (second entry: grank2)
+    int*     grank2;
     void*    entries;      // [2 n] int4     rows sorted by chunk (a near-tie row spanning two chunks is listed twice)
     void*    tile_tab;     // [group_tile_capacity] int2
     size_t   total_bytes;
@@ -65,6 +67,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline int    pad_codes(int k) { return (int)align_up((size_t)k, 128); }
 // near-tie candidates kept per row before the row falls back to the full exact scan
 inline int    cand_capacity(bool soft) { return soft ? 24 : 16; }
+constexpr int kGroupMaxCtas = 160;   // CTAs of the GROUP pass (one per SM)
 inline size_t group_tile_capacity(int64_t n, int k) { return (size_t)(2 * n / 128) + (size_t)(pad_codes(k) / 128) + 2; }
 inline size_t image_bytes(int d, int k) { return (size_t)(pad_codes(k) / 128) * (size_t)(d / 8 + 2) * 2048; }
 
@@ -118,10 +121,12 @@ inline Workspace carve(void* base, int64_t n, int d, int k, int topk) {
     w.small_part = take(small_route_fits(n, d, k) ? small_scratch_bytes(n, d, k, soft ? topk : 1) : 0);
     const size_t nchunks = (size_t)kpad / 128;
     w.grp       = (int*)take(sizeof(int) * n);
-    w.ghist     = (int*)take(sizeof(int) * nchunks);
+    w.ghist     = (int*)take(sizeof(int) * nchunks * kGroupMaxCtas);
     w.goff      = (int*)take(sizeof(int) * nchunks);
-    w.gcur      = (int*)take(sizeof(int) * nchunks);
     w.gtile     = (int*)take(sizeof(int) * (nchunks + 1));
+    w.gtot      = (int*)take(sizeof(int) * nchunks);
+    w.grank     = (int*)take(sizeof(int) * n);
+    w.grank2    = (int*)take(sizeof(int) * n);
     w.entries   = take(16 * (size_t)(2 * n));
     w.tile_tab  = take(8 * group_tile_capacity(n, k));
     w.total_bytes = off;
