@@ -199,8 +199,12 @@ int assign_rows(const float* z, int64_t n, int d, int norm_mode, const float* co
     c.n_rows_dev = ws.counters + CNT_OVER;
     c.denom = nullptr;
     MTVQ_CUDA(launch_coarse(c, MODE_COLLECT, 1, di.num_sms, st), "coarse collect");   // few rows: 128-row items
-    MTVQ_CUDA(launch_resolve(z, d, norm_mode, codes, k, ws, p.cand_cap, idx, di.num_sms, st,
-                             (two_pass && fused) ? fused->z_q : nullptr, (two_pass && fused) ? fused->stats : nullptr), "resolve");
+    if (two_pass) {
+        MTVQ_CUDA(launch_resolve8(z, denom, d, norm_mode, codes, k, ws, p.cand_cap, idx, di.num_sms, st,
+                                  fused ? fused->z_q : nullptr, fused ? fused->stats : nullptr), "resolve8");
+    } else {
+        MTVQ_CUDA(launch_resolve(z, d, norm_mode, codes, k, ws, p.cand_cap, idx, di.num_sms, st), "resolve");
+    }
     MTVQ_CUDA(launch_exact_scan(z, n, d, norm_mode, codes, k, ws.cc, ws.full_rows, ws.counters + CNT_FULL, idx, ws.bins_i32,
                                 nullptr, di.num_sms, st), "exact_scan(overflow)");
     if (two_pass && fused) {

@@ -142,8 +142,7 @@ __device__ __forceinline__ bool better(float v, int i, float bv, int bi) {
 __global__ void __launch_bounds__(kResWarps * 32, 4) resolve_kernel(
     const float* __restrict__ z, int d, int norm_mode, const float* __restrict__ w, int k, const float* __restrict__ cc,
     const int* __restrict__ flag_rows, const int* __restrict__ cand, const int* __restrict__ cand_cnt, int cand_cap,
-    int64_t* __restrict__ idx, int* __restrict__ bins, int* __restrict__ full_rows, int* __restrict__ counters,
-    float* __restrict__ z_q, double* __restrict__ stats) {
+    int64_t* __restrict__ idx, int* __restrict__ bins, int* __restrict__ full_rows, int* __restrict__ counters) {
     __shared__ __align__(16) float xs[kResWarps][kMaxDim];                  // normalised row per warp
     // granule slab per warp; row stride 36 floats keeps 16-byte accesses aligned and conflict free: within a
     // quarter-warp phase the 8 lanes' rows (or 8 consecutive float4 of a row) fall into 8 different bank quads
@@ -152,7 +151,6 @@ __global__ void __launch_bounds__(kResWarps * 32, 4) resolve_kernel(
     const int nflag = counters[CNT_FLAGGED];
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     int ncands = 0;
-    double sse = 0.0;
     for (int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < nflag; p += nwarps) {
         const int row = flag_rows[p];
         // candidate lists are indexed by row; the count word has two fields (assign_tc.h kCandBackShift): columns listed
@@ -289,17 +287,125 @@ __global__ void __launch_bounds__(kResWarps * 32, 4) resolve_kernel(
                 full_rows[atomicAdd(&counters[CNT_FULL], 1)] = row;
             }
         }
-        // two-pass route, fused rows: the row's share of :181,202,212-214 right here -- the normalised row is in shared
-        // memory and the winner is known (the REFINE pass did this for the rows it decided itself)
-        if (z_q != nullptr && bcol != 0x7fffffff) {
+    }
+    __syncwarp();
+    ncands = __reduce_add_sync(0xffffffffu, ncands);
+    if (lane == 0 && ncands) atomicAdd(&counters[CNT_CANDS], ncands);
+}
+
+// ------------------------------------------------------------------------------------------------
+// resolve for the two-pass route: every candidate is a single column (at most cand_cap <= 16 per row, 2-3 on average)
+// and the row norms are known (the GROUP pass wrote them), so a whole warp per row leaves most lanes idle.  Eight lanes
+// per row, four rows per warp: lane v of a group scores candidates v and v + 8 (the same sequential fmaf chain, the same
+// canon_sumsq chains -- four per lane -- and fold order), three shuffle rounds pick the lexicographic minimum, and the
+// group finishes the row (z_q, squared error, per-code sums) when the fused outputs are wanted.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 4) resolve8_kernel(
+    const float* __restrict__ z, const float* __restrict__ denom, int d, int norm_mode, const float* __restrict__ w, int k,
+    const float* __restrict__ cc, const int* __restrict__ flag_rows, const int* __restrict__ cand,
+    const int* __restrict__ cand_cnt, int cand_cap, int64_t* __restrict__ idx, int* __restrict__ bins,
+    int* __restrict__ full_rows, int* __restrict__ counters, float* __restrict__ z_q, double* __restrict__ stats) {
+    __shared__ __align__(16) float xs_all[8][4][kMaxDim];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, g = lane >> 3, v = lane & 7;
+    float* xs = xs_all[wib][g];
+    const int nflag = counters[CNT_FLAGGED];
+    const int ngroups = (gridDim.x * blockDim.x) >> 3;
+    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int rounds = (nflag + ngroups - 1) / ngroups;          // warp-uniform trip count (the shuffles below are full-warp)
+    const bool dots = score_dot(norm_mode);
+    const int nv4 = d >> 2, nvec = d >> 3, n4 = nvec >> 2;
+    int ncands = 0;
+    double sse = 0.0;
+    for (int it = 0; it < rounds; ++it) {
+        const int p = gid + it * ngroups;
+        const bool active = p < nflag;
+        const int row = active ? flag_rows[p] : 0;
+        const unsigned cw = active ? (unsigned)cand_cnt[row] : 0u;
+        const int nfront = (int)(cw & ((1u << kCandBackShift) - 1u)), nback = (int)(cw >> kCandBackShift);
+        const int cnt = nfront + nback;
+        const bool ok = active && cnt > 0 && cnt <= cand_cap;
+        __syncwarp();
+        if (ok) {
+            const float4* zr = reinterpret_cast<const float4*>(z + (size_t)row * d);
+            for (int j = v; j < nv4; j += 8) reinterpret_cast<float4*>(xs)[j] = __ldg(zr + j);
+        }
+        const float den = ok ? denom[row] : 1.0f;
+        __syncwarp();
+        if (ok)
+            for (int i = v; i < d; i += 8) xs[i] = __fdiv_rn(xs[i], den);
+        __syncwarp();
+        // canon_sumsq: lane v runs the chains acc[0..3][v], folds them in order, the eight lanes are then added in order
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        if (ok && !dots) {
+            for (int c = 0; c < n4; ++c) {
+                const float e0 = xs[(c * 4 + 0) * 8 + v], e1 = xs[(c * 4 + 1) * 8 + v], e2 = xs[(c * 4 + 2) * 8 + v],
+                            e3 = xs[(c * 4 + 3) * 8 + v];
+                a0 = __fadd_rn(a0, __fmul_rn(e0, e0)); a1 = __fadd_rn(a1, __fmul_rn(e1, e1));
+                a2 = __fadd_rn(a2, __fmul_rn(e2, e2)); a3 = __fadd_rn(a3, __fmul_rn(e3, e3));
+            }
+            for (int i = n4 * 4; i < nvec; ++i) { const float e = xs[i * 8 + v]; a0 = __fadd_rn(a0, __fmul_rn(e, e)); }
+            a0 = __fadd_rn(__fadd_rn(__fadd_rn(a0, a1), a2), a3);
+        }
+        float zz = 0.0f;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) zz = __fadd_rn(zz, __shfl_sync(0xffffffffu, a0, (lane & 24) + t));
+        if (dots) zz = 0.0f;
+        float best = 0.0f;
+        int bcol = 0x7fffffff;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int ci = v + 8 * r;
+            if (ok && ci < cnt) {
+                const int code = cand[(size_t)row * cand_cap + (ci < nfront ? ci : cand_cap - 1 - (ci - nfront))];
+                if (code >= 0 && code < k) {
+                    const float4* wr = reinterpret_cast<const float4*>(w + (size_t)code * d);
+                    float dot = 0.0f;
+                    for (int i0 = 0; i0 < nv4; i0 += 4) {        // d % 16 == 0: four 16-byte loads in flight per step
+                        float4 wv[4];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) wv[t] = __ldg(wr + i0 + t);
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const float4 xv = *reinterpret_cast<const float4*>(&xs[4 * (i0 + t)]);
+                            dot = __fmaf_rn(xv.x, wv[t].x, dot);
+                            dot = __fmaf_rn(xv.y, wv[t].y, dot);
+                            dot = __fmaf_rn(xv.z, wv[t].z, dot);
+                            dot = __fmaf_rn(xv.w, wv[t].w, dot);
+                        }
+                    }
+                    const float dist = canon_dist(zz, dots ? 0.0f : cc[code], dot);
+                    if (better(dist, code, best, bcol)) { best = dist; bcol = code; }
+                    ++ncands;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {                        // stays inside the eight-lane group
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bcol, o);
+            if (better(ov, oi, best, bcol)) { best = ov; bcol = oi; }
+        }
+        if (active && v == 0) {
+            if (bcol != 0x7fffffff) {
+                idx[row] = (int64_t)bcol;
+                atomicAdd(&bins[bcol], 1);
+            } else {
+                full_rows[atomicAdd(&counters[CNT_FULL], 1)] = row;      // empty / overflowing list, NaN distances
+            }
+        }
+        if (z_q != nullptr && ok && bcol != 0x7fffffff) {
             double* esum = stats + k + (size_t)bcol * d;
-            const float* wr = w + (size_t)bcol * d;
-            for (int i = lane; i < d; i += 32) {
-                const float zf = xs[wib][i];
-                const float dd = __fsub_rn(__ldg(wr + i), zf);
-                sse += (double)__fmul_rn(dd, dd);
-                z_q[(size_t)row * d + i] = __fadd_rn(zf, dd);
-                atomicAdd(esum + i, (double)zf);
+            const float4* wr = reinterpret_cast<const float4*>(w + (size_t)bcol * d);
+            for (int j = v; j < nv4; j += 8) {
+                const float4 zf = reinterpret_cast<const float4*>(xs)[j];
+                const float4 c = __ldg(wr + j);
+                const float d0 = __fsub_rn(c.x, zf.x), d1 = __fsub_rn(c.y, zf.y), d2 = __fsub_rn(c.z, zf.z), d3 = __fsub_rn(c.w, zf.w);
+                sse += (double)__fmul_rn(d0, d0) + (double)__fmul_rn(d1, d1) + (double)__fmul_rn(d2, d2) + (double)__fmul_rn(d3, d3);
+                float4 o;
+                o.x = __fadd_rn(zf.x, d0); o.y = __fadd_rn(zf.y, d1); o.z = __fadd_rn(zf.z, d2); o.w = __fadd_rn(zf.w, d3);
+                reinterpret_cast<float4*>(z_q + (size_t)row * d)[j] = o;
+                atomicAdd(esum + 4 * j + 0, (double)zf.x); atomicAdd(esum + 4 * j + 1, (double)zf.y);
+                atomicAdd(esum + 4 * j + 2, (double)zf.z); atomicAdd(esum + 4 * j + 3, (double)zf.w);
             }
         }
     }
@@ -460,11 +566,20 @@ cudaError_t launch_codebook_prep(const float* w, int k, int d, int flags, const 
     return cudaGetLastError();
 }
 
+cudaError_t launch_resolve8(const float* z, const float* denom, int d, int norm_mode, const float* w, int k,
+                            const Workspace& ws, int cand_cap, int64_t* idx, int num_sms, cudaStream_t stream, float* z_q,
+                            double* stats) {
+    resolve8_kernel<<<num_sms * 4, 256, 0, stream>>>(z, denom, d, norm_mode, w, k, ws.cc, ws.flag_rows, ws.cand, ws.cand_cnt,
+                                                     cand_cap, idx, ws.bins_i32, ws.full_rows, ws.counters, z_q, stats);
+    ++g_kernel_launches;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_resolve(const float* z, int d, int norm_mode, const float* w, int k, const Workspace& ws,
-                           int cand_cap, int64_t* idx, int num_sms, cudaStream_t stream, float* z_q, double* stats) {
+                           int cand_cap, int64_t* idx, int num_sms, cudaStream_t stream) {
     resolve_kernel<<<num_sms * 4, kResWarps * 32, 0, stream>>>(z, d, norm_mode, w, k, ws.cc, ws.flag_rows, ws.cand,
                                                                 ws.cand_cnt, cand_cap, idx, ws.bins_i32, ws.full_rows,
-                                                                ws.counters, z_q, stats);
+                                                                ws.counters);
     ++g_kernel_launches;
     return cudaGetLastError();
 }

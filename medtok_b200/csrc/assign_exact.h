@@ -15,10 +15,13 @@ cudaError_t launch_codebook_prep(const float* w, int k, int d, int flags, const 
 
 // near-tie rows (ws.flag_rows / counters[CNT_FLAGGED]) x their collected candidates -> idx[row] (int64) and
 // ws.bins_i32; rows whose candidate list is empty or overflowed go to ws.full_rows / counters[CNT_FULL]
-// z_q / stats non-null (two-pass route, fused rows): also z_q, squared error and per-code sums of the rows decided here
 cudaError_t launch_resolve(const float* z, int d, int norm_mode, const float* w, int k, const Workspace& ws,
-                           int cand_cap, int64_t* idx, int num_sms, cudaStream_t stream, float* z_q = nullptr,
-                           double* stats = nullptr);
+                           int cand_cap, int64_t* idx, int num_sms, cudaStream_t stream);
+// the same for lists of single columns and known row norms (two-pass route): eight lanes per row, four rows per warp;
+// z_q / stats non-null (fused rows): also z_q, squared error and per-code sums of the rows decided here
+cudaError_t launch_resolve8(const float* z, const float* denom, int d, int norm_mode, const float* w, int k,
+                            const Workspace& ws, int cand_cap, int64_t* idx, int num_sms, cudaStream_t stream,
+                            float* z_q = nullptr, double* stats = nullptr);
 
 // exact first-index argmin over ALL k codes for the rows in row_list (or rows [0,n) when null) -> idx[row]
 // (int64) and, when bins != nullptr, the per-code counts of those rows
