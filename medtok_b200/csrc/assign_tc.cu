@@ -1498,12 +1498,26 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_kernel(const CoarseParams 
                     } else if (norm_kind(p.norm_mode) == 0) {
                         // canon_norm8 on float4 loads: lane v accumulates x[8c+v]^2 in order of c
                         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f;
-                        for (int j = 0; j < nplanes; ++j) {
-                            const float4 x0 = __ldg(zr4 + 2 * j), x1 = __ldg(zr4 + 2 * j + 1);
-                            a0 = __fadd_rn(a0, __fmul_rn(x0.x, x0.x)); a1 = __fadd_rn(a1, __fmul_rn(x0.y, x0.y));
-                            a2 = __fadd_rn(a2, __fmul_rn(x0.z, x0.z)); a3 = __fadd_rn(a3, __fmul_rn(x0.w, x0.w));
-                            a4 = __fadd_rn(a4, __fmul_rn(x1.x, x1.x)); a5 = __fadd_rn(a5, __fmul_rn(x1.y, x1.y));
-                            a6 = __fadd_rn(a6, __fmul_rn(x1.z, x1.z)); a7 = __fadd_rn(a7, __fmul_rn(x1.w, x1.w));
+                        // four planes (eight 16-byte loads) in flight at a time: one thread reads a whole row, and with one
+                        // plane per iteration every iteration exposed a DRAM round trip (~10 us per tile)
+                        for (int j0 = 0; j0 < nplanes; j0 += 4) {
+                            float4 x[8];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const bool in = j0 + u < nplanes;
+                                x[2 * u] = in ? __ldg(zr4 + 2 * (j0 + u)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                x[2 * u + 1] = in ? __ldg(zr4 + 2 * (j0 + u) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                if (j0 + u < nplanes) {      // (in order of the planes: the canonical accumulation order)
+                                    const float4 x0 = x[2 * u], x1 = x[2 * u + 1];
+                                    a0 = __fadd_rn(a0, __fmul_rn(x0.x, x0.x)); a1 = __fadd_rn(a1, __fmul_rn(x0.y, x0.y));
+                                    a2 = __fadd_rn(a2, __fmul_rn(x0.z, x0.z)); a3 = __fadd_rn(a3, __fmul_rn(x0.w, x0.w));
+                                    a4 = __fadd_rn(a4, __fmul_rn(x1.x, x1.x)); a5 = __fadd_rn(a5, __fmul_rn(x1.y, x1.y));
+                                    a6 = __fadd_rn(a6, __fmul_rn(x1.z, x1.z)); a7 = __fadd_rn(a7, __fmul_rn(x1.w, x1.w));
+                                }
+                            }
                         }
                         float s = a0;
                         s = __fadd_rn(s, a1); s = __fadd_rn(s, a2); s = __fadd_rn(s, a3);
