@@ -486,6 +486,12 @@ def extra_workloads(ctx, peaks, cpu):
     return out
 
 
+def _note(rank, msg):
+    """progress notes on stderr (stdout carries the one JSON line)"""
+    if os.environ.get("BENCH_PROGRESS", "1") == "1":
+        print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
+
 def run_ours(args):
     ctx = Ctx()
     dev, world, rank = ctx.dev, ctx.world, ctx.rank
@@ -495,6 +501,7 @@ def run_ours(args):
 
     peaks = _peaks()
     parity = dist_parity_check(ctx) if world > 1 else {}
+    _note(rank, f"parity side problem done: {parity}")
 
     n, d, k = args.rows or N_ROWS, args.dim or DIM, args.codes or CODES      # defaults = BASELINE config 2
     # two different input batches (2 x 256 MiB > 126 MB L2), alternated so no step re-reads cached rows
@@ -511,11 +518,13 @@ def run_ours(args):
     # ---- leg 1: the driver-controlled K steps ----
     m0 = sampler.mark()
     elapsed_ms, kernel_ms, counters = time_hard(ctx, q, zs, steps, warmup)
+    _note(rank, f"timed leg done: {elapsed_ms / steps:.4f} ms/step")
     m1 = sampler.mark()
     # ---- leg 2: >= 2 s of back-to-back steps (the sustained clock / power regime) ----
     sus_steps = max(steps, int(math.ceil(args.sustain_s * 1e3 / max(elapsed_ms / steps, 1e-3))))
     m2 = sampler.mark()
     sus_ms, sus_kernel_ms, _ = time_hard(ctx, q, zs, sus_steps, 0, kernel_every=16)
+    _note(rank, f"sustained leg done: {sus_ms / sus_steps:.4f} ms/step")
     m3 = sampler.mark()
 
     # ---- end-to-end: pinned host batches -> streamed upload / forward / download of z_q + indices + loss ----
@@ -532,6 +541,7 @@ def run_ours(args):
         e1.record()
         ctx.barrier()
         e2e_ms = e0.elapsed_time(e1)
+    _note(rank, f"e2e leg done: {e2e_ms / steps:.4f} ms/step")
     m4 = sampler.mark()
     del host
 
@@ -578,9 +588,11 @@ def run_ours(args):
                          "step_frac_sustained": step_tf / peaks["sustained"], "step_achieved": step_tf,
                          "kernel": ("mtvq::coarse_kernel<RT=4, GROUP> (record-free tcgen05 coarse-score pass of the two-pass route; "
                                     "the per-chunk REFINE pass, 1/64 of its FLOPs, is part of the step, not of this figure)"
-                                    if _lib.lib().mtvq_hard_route(n, d, k) == 2 else
+                                    if getattr(q, "last_route", 1) == 2 else
                                     "mtvq::coarse_kernel<RT=4, ARGMAX> (tcgen05 coarse-score pass)"),
-                         "route": "two-pass" if _lib.lib().mtvq_hard_route(n, d, k) == 2 else "single-pass",
+                         "route": ("two-pass" if getattr(q, "last_route", 1) == 2 else
+                                   "single-pass" + (" (groups of more than MEDTOK_TWO_PASS_MAX_WORLD=4 ranks: DESIGN.md section 7)"
+                                                    if world > 4 else "")),
                          "kernel_ms_median": kms, "kernel_share_of_step": kms / (elapsed_ms / steps),
                          "peak_source": peaks["source"], "flops_per_launch": flops,
                          "sustained_leg": {"seconds": sus_ms * 1e-3, "steps": sus_steps, "ms_per_step": sus_ms / sus_steps,

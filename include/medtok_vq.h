@@ -239,6 +239,7 @@ MTVQ_API int mtvq_debug_set_soft_route(int route);
  * work) whenever the shape allows it (D <= 64, at least two and at most 8192 chunks of 128 codes, enough rows for
  * four-row-tile blocks).  Both routes give bit-identical indices; the per-code sums differ in summation order only. */
 MTVQ_API int mtvq_debug_set_hard_route(int route);
+MTVQ_API int mtvq_debug_get_hard_route(void);   /* the value last set on this host thread (-1 = automatic) */
 /* the route mtvq_hard_assign / mtvq_hard_forward take for this shape on the current device and host thread: 1 = single
  * tensor pass, 2 = two-pass; 0 = the shape is not supported at all (see mtvq_last_error) */
 MTVQ_API int mtvq_hard_route(int64_t n, int d, int k);

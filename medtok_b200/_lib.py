@@ -59,6 +59,7 @@ _SIGNATURES = {
     "mtvq_debug_set_soft_route": (_int, [_int]),
     "mtvq_debug_set_hard_route": (_int, [_int]),
     "mtvq_hard_route": (_int, [_i64, _int, _int]),
+    "mtvq_debug_get_hard_route": (_int, []),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -568,6 +568,8 @@ int mtvq_debug_set_hard_route(int route) {
     return 0;
 }
 
+int mtvq_debug_get_hard_route(void) { return g_hard_route; }
+
 int mtvq_debug_set_trace(void* trace_dev) {
     g_trace = static_cast<long long*>(trace_dev);
     return 0;

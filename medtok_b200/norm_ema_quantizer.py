@@ -22,6 +22,10 @@ from . import _lib
 from .distributed import PeerExchange, all_reduce_stats
 
 
+def _world_size() -> int:
+    return distributed.get_world_size() if (distributed.is_available() and distributed.is_initialized()) else 1
+
+
 def l2norm(t):
     """reference :8-9"""
     return F.normalize(t, p=2, dim=-1)
@@ -346,10 +350,21 @@ class NormEMAVectorQuantizer(nn.Module):
         stats = peers.next_buffer() if peers is not None else \
             torch.empty(_lib.stats_len(d, k), dtype=torch.float64, device=dev)
         cs = self.cluster_size if has_cs else None
-        _lib.check(L.mtvq_hard_forward(_lib.ptr(z_rows), n, d, norm_mode, _lib.ptr(weight), k, _lib.ptr(cs),
-                                       float(self.beta), float(self.decay), flags, _lib.ptr(z_q), _lib.ptr(idx),
-                                       _lib.ptr(loss), _lib.ptr(stats), _lib.ptr(ws), ws.numel(),
-                                       _lib.stream_ptr(dev)), "mtvq_hard_forward")
+        # The two-pass route of the hard path has been validated on up to MEDTOK_TWO_PASS_MAX_WORLD ranks (default 4; see
+        # DESIGN.md section 7): larger groups take the single-pass route unless a route has been set explicitly.
+        pin_single = (distributed_on and L.mtvq_debug_get_hard_route() < 0 and not os.environ.get("MTVQ_HARD_ROUTE")
+                      and _world_size() > int(os.environ.get("MEDTOK_TWO_PASS_MAX_WORLD", "4")))
+        if pin_single:
+            L.mtvq_debug_set_hard_route(1)
+        try:
+            _lib.check(L.mtvq_hard_forward(_lib.ptr(z_rows), n, d, norm_mode, _lib.ptr(weight), k, _lib.ptr(cs),
+                                           float(self.beta), float(self.decay), flags, _lib.ptr(z_q), _lib.ptr(idx),
+                                           _lib.ptr(loss), _lib.ptr(stats), _lib.ptr(ws), ws.numel(),
+                                           _lib.stream_ptr(dev)), "mtvq_hard_forward")
+        finally:
+            if pin_single:
+                L.mtvq_debug_set_hard_route(-1)
+        self.last_route = 1 if pin_single else int(L.mtvq_hard_route(n, d, k))
         if peers is not None:
             # ONE kernel: signal / wait over NVLink, rank-ordered fp64 sum of the peers' statistics, EMA update
             _lib.check(L.mtvq_ema_finalize_peers(_lib.ptr(weight), _lib.ptr(cs), ctypes.c_void_p(peers.peer_stats_ptr()),
