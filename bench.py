@@ -486,6 +486,15 @@ def extra_workloads(ctx, peaks, cpu):
     return out
 
 
+def sustained_steps(max_over_ranks, elapsed_ms, steps, sustain_s):
+    """Step count of the sustained leg.  It must be the SAME on every rank -- each step is a rendezvous in the exchange,
+    so a rank that ran one step more than a peer would wait for statistics that never come -- hence it is derived from
+    the max-over-ranks time of the driver leg, not from this rank's own event pair (whose microsecond skew can straddle
+    a ceil() boundary: at 8 ranks that hung one r02b run inside the exchange)."""
+    worst = max_over_ranks([elapsed_ms])[0]
+    return max(steps, int(math.ceil(sustain_s * 1e3 / max(worst / steps, 1e-3))))
+
+
 def _note(rank, msg):
     """progress notes on stderr (stdout carries the one JSON line)"""
     if os.environ.get("BENCH_PROGRESS", "1") == "1":
@@ -521,7 +530,7 @@ def run_ours(args):
     _note(rank, f"timed leg done: {elapsed_ms / steps:.4f} ms/step")
     m1 = sampler.mark()
     # ---- leg 2: >= 2 s of back-to-back steps (the sustained clock / power regime) ----
-    sus_steps = max(steps, int(math.ceil(args.sustain_s * 1e3 / max(elapsed_ms / steps, 1e-3))))
+    sus_steps = sustained_steps(ctx.max_over_ranks, elapsed_ms, steps, args.sustain_s)
     m2 = sampler.mark()
     sus_ms, sus_kernel_ms, _ = time_hard(ctx, q, zs, sus_steps, 0, kernel_every=16)
     _note(rank, f"sustained leg done: {sus_ms / sus_steps:.4f} ms/step")
