@@ -502,6 +502,9 @@ def _note(rank, msg):
 
 
 def run_ours(args):
+    # a rank waiting inside the fused exchange for statistics that never come traps after this many seconds (library
+    # default 600): the ranks of a bench run are never more than seconds apart, so fail fast instead of hanging
+    os.environ.setdefault("MEDTOK_EXCHANGE_TIMEOUT_S", "180")
     ctx = Ctx()
     dev, world, rank = ctx.dev, ctx.world, ctx.rank
     from medtok_b200 import _lib
