@@ -52,3 +52,29 @@ def test_sustained_leg_never_shorter_than_the_driver_leg():
     import bench
     assert bench.sustained_steps(lambda v: v, 5000.0, 20, 2.2) == 20          # 250 ms steps: 20 steps already exceed 2.2 s
     assert bench.sustained_steps(lambda v: v, 26.0, 20, 2.2) == math.ceil(2200 / 1.3)
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's own CPU path on the host cores) needs no GPU: one step of its
+    bounded sample, checked for the keys the driver reads."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["higher_is_better"] is True and line["vs_baseline"] is None
+    assert line["metric"] == "quantized embeddings/sec (fwd+EMA)" and line["unit"] == "embeddings/s"
+    assert line["value"] > 0 and line["steps"] == 1 and line["n_gpus"] == 1
+    assert "BASELINE config 2" in line["config"]["workload"]
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_reference_arm_other_ranks_exit_without_work():
+    import subprocess
+    env = dict(os.environ, RANK="3", WORLD_SIZE="8", LOCAL_RANK="3")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "8"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
