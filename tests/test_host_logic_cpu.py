@@ -107,3 +107,99 @@ def test_groups_above_the_validated_size_pin_the_single_pass_route():
 def test_an_explicit_route_is_never_overridden():
     for names, flags, last_route, pinned in _spawn(2, 29775, {"MEDTOK_TWO_PASS_MAX_WORLD": "1", "MTVQ_HARD_ROUTE": "2"}):
         assert "mtvq_debug_set_hard_route" not in names
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Soft quantizer: structure of the forward dict against the UNMODIFIED reference run live on CPU (same inputs): every
+# key the reference returns, with the same container types, tensor shapes and dtypes; plus the token keys
+# tokenizer.py:235-238 reads.  Values are NOT compared here (the recorder computes nothing; tests/test_gpu_soft.py does).
+# ------------------------------------------------------------------------------------------------------------------
+def _structure(v):
+    if isinstance(v, torch.Tensor):
+        return ("tensor", tuple(v.shape), str(v.dtype))
+    if isinstance(v, (tuple, list)):
+        return ("tuple", tuple(_structure(x) for x in v))
+    if v is None:
+        return ("none",)
+    return (type(v).__name__,)
+
+
+def _soft_inputs(e_dim, bsz=6, tokens=7, nodes=15):
+    g = torch.Generator().manual_seed(5)
+    z = torch.randn(bsz, 2 * e_dim, generator=g)
+    z_aug = torch.randn(bsz, 2 * e_dim, generator=g)
+    text = torch.randn(bsz, tokens, e_dim, generator=g)
+    graph = torch.randn(nodes, e_dim, generator=g)
+    mask = torch.ones(bsz, tokens, dtype=torch.long)
+    mask[1, 4:] = 0
+    mask[3, 2:] = 0
+    batch = torch.tensor([0, 0, 0, 1, 1, 2, 2, 2, 3, 3, 4, 4, 5, 5, 5])
+    return z, text, graph, mask, batch, z_aug
+
+
+def _soft_structure(queue, training):
+    import contextlib
+    import io
+    _lib, rec, _ = _patched_module()
+    from medtok_b200.vector_quantization_soft_one_new import VectorQuantizer
+    e_dim, n_e, k = 32, 96, 5
+    with contextlib.redirect_stdout(io.StringIO()):
+        ours = VectorQuantizer(n_e=n_e, e_dim=e_dim, beta=0.25, entropy_loss_ratio=0.0, l2_norm=True, show_usage=True,
+                               split=[e_dim, e_dim], k=k).train(training)
+    z, text, graph, mask, batch, z_aug = _soft_inputs(e_dim)
+    out = ours(z, text, graph, mask, batch, z_aug=z_aug if training else None)
+    result = {"ours": {key: _structure(v) for key, v in out.items()}, "calls": rec.names(), "ref": None}
+    if training:                                   # the backward reaches the fused kernel and hands gradients on
+        loss = out["specific_embedding_text"].sum() + out["text_specific_loss"][0] + out["shared_embed_loss"][1]
+        loss.backward()
+        result["grads"] = {"codebook": _structure(ours.codebook.weight.grad), "proj_text": _structure(ours.proj_text.weight.grad)}
+        result["calls_bwd"] = [n for n in rec.names() if "backward" in n]
+    from oracle import ref_loader
+    if ref_loader.available():
+        with contextlib.redirect_stdout(io.StringIO()):
+            _, soft = ref_loader.load()
+            ref = soft.VectorQuantizer(n_e=n_e, e_dim=e_dim, beta=0.25, entropy_loss_ratio=0.0, l2_norm=True,
+                                       show_usage=True, split=[e_dim, e_dim], k=k).train(training)
+        del ref._buffers["codebook_used"]          # harness accommodation of SURVEY Appendix B-3 (oracle/make_golden.py)
+        ref.register_buffer("codebook_used", torch.zeros(300000))
+        rout = ref(z, text, graph, mask, batch, z_aug=z_aug if training else None)
+        result["ref"] = {key: _structure(v) for key, v in rout.items()}
+    queue.put(result)
+
+
+def _run_soft(training):
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    p = ctx.Process(target=_soft_structure, args=(queue, training))
+    p.start()
+    res = queue.get(timeout=300)
+    p.join(timeout=60)
+    assert p.exitcode == 0
+    return res
+
+
+def test_soft_forward_dict_has_the_reference_structure_train():
+    res = _run_soft(True)
+    ours, ref = res["ours"], res["ref"]
+    # 2 shared passes + 2 specific + 2 augmented specific passes, each followed by its usage-window update where the
+    # reference has one (shared: one update for both modalities)
+    assert res["calls"].count("mtvq_soft_forward") == 6 and res["calls"].count("mtvq_codebook_usage") == 5
+    assert res["calls_bwd"] and set(res["calls_bwd"]) == {"mtvq_soft_backward_fused"}
+    assert res["grads"]["codebook"] == ("tensor", (96, 32), "torch.float32")
+    assert res["grads"]["proj_text"] == ("tensor", (32, 32), "torch.float32")
+    for key in ("text_tokens", "graph_tokens", "shared_text_tokens", "shared_graph_tokens"):
+        assert ours[key] == ("tensor", (6, 5), "torch.int64")
+        assert ours[key + "_weights"] == ("tensor", (6, 5), "torch.float32")
+    if ref is not None:
+        for key, st in ref.items():
+            assert ours[key] == st, f"{key}: ours {ours[key]} vs reference {st}"
+
+
+def test_soft_forward_dict_has_the_reference_structure_eval():
+    res = _run_soft(False)
+    ours, ref = res["ours"], res["ref"]
+    assert res["calls"].count("mtvq_soft_forward") == 4
+    assert ours["specific_embedding_text_aug"] == ("none",) and ours["specific_embedding_graph_aug"] == ("none",)
+    if ref is not None:
+        for key, st in ref.items():
+            assert ours[key] == st, f"{key}: ours {ours[key]} vs reference {st}"
