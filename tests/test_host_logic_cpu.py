@@ -203,3 +203,69 @@ def test_soft_forward_dict_has_the_reference_structure_eval():
     if ref is not None:
         for key, st in ref.items():
             assert ours[key] == st, f"{key}: ours {ours[key]} vs reference {st}"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Hard quantizers: return tuple of forward against the UNMODIFIED reference run live on CPU (structure only).
+# ------------------------------------------------------------------------------------------------------------------
+def _hard_structure(queue):
+    import contextlib
+    import io
+    _lib, rec, mod = _patched_module()
+    from oracle import ref_loader
+    hard = None
+    if ref_loader.available():
+        with contextlib.redirect_stdout(io.StringIO()):
+            hard, _ = ref_loader.load()
+    out = []
+    g = torch.Generator().manual_seed(3)
+    for shape, training in (((40, 64, 1, 1), True), ((5, 32, 4, 3), True), ((40, 64, 1, 1), False)):
+        z = torch.randn(*shape, generator=g)
+        k, d = 128, shape[1]
+        ours = mod.NormEMAVectorQuantizer(k, d, 0.25).train(training)
+        with torch.no_grad():
+            o = ours(z)
+        r = None
+        if hard is not None:
+            ref = hard.NormEMAVectorQuantizer(n_embed=k, embedding_dim=d, beta=0.25).train(training)
+            with torch.no_grad():
+                r = ref(z)
+        out.append(("hard", shape, training, _structure(o), None if r is None else _structure(r),
+                    sorted(ours.state_dict().keys()), None if r is None else sorted(ref.state_dict().keys())))
+    # lookup-only quantizer: code indices in, codebook rows out (reference :222-268)
+    for bhw, d, with_z, training in (((6, 4, 3), 32, True, True), ((6, 4, 3), 32, False, False), ((10, 1, 1), 64, True, False)):
+        k = 50
+        idx = torch.randint(0, k, (bhw[0] * bhw[1] * bhw[2],), generator=g)
+        z = torch.randn(bhw[0], d, bhw[1], bhw[2], generator=g) if with_z else None
+        ours = mod.VectorQuantizer(k, d, 0.25).train(training)
+        with torch.no_grad():
+            o = ours(bhw, idx, z)
+        r = None
+        if hard is not None:
+            ref = hard.VectorQuantizer(n_embed=k, embedding_dim=d, beta=0.25).train(training)
+            with torch.no_grad():
+                r = ref(bhw, idx, z)
+        out.append(("lookup", bhw, training, _structure(o), None if r is None else _structure(r),
+                    sorted(ours.state_dict().keys()), None if r is None else sorted(ref.state_dict().keys())))
+    queue.put((out, rec.names()))
+
+
+def test_hard_quantizers_return_the_reference_structure():
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    p = ctx.Process(target=_hard_structure, args=(queue,))
+    p.start()
+    cases, calls = queue.get(timeout=300)
+    p.join(timeout=60)
+    assert p.exitcode == 0
+    assert calls.count("mtvq_hard_forward") == 3 and calls.count("mtvq_lookup") == 3
+    for kind, shape, training, ours, ref, keys, ref_keys in cases:
+        assert ours[0] == "tuple" and len(ours[1]) == 3
+        if kind == "hard":
+            b, c, h, w = shape
+            assert ours[1][0] == ("tensor", (b, c, h, w), "torch.float32")
+            assert ours[1][1] == ("tensor", (), "torch.float32")
+            assert ours[1][2] == ("tensor", (b * h * w,), "torch.int64")
+        if ref is not None:
+            assert ours == ref, f"{kind} {shape} training={training}: ours {ours} vs reference {ref}"
+            assert keys == ref_keys
