@@ -71,3 +71,30 @@ def test_state_dict_keys_match_reference():
     meta, _ = load_golden("soft_specific_ne3072_d64_n300")
     sq = VectorQuantizer(3072, 64, 0.25, 0.0, True, True, [64, 64])
     assert sorted(sq.state_dict().keys()) == meta["state_dict_keys"]
+
+
+def test_every_entry_point_validates_its_arguments_on_the_host(lib):
+    """Null pointers / out-of-range scalars are rejected before anything is launched: a non-zero return code and a
+    message from mtvq_last_error(), never a crash and never a CUDA call (this box has no GPU).  ABI error behaviour:
+    include/medtok_vq.h ("functions return 0 or an error code; no exception crosses the boundary")."""
+    from medtok_b200 import _lib
+    host_only = {"mtvq_abi_version", "mtvq_last_error", "mtvq_workspace_bytes", "mtvq_stats_len", "mtvq_hard_route",
+                 "mtvq_debug_set_hard_route", "mtvq_debug_get_hard_route", "mtvq_debug_set_soft_route",
+                 "mtvq_debug_set_events", "mtvq_debug_set_trace", "mtvq_debug_coarse_scores"}
+    checked = 0
+    for name, (_res, args) in _lib._SIGNATURES.items():
+        if name in host_only:
+            continue
+        vals = []
+        for a in args:
+            if a is ctypes.c_void_p or (hasattr(a, "_type_") and not isinstance(a._type_, str)):
+                vals.append(None)                               # every pointer null
+            elif a is ctypes.c_double:
+                vals.append(0.5)
+            else:
+                vals.append(64)                                 # d = k = n = topk = 64, norm_mode / flags = 64
+        rc = getattr(lib, name)(*vals)
+        assert rc != 0, f"{name} accepted null pointers"
+        assert len(lib.mtvq_last_error()) > 0, f"{name} failed without a message"
+        checked += 1
+    assert checked >= 14
